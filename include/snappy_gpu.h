@@ -1,0 +1,222 @@
+/*
+ * snappy_gpu.h -- C ABI of libsnappygpu.so, the B200-native replacement for the inside of
+ * SnappyData's partial-aggregation stage:
+ *
+ *     ColumnTableScan -> [FilterExec / ProjectExec] -> SnappyHashAggregateExec(Partial)
+ *
+ * These entry points are what a JNI shim on the reference side binds (INTEGRATION.md shows it).
+ * Plain pointers and sizes only; no C++ / torch types.  Every function returns 0 on success and a
+ * non-zero sd_status otherwise; sd_last_error() then holds a thread-local message.  There is NO
+ * CPU fallback: a plan or buffer the GPU path cannot execute is an error (the reference's
+ * CodegenSparkFallback, core/.../execution/CodegenSparkFallback.scala:48-134, is deliberately not
+ * mirrored; BASELINE.json north_star).
+ *
+ * Citations are to /root/reference; enc = encoders/src/main/scala/org/apache/spark/sql/execution/
+ * columnar/encoding, core = core/src/main/scala/org/apache/spark/sql.
+ *
+ * Threading: one thread drives one sd_plan from create to destroy; distinct plans may
+ * be driven concurrently from distinct threads; an sd_store may be shared by plans (reads only while
+ * plans scan it).
+ */
+#ifndef SNAPPY_GPU_H
+#define SNAPPY_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+typedef enum sd_status {
+  SD_OK = 0,
+  SD_ERR_INVALID = 1,      /* malformed descriptor / buffer                         */
+  SD_ERR_UNSUPPORTED = 2,  /* plan shape or encoding the GPU path does not execute  */
+  SD_ERR_CUDA = 3,         /* CUDA runtime / driver / NVRTC failure                 */
+  SD_ERR_OVERFLOW = 4,     /* caller's output buffer too small (outLen = needed)    */
+  SD_ERR_STATE = 5         /* call sequence violation                               */
+} sd_status;
+
+/* SQL types of scan columns / expression nodes (Catalyst DataType of the attribute;
+ * core/execution/columnar/ColumnTableScan.scala:684-760 picks the decoder read method from it). */
+typedef enum sd_type {
+  SD_BOOLEAN = 1, SD_BYTE = 2, SD_SHORT = 3, SD_INT = 4, SD_LONG = 5, SD_FLOAT = 6, SD_DOUBLE = 7,
+  SD_DATE = 8,       /* int32 days since epoch       */
+  SD_TIMESTAMP = 9,  /* int64 microseconds           */
+  SD_STRING = 10,    /* UTF8String                   */
+  SD_DECIMAL = 11    /* precision <= 18, int64 unscaled (enc/Uncompressed.scala:95-98) */
+} sd_type;
+
+/* One projected scan column (ColumnTableScan.output attribute). */
+typedef struct sd_column {
+  int32_t type;           /* sd_type                                                  */
+  int32_t nullable;       /* field.nullable: selects Nullable vs NotNull decoder
+                             (enc/ColumnEncoding.scala:817-822)                       */
+  int32_t table_ordinal;  /* 0-based column of the table (ColumnFormatKey.columnIndex-1) */
+  int32_t scale;          /* SD_DECIMAL scale; else 0                                 */
+} sd_column;
+
+/* Expression tree, flattened; children always precede parents.  Mirrors the Catalyst trees that
+ * FilterExec / ProjectExec / the aggregate functions' children hold.
+ * Semantics restated from Spark 2.1.1: SQL three-valued logic, NULL in any
+ * operand of arithmetic/comparison => NULL, x / 0 => NULL, integral arithmetic wraps,
+ * FLOAT/DOUBLE comparisons use the NaN-safe total order (NaN == NaN, NaN greatest, -0.0 == 0.0),
+ * strings compare as unsigned bytes. */
+typedef enum sd_op {
+  SD_OP_COL = 1,        /* a = index into sd_plan_desc.cols                      */
+  SD_OP_LIT = 2,        /* a = literal slot (runtime value, cf. ParamLiteral,
+                           core/catalyst/expressions/ParamLiteral.scala:43-110)  */
+  SD_OP_ADD = 10, SD_OP_SUB = 11, SD_OP_MUL = 12, SD_OP_DIV = 13, SD_OP_NEG = 14,
+  SD_OP_CAST = 15,      /* a -> node type                                        */
+  SD_OP_EQ = 20, SD_OP_NE = 21, SD_OP_LT = 22, SD_OP_LE = 23, SD_OP_GT = 24, SD_OP_GE = 25,
+  SD_OP_AND = 30, SD_OP_OR = 31, SD_OP_NOT = 32,
+  SD_OP_ISNULL = 33, SD_OP_ISNOTNULL = 34,
+  SD_OP_IN = 35,        /* a = expr, b = first literal slot, c = number of literals */
+  SD_OP_STARTSWITH = 36 /* a = string expr, b = literal node                     */
+} sd_op;
+
+typedef struct sd_expr {
+  int32_t op;    /* sd_op                     */
+  int32_t type;  /* sd_type of the result     */
+  int32_t a, b, c;
+} sd_expr;
+
+/* Aggregate functions (Spark DeclarativeAggregate) and their partial
+ * buffer fields, in the order SnappyHashAggregateExec lays them out
+ * (core/execution/aggregate/SnappyHashAggregateExec.scala:174-210,456-471):
+ *   COUNT_STAR / COUNT : [count LONG]
+ *   SUM                : [sum LONG (integral input) | DOUBLE (float/double input)]   (nullable)
+ *   AVG                : [sum DOUBLE, count LONG]
+ *   MIN / MAX          : [value of the input type]                                   (nullable) */
+typedef enum sd_agg_fn {
+  SD_AGG_COUNT_STAR = 1, SD_AGG_COUNT = 2, SD_AGG_SUM = 3, SD_AGG_AVG = 4, SD_AGG_MIN = 5, SD_AGG_MAX = 6
+} sd_agg_fn;
+
+typedef struct sd_agg {
+  int32_t fn;    /* sd_agg_fn                               */
+  int32_t expr;  /* input expression node; -1 for COUNT(*)  */
+} sd_agg;
+
+/* The fused plan: scan columns -> filter -> (group keys, aggregates) | projection. */
+typedef struct sd_plan_desc {
+  int32_t abi_version;          /* SD_ABI_VERSION                                        */
+  int32_t ncols;   const sd_column* cols;
+  int32_t nexprs;  const sd_expr* exprs;
+  int32_t filter;               /* root node of the FilterExec condition, or -1          */
+  int32_t nkeys;   const int32_t* keys;    /* grouping expressions (node indexes)        */
+  int32_t naggs;   const sd_agg* aggs;
+  int32_t nproj;   const int32_t* proj;    /* naggs == 0 && nkeys == 0: output columns   */
+  int32_t nliterals; const int32_t* literal_types;   /* sd_type per literal slot         */
+  int32_t flags;                /* reserved, 0                                           */
+} sd_plan_desc;
+
+typedef struct sd_literal {
+  int32_t type;      /* sd_type                              */
+  int32_t is_null;
+  int64_t i;         /* integral / date / timestamp / boolean / decimal-unscaled value */
+  double  d;         /* FLOAT / DOUBLE value                 */
+  const char* s;     /* STRING bytes (not NUL terminated)    */
+  int32_t slen;
+  int32_t pad_;
+} sd_literal;
+
+/* One column batch as ColumnBatchIterator serves it to the generated loop
+ * (core/execution/columnar/ColumnBatchIterator.scala:53-231): per projected column the value
+ * buffer (getColumnLob) and up to two update deltas (getUpdatedColumnDecoder, depth 0 and 1), the
+ * delete mask (getDeletedColumnDecoder), the stats row (next()), ids.  Arrays are indexed like
+ * sd_plan_desc.cols.  Buffers may be heap or direct memory; the library has finished reading (or
+ * copied) them when sd_batch_submit returns (ownership rule).  A buffer whose first
+ * int32 is negative is a compressed envelope (encoders/.../store/CompressionUtils.scala:53-61). */
+typedef struct sd_batch {
+  int32_t num_rows;
+  int32_t ncols;
+  const void* const* col_bufs;  const int64_t* col_lens;
+  const void* const* delta0;    const int64_t* delta0_lens;   /* may be NULL; entries may be NULL */
+  const void* const* delta1;    const int64_t* delta1_lens;
+  const void* delete_buf;       int64_t delete_len;           /* may be NULL                      */
+  const void* stats_row;        int64_t stats_len;            /* may be NULL (no batch skipping)  */
+  int32_t stats_ncols;          /* number of table columns described by the stats row            */
+  int32_t bucket_id;
+  int64_t batch_id;
+} sd_batch;
+
+typedef struct sd_plan sd_plan;
+typedef struct sd_store sd_store;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+int sd_init(int device);                       /* bind the calling thread's plans to a GPU          */
+int sd_device_count(int* out);
+const char* sd_last_error(void);               /* thread-local, valid until the next failing call   */
+const char* sd_version(void);
+
+/* ---- plan (one per Spark task / partition; ColumnTableScan.doProduce + SnappyHashAggregateExec
+ *      doProduce/doConsume fused, core/.../ColumnTableScan.scala:186-672,
+ *      core/.../aggregate/SnappyHashAggregateExec.scala:240-263) --------------------------------- */
+int sd_plan_create(const sd_plan_desc* desc, sd_plan** out);
+int sd_plan_set_literals(sd_plan* p, const sd_literal* vals, int32_t n);
+/* scan one batch from host buffers (copied to the device inside the call) */
+int sd_batch_submit(sd_plan* p, const sd_batch* b);
+/* row-buffer rows of the hybrid scan (core/execution/row/RowFormatScanRDD.scala; consumed through the
+ * same loop with batch size 1, ColumnTableScan.scala:572-588): nrows UnsafeRows of the plan's
+ * scan columns, each prefixed by its int64 size */
+int sd_rows_submit(sd_plan* p, const void* rows, int64_t len, int32_t nrows);
+/* finish the partition: run what is pending, emit partial-aggregate rows (or projected rows) as
+ * repeated [int64 sizeInBytes][UnsafeRow(group keys ++ aggregate buffers)].  On SD_ERR_OVERFLOW
+ * *out_len is the size needed and the call may be repeated. */
+int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
+/* make the handle reusable for another execution of the same (cached) plan */
+int sd_plan_reset(sd_plan* p);
+/* SQLMetrics of the two operators (ColumnTableScan.scala:111-127, SnappyHashAggregateExec.scala:132-137):
+ * [0] numOutputRows (aggregate) [1] numRowsBuffer [2] columnBatchesSeen [3] updatedColumnCount
+ * [4] deletedBatchCount [5] columnBatchesSkipped [6] aggTime (device ns) [7] kernel launches
+ * [8] rows scanned [9] algorithmic bytes scanned [10] host->device bytes [11] scan numOutputRows */
+#define SD_NUM_METRICS 12
+int sd_plan_metrics(sd_plan* p, int64_t out[SD_NUM_METRICS]);
+/* run the plan's kernels on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's */
+int sd_plan_set_stream(sd_plan* p, void* cuda_stream);
+/* kernel variant actually selected for the plan ("aot:<signature>" | "jit:<signature>") */
+const char* sd_plan_kernel_name(sd_plan* p);
+void sd_plan_destroy(sd_plan* p);
+
+/* ---- device-resident column store (residency policy of this engine; the reference keeps batches
+ *      in region memory and faults them in per scan, ColumnBatchIterator.scala:179-223) ---------- */
+int sd_store_create(int device, sd_store** out);
+/* upload one batch; b->col_bufs is indexed by TABLE column here (ncols = table width; NULL entries
+ * for columns never scanned); delta arrays likewise */
+int sd_store_put_batch(sd_store* s, const sd_batch* b);
+int sd_store_num_batches(sd_store* s, int64_t* out);
+int sd_store_bytes(sd_store* s, int64_t* out);
+/* scan every resident batch of the given buckets (NULL/0 = all) with plan p: stats-row skipping on
+ * the host, then the fused kernels over the resident bytes; results are collected by sd_plan_finish */
+int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32_t nbuckets);
+void sd_store_destroy(sd_store* s);
+
+/* ---- final merge (SnappyHashAggregateExec(Final) / CollectAggregateExec.executeCollect,
+ *      core/execution/aggregate/CollectAggregateExec.scala:67-121): merges partial rows of all
+ *      partitions (sums add, counts add, min/max combine) and evaluates results (avg = sum/count).
+ *      Host-side: payload is a handful of rows.  Output rows: keys ++ one result per aggregate. --- */
+int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len,
+                   void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
+
+/* ---- export of the dense partial table for an on-device exchange (NCCL all-reduce over NVLink of
+ *      per-GPU partials).  Writes nslots int64/double words per group into dev_out
+ *      (device pointer) on the plan's stream.  Only for plans without string/hash keys. ---------- */
+int sd_plan_partials_layout(sd_plan* p, int32_t* ngroups, int32_t* nslots, int32_t* slot_is_f64);
+int sd_plan_export_partials(sd_plan* p, void* dev_out, int64_t cap_bytes);
+int sd_plan_import_partials(sd_plan* p, const void* dev_in, int64_t bytes);
+
+/* ---- synthetic lineitem tables generated on the device straight into a store (bench/test
+ *      utility; byte-identical to snappydata_b200/lineitem.py; not part of the reference boundary) */
+int sdx_store_gen_lineitem(sd_store* s, int64_t first_row, int64_t nrows, int32_t rows_per_batch,
+                           int32_t nbuckets, uint64_t seed, int32_t column_mask);
+/* copy a resident buffer back to the host (tests: device generator == host generator) */
+int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, void* out, int64_t cap,
+                         int64_t* out_len);
+int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id,
+                         int64_t* batch_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPPY_GPU_H */

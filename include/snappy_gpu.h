@@ -181,7 +181,9 @@ void sd_plan_destroy(sd_plan* p);
 
 /* ---- device-resident column store (residency policy of this engine; the reference keeps batches
  *      in region memory and faults them in per scan, ColumnBatchIterator.scala:179-223) ---------- */
-int sd_store_create(int device, sd_store** out);
+/* schema = the table's columns in table order (ColumnFormatRelation.schema); type and nullability
+ * select the decoders exactly as field.dataType / field.nullable do in the reference */
+int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store** out);
 /* upload one batch; b->col_bufs is indexed by TABLE column here (ncols = table width; NULL entries
  * for columns never scanned); delta arrays likewise */
 int sd_store_put_batch(sd_store* s, const sd_batch* b);

@@ -195,7 +195,7 @@ class Api:
         self.version = fn("version", C.c_char_p, required=False)
         self.plan_set_stream = fn("plan_set_stream", C.c_int, vp, vp, required=False)
         self.plan_kernel_name = fn("plan_kernel_name", C.c_char_p, vp, required=False)
-        self.store_create = fn("store_create", C.c_int, C.c_int, C.POINTER(vp), required=False)
+        self.store_create = fn("store_create", C.c_int, C.c_int, i32, C.POINTER(sd_column), C.POINTER(vp), required=False)
         self.store_put_batch = fn("store_put_batch", C.c_int, vp, C.POINTER(sd_batch), required=False)
         self.store_num_batches = fn("store_num_batches", C.c_int, vp, C.POINTER(i64), required=False)
         self.store_bytes = fn("store_bytes", C.c_int, vp, C.POINTER(i64), required=False)
@@ -404,10 +404,15 @@ def final_merge(api: Api, desc: PlanDesc, partial_raw: bytes) -> List[List[objec
 class Store:
     """Device-resident column store handle (product only)."""
 
-    def __init__(self, api: Api, device: int = 0):
+    def __init__(self, api: Api, schema, device: int = 0):
+        """schema: [(SqlType, nullable)] per table column, in table order."""
         self.api = api
+        self.schema = [(SqlType(t), bool(n)) for t, n in schema]
+        arr = (sd_column * max(1, len(self.schema)))()
+        for i, (t, n) in enumerate(self.schema):
+            arr[i] = sd_column(int(t), int(n), i, 0)
         h = C.c_void_p()
-        api.check(api.store_create(device, C.byref(h)))
+        api.check(api.store_create(device, len(self.schema), arr, C.byref(h)))
         self.h = h
 
     def put(self, batch: ColumnBatch):

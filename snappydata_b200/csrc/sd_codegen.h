@@ -1,0 +1,77 @@
+// sd_codegen.h -- plan analysis and generation of the per-plan PLAN struct for sd_kernels.cuh.
+#ifndef SD_CODEGEN_H
+#define SD_CODEGEN_H
+
+#include <string>
+#include <vector>
+
+#include "../../include/snappy_gpu.h"
+#include "sd_device.h"
+
+namespace sd {
+
+enum TableKind { TABLE_TRUTH = 0, TABLE_KEYMAP = 1 };
+
+// A per-batch lookup table indexed by a STRING column's dictionary code.
+struct TableSpec {
+  int kind;   // TableKind
+  int col;    // scan column
+  int node;   // TABLE_TRUTH: the predicate node evaluated per dictionary entry
+  int key;    // TABLE_KEYMAP: index into keys
+};
+
+enum SlotGate { GATE_VALUE = 0, GATE_NONNULL_COUNT = 1, GATE_ONE = 2 };
+
+struct SlotSpec {
+  int op;     // SLOT_*
+  int node;   // input expression (-1: none)
+  int gate;   // SlotGate
+};
+
+// how an aggregate's buffer fields map to slots
+struct AggMap {
+  int fn;
+  int value_slot;   // SUM/AVG sum, MIN/MAX value, COUNT count
+  int count_slot;   // AVG count; SUM/MIN/MAX non-null count when the buffer is nullable (-1 otherwise)
+  int in_type;      // sd_type of the input
+  int buf_type;     // sd_type of the (first) buffer field
+  int buf_nullable;
+};
+
+struct PlanSpec {
+  // deep copy of the descriptor
+  std::vector<sd_column> cols;
+  std::vector<sd_expr> exprs;
+  std::vector<int32_t> keys;
+  std::vector<sd_agg> aggs;
+  std::vector<int32_t> proj;
+  std::vector<int32_t> literal_types;
+  int filter = -1;
+  // analysis
+  std::vector<int> expr_nullable;
+  std::vector<int> kinds;            // K_* per scan column
+  std::vector<TableSpec> tables;
+  std::vector<SlotSpec> slots;
+  std::vector<AggMap> agg_map;
+  int rows_slot = -1;                // COUNT(*)-like slot that tells which groups exist
+  int mode = 0;                      // MODE_NOKEY | MODE_GROUPS
+  std::string signature;             // canonical text of everything the generated code depends on
+  std::string struct_name;           // Plan_<hash of signature>
+  std::string source;                // the generated PLAN struct (CUDA C++)
+  sd_plan_desc desc_view() const;    // a descriptor pointing into the vectors above
+};
+
+// Analyse + generate.  Returns SD_OK or an sd_status with `err` set.
+int analyze_plan(const sd_plan_desc* desc, PlanSpec& out, std::string& err);
+
+// Host evaluation of a string predicate node for one dictionary entry (used to fill truth tables):
+// returns 0 FALSE, 1 TRUE, 2 NULL.  `s == nullptr` means the NULL code.
+int eval_string_predicate(const PlanSpec& p, int node, const char* s, int slen, const sd_literal* lits);
+
+int sum_buffer_type(int t);
+bool type_is_integral(int t);
+bool type_is_fp(int t);
+int kind_of_type(int t);
+
+}  // namespace sd
+#endif

@@ -1,0 +1,121 @@
+// sd_device.h -- structures shared by the host engine and the device kernels.
+// Self-contained (no std headers) so that the NVRTC-compiled plan kernels can include it as text.
+#ifndef SD_DEVICE_H
+#define SD_DEVICE_H
+
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
+#include <stdint.h>
+#endif
+
+namespace sd {
+
+// ---- column encodings as the kernels see them (enc/ColumnEncoding.scala:766-773) -------------
+enum : int32_t { ENC_UNCOMPRESSED = 0, ENC_RUN_LENGTH = 1, ENC_DICTIONARY = 2, ENC_BIG_DICTIONARY = 3, ENC_BOOLEAN_BITSET = 4 };
+
+// ---- register value kinds of a scan column ---------------------------------------------------
+// K_CODE: a STRING column travels through the kernel as its per-batch dictionary index ("code");
+// predicates on it are per-batch truth tables and group keys per-batch code->group maps, both
+// prepared on the host from the (tiny) dictionaries -- the reference's own dictionary-array
+// shortcut (SnappyHashAggregateExec.scala:1340-1369) taken to its conclusion.
+enum : int32_t { K_I8 = 0, K_I16 = 1, K_I32 = 2, K_I64 = 3, K_F32 = 4, K_F64 = 5, K_BOOL = 6, K_CODE = 7 };
+
+// ---- tiling ----------------------------------------------------------------------------------
+// A CTA of THREADS threads processes tiles of THREADS*RPT rows; thread t owns the row pairs
+// tile + u*2*THREADS + 2*t + {0,1}, u < RPT/2, so that every per-column load instruction is a fully
+// coalesced 16/8/4/2-byte-per-lane vector load.  A work item ("chunk") is CHUNK_TILES tiles of one
+// batch.
+constexpr int THREADS = 256;
+constexpr int RPT = 4;                        // rows per thread per tile
+constexpr int TILE_ROWS = THREADS * RPT;      // 1024
+constexpr int CHUNK_TILES = 8;
+constexpr int CHUNK_ROWS = TILE_ROWS * CHUNK_TILES;   // 8192
+constexpr int TILE_WORDS = TILE_ROWS / 64;    // 16 null words per tile
+
+// bytes of TileSmem<PLAN> for a plan with nc scan columns (kept in sync with sd_kernels.cuh)
+constexpr int tile_smem_bytes(int nc) { return (TILE_ROWS / 32) * 4 + (nc > 0 ? nc : 1) * ((TILE_ROWS / 32) * 4 + TILE_WORDS * 4 + 16); }
+
+constexpr int MAX_LITERALS = 64;
+constexpr int MAX_KEYS = 4;
+
+// One update delta of one column (enc/ColumnDeltaEncoder.scala:300-331): ascending positions +
+// values in the column's normal encoding; null bits index the relative entry.
+struct DevDelta {
+  const int32_t* positions;   // [n] ascending base-row ordinals
+  const uint8_t* data;        // first encoded value / index
+  const uint64_t* nulls;      // relative null words (8-byte aligned copy) or nullptr
+  const uint8_t* dict;        // int32/int64 dictionary values (ENC_DICTIONARY of INT/LONG) or code map
+  int32_t n;
+  int32_t nwords;
+  int32_t enc;
+  int32_t dict_n;
+};
+
+// One scan column of one batch.
+struct DevCol {
+  const uint8_t* data;        // first encoded value (uncompressed), first index (dictionary),
+                              // first word (bitset) or first run (run length); 128-byte aligned
+  const uint64_t* nulls;      // null words (8-byte aligned copy), or nullptr when the batch has none
+  const int32_t* tile_nulls;  // [num_tiles] nulls before each tile start (host-computed), or nullptr
+  const uint8_t* dict;        // int32/int64 dictionary values; for RLE strings: int32 code per run
+  const int32_t* run_ends;    // RLE: [nruns] exclusive end (in stored-value index) of each run
+  const DevDelta* delta0;     // depth-0 delta (wins on equal position) or nullptr
+  const DevDelta* delta1;     // depth-1 delta or nullptr
+  int32_t nwords;             // number of null words (trailing zero words are trimmed)
+  int32_t enc;
+  int32_t dict_n;             // dictionary entries (NULL code == dict_n for nullable columns)
+  int32_t nruns;
+};
+
+template <int NC>
+struct DevBatch {
+  int32_t num_rows;
+  int32_t num_deletes;
+  const int32_t* deletes;     // ascending deleted ordinals or nullptr (enc/ColumnDeleteEncoder.scala:101-134)
+  const uint8_t* aux;         // per-plan per-batch tables: key code->group maps, predicate truth tables
+  int32_t flags;              // bit0: every column takes the vector fast path
+  int32_t pad_;
+  DevCol cols[NC > 0 ? NC : 1];
+};
+constexpr int32_t BATCH_ALL_FAST = 1;
+
+struct Literals {
+  int64_t i[MAX_LITERALS];
+  double d[MAX_LITERALS];
+  uint64_t nullmask;          // bit k: literal slot k is NULL
+};
+
+// aggregation strategy of a generated plan struct
+enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1 };
+
+// accumulator slot operations; every slot is 8 bytes
+enum : int32_t { SLOT_ADD_F64 = 0, SLOT_ADD_I64 = 1, SLOT_MIN_I64 = 2, SLOT_MAX_I64 = 3, SLOT_MIN_F64 = 4, SLOT_MAX_F64 = 5 };
+
+struct ScanArgs {
+  const void* batches;            // DevBatch<NC>[nbatches]
+  const int32_t* chunk_prefix;    // [nbatches + 1] cumulative chunk counts
+  int32_t nbatches;
+  int32_t total_chunks;
+  uint64_t* partials;             // [gridDim.x][ngroups * NSLOT] per-CTA partial tables
+  uint64_t* result;               // [ngroups * NSLOT] running result (combined into, not overwritten)
+  unsigned int* ticket;           // CTA completion counter (reset by the last CTA)
+  unsigned long long* counters;   // [0] rows scanned, [1] rows that passed the filter
+  int32_t ngroups;                // group slots of the private tables (1 without keys)
+  int32_t radix[MAX_KEYS];        // group index = ((g0 * radix[1] + g1) * radix[2] + g2) ...
+  // projection mode
+  uint8_t* out_rows;              // projected output (PROJECT mode)
+  unsigned long long* out_count;
+  int64_t out_cap;
+  Literals lits;
+};
+
+}  // namespace sd
+#endif

@@ -1,0 +1,1029 @@
+// sd_engine.cu -- plan handles: stats-row batch skipping, per-batch descriptor/table preparation,
+// kernel launch, partial-row emission, final merge.  Host-side counterpart of
+//   ColumnTableScan.doProduce batch loop        core/execution/columnar/ColumnTableScan.scala:518-599
+//   ColumnTableScan.generateStatPredicate       core/execution/columnar/ColumnTableScan.scala:820-963
+//   SnappyHashAggregateExec partial output      core/execution/aggregate/SnappyHashAggregateExec.scala:1148-1178
+//   CollectAggregateExec / final merge          core/execution/aggregate/CollectAggregateExec.scala:67-121
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "sd_host.h"
+
+using namespace sd;
+
+namespace {
+
+thread_local int t_device = 0;
+
+inline int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline int16_t rd_i16(const uint8_t* p) { int16_t v; memcpy(&v, p, 2); return v; }
+inline int64_t rd_i64(const uint8_t* p) { int64_t v; memcpy(&v, p, 8); return v; }
+inline double rd_f64(const uint8_t* p) { double v; memcpy(&v, p, 8); return v; }
+inline float rd_f32(const uint8_t* p) { float v; memcpy(&v, p, 4); return v; }
+
+// ---- host values (stats rows, partial rows) -------------------------------------------------------
+struct HVal {
+  bool isnull = false;
+  int64_t i = 0;
+  double d = 0;
+  std::string s;
+};
+
+int cmp_str(const std::string& a, const std::string& b) {
+  size_t n = std::min(a.size(), b.size());
+  int c = n ? memcmp(a.data(), b.data(), n) : 0;
+  return c ? c : (a.size() < b.size() ? -1 : (a.size() > b.size() ? 1 : 0));
+}
+int cmp_f64(double x, double y) {   // Utils.nanSafeCompareDoubles
+  const bool xn = std::isnan(x), yn = std::isnan(y);
+  if (xn || yn) return xn && yn ? 0 : (xn ? 1 : -1);
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+int cmp_hval(const HVal& a, const HVal& b, int t) {
+  if (t == SD_STRING) return cmp_str(a.s, b.s);
+  if (type_is_fp(t)) return cmp_f64(a.d, b.d);
+  return a.i < b.i ? -1 : (a.i > b.i ? 1 : 0);
+}
+
+// field `idx` of a Spark UnsafeRow with `nfields` fields
+bool unsafe_field(const uint8_t* row, int64_t len, int nfields, int idx, int type, HVal* out) {
+  const int64_t bits = ((nfields + 63) / 64) * 8;
+  if (idx < 0 || idx >= nfields || bits + 8 * (int64_t)nfields > len) return false;
+  *out = HVal();
+  if (row[idx >> 3] & (1u << (idx & 7))) { out->isnull = true; return true; }
+  const uint8_t* slot = row + bits + 8 * (int64_t)idx;
+  switch (type) {
+    case SD_STRING: {
+      const int64_t ol = rd_i64(slot);
+      const int64_t off = ol >> 32, ln = ol & 0xffffffff;
+      if (off < 0 || off + ln > len) return false;
+      out->s.assign(reinterpret_cast<const char*>(row + off), (size_t)ln);
+      break;
+    }
+    case SD_BOOLEAN: out->i = slot[0] != 0; break;
+    case SD_BYTE: out->i = (int8_t)slot[0]; break;
+    case SD_SHORT: out->i = rd_i16(slot); break;
+    case SD_INT: case SD_DATE: out->i = rd_i32(slot); break;
+    case SD_FLOAT: out->d = rd_f32(slot); break;
+    case SD_DOUBLE: out->d = rd_f64(slot); break;
+    default: out->i = rd_i64(slot); break;
+  }
+  return true;
+}
+
+void emit_unsafe_row(std::vector<uint8_t>& out, const std::vector<int>& types, const std::vector<HVal>& vals) {
+  const int n = (int)types.size();
+  const int64_t bits = ((n + 63) / 64) * 8, fixed = bits + 8 * (int64_t)n;
+  int64_t var = 0;
+  for (int i = 0; i < n; i++) if (types[i] == SD_STRING && !vals[i].isnull) var += ((int64_t)vals[i].s.size() + 7) & ~int64_t(7);
+  const int64_t sz = fixed + var;
+  const size_t base = out.size();
+  out.resize(base + 8 + sz, 0);
+  uint8_t* r = out.data() + base;
+  memcpy(r, &sz, 8);
+  r += 8;
+  int64_t voff = fixed;
+  for (int i = 0; i < n; i++) {
+    if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); continue; }
+    uint8_t* slot = r + bits + 8 * (int64_t)i;
+    switch (types[i]) {
+      case SD_STRING: {
+        const int64_t ol = (voff << 32) | (uint32_t)vals[i].s.size();
+        memcpy(slot, &ol, 8);
+        memcpy(r + voff, vals[i].s.data(), vals[i].s.size());
+        voff += ((int64_t)vals[i].s.size() + 7) & ~int64_t(7);
+        break;
+      }
+      case SD_BOOLEAN: slot[0] = vals[i].i != 0; break;
+      case SD_BYTE: { int8_t v = (int8_t)vals[i].i; memcpy(slot, &v, 1); break; }
+      case SD_SHORT: { int16_t v = (int16_t)vals[i].i; memcpy(slot, &v, 2); break; }
+      case SD_INT: case SD_DATE: { int32_t v = (int32_t)vals[i].i; memcpy(slot, &v, 4); break; }
+      case SD_FLOAT: { float v = (float)vals[i].d; memcpy(slot, &v, 4); break; }
+      case SD_DOUBLE: memcpy(slot, &vals[i].d, 8); break;
+      default: memcpy(slot, &vals[i].i, 8); break;
+    }
+  }
+}
+
+// ---- stats-row batch skipping (ColumnTableScan.generateStatPredicate, :820-963) -------------------
+struct Tri { bool isnull; bool v; };
+Tri tri_and(Tri a, Tri b) { if ((!a.isnull && !a.v) || (!b.isnull && !b.v)) return {false, false}; if (a.isnull || b.isnull) return {true, false}; return {false, true}; }
+Tri tri_or(Tri a, Tri b) { if ((!a.isnull && a.v) || (!b.isnull && b.v)) return {false, true}; if (a.isnull || b.isnull) return {true, false}; return {false, false}; }
+Tri tri_cmp(const HVal& a, const HVal& b, int t, bool le) {
+  if (a.isnull || b.isnull) return {true, false};
+  const int c = cmp_hval(a, b, t);
+  return {false, le ? c <= 0 : c < 0};
+}
+HVal lit_val(const sd_literal& l, int t) {
+  HVal v;
+  v.isnull = l.is_null != 0;
+  v.i = l.i;
+  v.d = t == SD_FLOAT ? (double)(float)l.d : l.d;
+  if (l.s && l.slen > 0) v.s.assign(l.s, (size_t)l.slen);
+  return v;
+}
+
+struct StatEval {
+  const PlanSpec& p;
+  const std::vector<sd_literal>& lits;
+  const uint8_t* stats; int64_t slen; int nfields; int num_rows;
+  bool stat(int ord, int which, int type, HVal* out) const {   // which: 0 lower, 1 upper, 2 nullCount
+    const int idx = 1 + 3 * ord + which;
+    return idx < nfields && unsafe_field(stats, slen, nfields, idx, which == 2 ? (int)SD_INT : type, out);
+  }
+  // true when a stats filter is defined for `node` (buildFilter.isDefinedAt)
+  bool eval(int node, Tri* out) const {
+    const sd_expr& e = p.exprs[node];
+    Tri l, r;
+    switch (e.op) {
+      case SD_OP_AND: {
+        const bool dl = eval(e.a, &l), dr = eval(e.b, &r);
+        if (!dl && !dr) return false;
+        *out = dl && dr ? tri_and(l, r) : (dl ? l : r);
+        return true;
+      }
+      case SD_OP_OR: {
+        const bool dl = eval(e.a, &l), dr = eval(e.b, &r);
+        if (!(dl && dr)) return false;
+        *out = tri_or(l, r);
+        return true;
+      }
+      case SD_OP_EQ: case SD_OP_LT: case SD_OP_LE: case SD_OP_GT: case SD_OP_GE: {
+        const sd_expr &ea = p.exprs[e.a], &eb = p.exprs[e.b];
+        const bool cl = ea.op == SD_OP_COL && eb.op == SD_OP_LIT, cr = eb.op == SD_OP_COL && ea.op == SD_OP_LIT;
+        if (!cl && !cr) return false;
+        const sd_expr& ec = cl ? ea : eb;
+        const sd_expr& el = cl ? eb : ea;
+        const int t = ec.type, ord = p.cols[ec.a].table_ordinal;
+        HVal lo, hi;
+        if (!stat(ord, 0, t, &lo) || !stat(ord, 1, t, &hi)) return false;
+        const HVal lit = lit_val(lits[el.a], t);
+        int op = e.op;
+        if (cr) op = op == SD_OP_LT ? SD_OP_GT : op == SD_OP_LE ? SD_OP_GE : op == SD_OP_GT ? SD_OP_LT : op == SD_OP_GE ? SD_OP_LE : op;
+        switch (op) {
+          case SD_OP_EQ: *out = tri_and(tri_cmp(lo, lit, t, true), tri_cmp(lit, hi, t, true)); break;
+          case SD_OP_LT: *out = tri_cmp(lo, lit, t, false); break;
+          case SD_OP_LE: *out = tri_cmp(lo, lit, t, true); break;
+          case SD_OP_GT: *out = tri_cmp(lit, hi, t, false); break;
+          default: *out = tri_cmp(lit, hi, t, true); break;
+        }
+        return true;
+      }
+      case SD_OP_IN: {
+        const sd_expr& ea = p.exprs[e.a];
+        if (ea.op != SD_OP_COL || e.c > 200 || e.c < 1) return false;
+        const int t = ea.type, ord = p.cols[ea.a].table_ordinal;
+        HVal lo, hi, mn, mx;
+        if (!stat(ord, 0, t, &lo) || !stat(ord, 1, t, &hi)) return false;
+        bool have = false;
+        for (int k = 0; k < e.c; k++) {   // Greatest / Least skip nulls
+          if (lits[e.b + k].is_null) continue;
+          const HVal v = lit_val(lits[e.b + k], t);
+          if (!have) { mn = mx = v; have = true; }
+          else { if (cmp_hval(v, mn, t) < 0) mn = v; if (cmp_hval(v, mx, t) > 0) mx = v; }
+        }
+        if (!have) mn.isnull = mx.isnull = true;
+        *out = tri_and(tri_cmp(lo, mx, t, true), tri_cmp(mn, hi, t, true));
+        return true;
+      }
+      case SD_OP_STARTSWITH: {   // StartsWithForStats (ColumnTableScan.scala:1028-1088); never NULL
+        const sd_expr &ea = p.exprs[e.a], &eb = p.exprs[e.b];
+        if (ea.op != SD_OP_COL || eb.op != SD_OP_LIT) return false;
+        const int ord = p.cols[ea.a].table_ordinal;
+        HVal lo, hi;
+        if (!stat(ord, 0, SD_STRING, &lo) || !stat(ord, 1, SD_STRING, &hi)) return false;
+        const sd_literal& L = lits[eb.a];
+        Tri r0 = {false, true};
+        if (!L.is_null) {
+          std::string pat(L.s ? L.s : "", (size_t)std::max(0, L.slen)), up = pat;
+          int last = (int)up.size() - 1;
+          while (last >= 0 && (uint8_t)up[last] == 0xff) last--;
+          if (last < 0 || lo.isnull) {
+            if (!hi.isnull) r0.v = cmp_str(pat, hi.s) <= 0;
+          } else {
+            up[last] = (char)((uint8_t)up[last] + 1);
+            r0.v = (hi.isnull || cmp_str(pat, hi.s) <= 0) && cmp_str(lo.s, up) < 0;
+          }
+        }
+        *out = r0;
+        return true;
+      }
+      case SD_OP_ISNULL: case SD_OP_ISNOTNULL: {
+        const sd_expr& ea = p.exprs[e.a];
+        if (ea.op != SD_OP_COL) return false;
+        HVal nc;
+        if (!stat(p.cols[ea.a].table_ordinal, 2, SD_INT, &nc)) return false;
+        *out = nc.isnull ? Tri{true, false} : Tri{false, e.op == SD_OP_ISNULL ? nc.i > 0 : num_rows > nc.i};
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+}  // namespace
+
+// =====================================================================================================
+struct sd_plan {
+  int device = 0;
+  PlanSpec spec;
+  KernelEntry kernel;
+  std::string kernel_name;
+  int max_ctas_per_sm = 0;
+  size_t last_smem = (size_t)-1;
+  int num_sms = 0;
+  int smem_optin = 0;
+  // literals
+  std::vector<sd_literal> lits;
+  std::vector<std::string> lit_strs;
+  bool lits_set = false;
+  // streams / events
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  // private store for sd_batch_submit / sd_rows_submit
+  sd_store* priv = nullptr;
+  // pending batches
+  struct Pending { const StoredBatch* sb; };
+  std::vector<Pending> pending;
+  int64_t pending_bytes = 0;
+  // device state
+  Arena scratch;                 // descriptors, aux tables (reset per execution)
+  uint64_t* d_result = nullptr;  // [result_cap]
+  uint64_t* d_partials = nullptr;
+  size_t partials_cap = 0;
+  unsigned int* d_ticket = nullptr;
+  unsigned long long* d_counters = nullptr;
+  size_t result_cap = 0;         // entries
+  int ngroups = 1;
+  int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
+  bool result_init = false;
+  // group key dictionaries (query-global ids per key column)
+  std::vector<std::unordered_map<std::string, int>> key_ids;
+  std::vector<std::vector<std::string>> key_vals;
+  std::vector<int> key_null_id;
+  // store-scan cache
+  struct ScanCache {
+    const sd_store* store = nullptr; int64_t version = -1; std::vector<int32_t> buckets; std::string lit_key;
+    const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
+    int64_t rows = 0, algo_bytes = 0, seen = 0, skipped = 0, updated_cols = 0, deleted_batches = 0;
+    int32_t radix[MAX_KEYS] = {1, 1, 1, 1}; int ngroups = 1; bool valid = false;
+  } cache;
+  Arena cache_arena;
+  int64_t metrics[SD_NUM_METRICS] = {0};
+  float agg_ms = 0;
+  bool have_timing = false;
+};
+
+namespace {
+
+std::string literal_key(const sd_plan* p) {
+  std::string k;
+  for (auto& l : p->lits) {
+    k.append(reinterpret_cast<const char*>(&l.is_null), 4);
+    k.append(reinterpret_cast<const char*>(&l.i), 8);
+    k.append(reinterpret_cast<const char*>(&l.d), 8);
+    if (l.s) k.append(l.s, (size_t)l.slen);
+    k.push_back('|');
+  }
+  return k;
+}
+
+int ensure_result(sd_plan* p, size_t entries) {
+  if (entries <= p->result_cap) return 0;
+  SD_CUDA(cudaSetDevice(p->device));
+  uint64_t* nr = nullptr;
+  SD_CUDA(cudaMalloc(&nr, entries * 8));
+  if (p->d_result) cudaFree(p->d_result);
+  p->d_result = nr;
+  p->result_cap = entries;
+  p->result_init = false;
+  return 0;
+}
+
+// (re)initialise the running result with the slot identities for `ngroups` groups
+int init_result(sd_plan* p, int ngroups) {
+  const int ns = (int)p->spec.slots.size();
+  const size_t ne = (size_t)ngroups * ns;
+  int rc = ensure_result(p, ne);
+  if (rc) return rc;
+  std::vector<uint64_t> h(ne);
+  for (size_t e = 0; e < ne; e++) {
+    const int op = p->spec.slots[e % ns].op;
+    h[e] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+         : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull : op == SLOT_MAX_F64 ? 0xfff0000000000000ull : 0ull;
+  }
+  SD_CUDA(cudaMemcpyAsync(p->d_result, h.data(), ne * 8, cudaMemcpyHostToDevice, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  p->result_init = true;
+  return 0;
+}
+
+// group id of one key value in the query-global dictionary of key k
+int key_id(sd_plan* p, int k, const std::string& s) {
+  auto it = p->key_ids[k].find(s);
+  if (it != p->key_ids[k].end()) return it->second;
+  const int id = (int)p->key_vals[k].size();
+  p->key_ids[k].emplace(s, id);
+  p->key_vals[k].push_back(s);
+  return id;
+}
+int key_null(sd_plan* p, int k) {
+  if (p->key_null_id[k] < 0) {
+    p->key_null_id[k] = (int)p->key_vals[k].size();
+    p->key_vals[k].push_back(std::string());   // placeholder; identified by key_null_id
+  }
+  return p->key_null_id[k];
+}
+
+// when dictionaries grew between launches of one execution the dense group table is re-indexed
+int remap_result(sd_plan* p, const int32_t* old_radix, int old_groups, const int32_t* new_radix, int new_groups) {
+  const int ns = (int)p->spec.slots.size(), nk = (int)p->spec.keys.size();
+  std::vector<uint64_t> oldh((size_t)old_groups * ns);
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  SD_CUDA(cudaMemcpy(oldh.data(), p->d_result, oldh.size() * 8, cudaMemcpyDeviceToHost));
+  int rc = init_result(p, new_groups);
+  if (rc) return rc;
+  std::vector<uint64_t> newh((size_t)new_groups * ns);
+  SD_CUDA(cudaMemcpy(newh.data(), p->d_result, newh.size() * 8, cudaMemcpyDeviceToHost));
+  for (int g = 0; g < old_groups; g++) {
+    int idx[MAX_KEYS], rem = g;
+    for (int k = nk - 1; k >= 0; k--) { idx[k] = rem % old_radix[k]; rem /= old_radix[k]; }
+    int ng = 0;
+    for (int k = 0; k < nk; k++) ng = ng * new_radix[k] + idx[k];
+    memcpy(&newh[(size_t)ng * ns], &oldh[(size_t)g * ns], (size_t)ns * 8);
+  }
+  SD_CUDA(cudaMemcpy(p->d_result, newh.data(), newh.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+struct BuiltScan {
+  const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
+  int64_t rows = 0, algo_bytes = 0, updated_cols = 0, deleted_batches = 0;
+};
+
+// Build the device descriptors + per-batch tables for a list of resident batches.
+int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& arena, BuiltScan* out) {
+  const PlanSpec& sp = p->spec;
+  const int nc = (int)sp.cols.size();
+  const size_t bstride = sizeof(DevBatch<1>) - sizeof(DevCol) + (size_t)std::max(nc, 1) * sizeof(DevCol);
+  const int nt = (int)sp.tables.size();
+  std::vector<uint8_t> hb(bstride * std::max<size_t>(list.size(), 1), 0);
+  std::vector<int32_t> prefix(list.size() + 1, 0);
+  std::vector<uint8_t> aux;
+  std::vector<size_t> aux_off(list.size(), 0);
+  for (size_t bi = 0; bi < list.size(); bi++) {
+    const StoredBatch& sb = *list[bi];
+    uint8_t* rec = hb.data() + bi * bstride;
+    DevBatch<1>* hdr = reinterpret_cast<DevBatch<1>*>(rec);
+    hdr->num_rows = sb.num_rows;
+    hdr->num_deletes = sb.num_deletes;
+    hdr->deletes = sb.dev_deletes;
+    bool all_fast = sb.dev_deletes == nullptr;
+    if (sb.dev_deletes) out->deleted_batches++;
+    DevCol* dc = reinterpret_cast<DevCol*>(rec + (sizeof(DevBatch<1>) - sizeof(DevCol)));
+    for (int c = 0; c < nc; c++) {
+      const int t = sb.positional ? c : sp.cols[c].table_ordinal;
+      if (t < 0 || t >= (int)sb.cols.size() || !sb.cols[t].present)
+        return set_error(SD_ERR_INVALID, "batch %lld: table column %d is not resident", (long long)sb.batch_id, t);
+      const StoredCol& sc = sb.cols[t];
+      if (!sc.unsupported.empty()) return set_error(SD_ERR_UNSUPPORTED, "column %d: %s", t, sc.unsupported.c_str());
+      dc[c] = sc.dev;
+      all_fast = all_fast && sc.fast;
+      out->algo_bytes += sc.algo_bytes;
+      if (sc.delta[0].present || sc.delta[1].present) out->updated_cols++;
+      for (int d = 0; d < 2; d++) if (sc.delta[d].present) out->algo_bytes += sc.delta[d].len;
+    }
+    if (sb.dev_deletes) out->algo_bytes += 12 + 4 * (int64_t)sb.num_deletes;
+    hdr->flags = all_fast ? BATCH_ALL_FAST : 0;
+    // per-batch tables: [int32 offset x nt][tables], every table indexed by the unified dictionary code
+    if (nt) {
+      while (aux.size() % 16) aux.push_back(0);
+      aux_off[bi] = aux.size();
+      const size_t base = aux.size();
+      aux.resize(base + 4 * (size_t)nt, 0);
+      for (int ti = 0; ti < nt; ti++) {
+        const TableSpec& ts = sp.tables[ti];
+        const StoredCol& sc = sb.cols[sb.positional ? ts.col : sp.cols[ts.col].table_ordinal];
+        const int n = sc.dev.dict_n;                         // NULL code
+        const int ncodes = std::max((int)sc.dict_strings.size(), n + 1);
+        while (aux.size() % 4) aux.push_back(0);
+        const int32_t off = (int32_t)(aux.size() - base);
+        memcpy(aux.data() + base + 4 * (size_t)ti, &off, 4);
+        if (ts.kind == TABLE_TRUTH) {
+          for (int code = 0; code < ncodes; code++) {
+            const bool isnull = code == n || code >= (int)sc.dict_strings.size();
+            const std::string* s = isnull ? nullptr : &sc.dict_strings[code];
+            aux.push_back((uint8_t)eval_string_predicate(sp, ts.node, s ? s->data() : nullptr, s ? (int)s->size() : 0, p->lits.data()));
+          }
+        } else {
+          for (int code = 0; code < ncodes; code++) {
+            const bool isnull = code == n || code >= (int)sc.dict_strings.size();
+            const int32_t id = isnull ? key_null(p, ts.key) : key_id(p, ts.key, sc.dict_strings[code]);
+            aux.insert(aux.end(), reinterpret_cast<const uint8_t*>(&id), reinterpret_cast<const uint8_t*>(&id) + 4);
+          }
+        }
+      }
+    }
+    out->rows += sb.num_rows;
+    prefix[bi + 1] = prefix[bi] + (sb.num_rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
+  }
+  // NULL key ids are only materialised when a nullable key column is present in the plan
+  uint8_t* d_aux = nullptr;
+  if (!aux.empty()) {
+    d_aux = arena.alloc(aux.size() + 16, 16);
+    if (!d_aux) return SD_ERR_CUDA;
+    SD_CUDA(cudaMemcpyAsync(d_aux, aux.data(), aux.size(), cudaMemcpyHostToDevice, p->stream));
+    for (size_t bi = 0; bi < list.size(); bi++) reinterpret_cast<DevBatch<1>*>(hb.data() + bi * bstride)->aux = d_aux + aux_off[bi];
+  }
+  uint8_t* d_b = arena.alloc(hb.size() + 16, 16);
+  uint8_t* d_p = arena.alloc(prefix.size() * 4 + 16, 16);
+  if (!d_b || !d_p) return SD_ERR_CUDA;
+  SD_CUDA(cudaMemcpyAsync(d_b, hb.data(), hb.size(), cudaMemcpyHostToDevice, p->stream));
+  SD_CUDA(cudaMemcpyAsync(d_p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));   // host vectors go out of scope
+  out->d_batches = d_b;
+  out->d_prefix = reinterpret_cast<const int32_t*>(d_p);
+  out->nbatches = (int)list.size();
+  out->total_chunks = prefix.back();
+  return 0;
+}
+
+int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks) {
+  if (nbatches == 0 || total_chunks == 0) return 0;
+  const PlanSpec& sp = p->spec;
+  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  // group radices from the current key dictionaries
+  int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
+  int ngroups = 1;
+  for (int k = 0; k < nk; k++) {
+    radix[k] = std::max<int>(1, (int)p->key_vals[k].size());
+    if ((int64_t)ngroups * radix[k] > (1 << 20)) return set_error(SD_ERR_UNSUPPORTED, "group cardinality too high for the dense group table");
+    ngroups *= radix[k];
+  }
+  const size_t ne = (size_t)ngroups * ns;
+  size_t smem = p->kernel.tile_smem + (sp.mode == MODE_GROUPS ? ne * THREADS * 8 : (size_t)std::max(ns, 1) * (THREADS / 32) * 8);
+  if ((int)smem > p->smem_optin)
+    return set_error(SD_ERR_UNSUPPORTED, "group-by needs %zu bytes of per-CTA shared memory for %d groups x %d slots (limit %d); "
+                     "high-cardinality hash aggregation is not in the GPU path yet", smem, ngroups, ns, p->smem_optin);
+  if (!p->result_init) {
+    int rc = init_result(p, ngroups);
+    if (rc) return rc;
+  } else if (ngroups != p->ngroups || memcmp(radix, p->radix, sizeof(radix)) != 0) {
+    int rc = remap_result(p, p->radix, p->ngroups, radix, ngroups);
+    if (rc) return rc;
+  }
+  p->ngroups = ngroups;
+  memcpy(p->radix, radix, sizeof(radix));
+
+  if (smem != p->last_smem) {
+    int occ = 0;
+    int rc = kernel_prepare(p->kernel, smem, &occ);
+    if (rc) return rc;
+    if (occ < 1) return set_error(SD_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    p->max_ctas_per_sm = occ;
+    p->last_smem = smem;
+  }
+  const int occ = p->max_ctas_per_sm;
+  const int grid = std::min(total_chunks, p->num_sms * occ);
+  if ((size_t)grid * ne > p->partials_cap) {
+    if (p->d_partials) cudaFree(p->d_partials);
+    p->partials_cap = (size_t)grid * ne * 2;
+    SD_CUDA(cudaMalloc(&p->d_partials, p->partials_cap * 8));
+  }
+  ScanArgs args;
+  memset(&args, 0, sizeof(args));
+  args.batches = d_batches;
+  args.chunk_prefix = d_prefix;
+  args.nbatches = nbatches;
+  args.total_chunks = total_chunks;
+  args.partials = p->d_partials;
+  args.result = p->d_result;
+  args.ticket = p->d_ticket;
+  args.counters = p->d_counters;
+  args.ngroups = ngroups;
+  memcpy(args.radix, radix, sizeof(radix));
+  for (size_t i = 0; i < p->lits.size(); i++) {
+    args.lits.i[i] = p->lits[i].i;
+    args.lits.d[i] = p->lits[i].d;
+    if (p->lits[i].is_null) args.lits.nullmask |= 1ull << i;
+  }
+  void* kargs[] = {&args};
+  if (!p->have_timing) SD_CUDA(cudaEventRecord(p->ev_start, p->stream));
+  { int rc = kernel_launch(p->kernel, grid, smem, p->stream, kargs); if (rc) return rc; }
+  SD_CUDA(cudaEventRecord(p->ev_stop, p->stream));
+  p->have_timing = true;
+  p->metrics[7]++;
+  return 0;
+}
+
+int flush_pending(sd_plan* p) {
+  if (p->pending.empty()) return 0;
+  std::vector<const StoredBatch*> list;
+  for (auto& x : p->pending) list.push_back(x.sb);
+  BuiltScan bs;
+  int rc = build_scan(p, list, p->scratch, &bs);
+  if (rc) return rc;
+  p->metrics[3] += bs.updated_cols;
+  p->metrics[4] += bs.deleted_batches;
+  p->metrics[9] += bs.algo_bytes;
+  rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks);
+  p->pending.clear();
+  p->pending_bytes = 0;
+  return rc;
+}
+
+bool batch_passes_stats(const sd_plan* p, const StoredBatch& sb) {
+  if (p->spec.filter < 0 || sb.stats.empty()) return true;
+  StatEval ev{p->spec, p->lits, sb.stats.data(), (int64_t)sb.stats.size(), 1 + 3 * sb.stats_ncols, sb.num_rows};
+  Tri r;
+  if (!ev.eval(p->spec.filter, &r)) return true;
+  return r.isnull || r.v;   // only a definite FALSE skips the batch (:948-957)
+}
+
+int ensure_private_store(sd_plan* p) {
+  if (p->priv) return 0;
+  // the private store's "table" is exactly the plan's scan columns
+  std::vector<sd_column> schema(p->spec.cols);
+  return sd_store_create(p->device, (int32_t)schema.size(), schema.data(), &p->priv);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sd_init(int device) {
+  int n = 0;
+  SD_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return set_error(SD_ERR_INVALID, "sd_init: device %d of %d", device, n);
+  SD_CUDA(cudaSetDevice(device));
+  t_device = device;
+  return 0;
+}
+int sd_device_count(int* out) { SD_CUDA(cudaGetDeviceCount(out)); return 0; }
+const char* sd_version(void) { return "snappydata_b200 0.1.0 (sm_100a)"; }
+
+int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
+  if (!out) return set_error(SD_ERR_INVALID, "sd_plan_create: null out");
+  std::unique_ptr<sd_plan> p(new sd_plan());
+  std::string err;
+  int rc = analyze_plan(desc, p->spec, err);
+  if (rc) return set_error(rc, "sd_plan_create: %s", err.c_str());
+  p->device = t_device;
+  SD_CUDA(cudaSetDevice(p->device));
+  // kernel: ahead-of-time compiled plan, else NVRTC
+  bool found = false;
+  for (auto& k : kernel_registry()) if (k.signature == p->spec.signature) { p->kernel = k; found = true; break; }
+  if (!found) {
+    KernelEntry k;
+    rc = jit_compile(p->spec, p->device, k);
+    if (rc) return rc;
+    kernel_registry().push_back(k);
+    p->kernel = k;
+  }
+  p->kernel_name = p->kernel.origin + ":" + p->spec.struct_name;
+  cudaDeviceProp prop;
+  SD_CUDA(cudaGetDeviceProperties(&prop, p->device));
+  p->num_sms = prop.multiProcessorCount;
+  p->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  SD_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->own_stream = true;
+  SD_CUDA(cudaEventCreate(&p->ev_start));
+  SD_CUDA(cudaEventCreate(&p->ev_stop));
+  SD_CUDA(cudaMalloc(&p->d_ticket, 64));
+  SD_CUDA(cudaMalloc(&p->d_counters, 64));
+  SD_CUDA(cudaMemset(p->d_ticket, 0, 64));
+  SD_CUDA(cudaMemset(p->d_counters, 0, 64));
+  p->scratch.device = p->device;
+  p->scratch.slab_bytes = size_t(8) << 20;
+  p->cache_arena.device = p->device;
+  p->cache_arena.slab_bytes = size_t(8) << 20;
+  const int nk = (int)p->spec.keys.size();
+  p->key_ids.resize(nk);
+  p->key_vals.resize(nk);
+  p->key_null_id.assign(nk, -1);
+  p->lits.resize(p->spec.literal_types.size());
+  p->lit_strs.resize(p->spec.literal_types.size());
+  for (size_t i = 0; i < p->lits.size(); i++) { memset(&p->lits[i], 0, sizeof(sd_literal)); p->lits[i].type = p->spec.literal_types[i]; }
+  p->lits_set = p->lits.empty();
+  *out = p.release();
+  return 0;
+}
+
+int sd_plan_set_literals(sd_plan* p, const sd_literal* vals, int32_t n) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  if (n != (int)p->lits.size()) return set_error(SD_ERR_INVALID, "sd_plan_set_literals: plan has %zu literal slots, got %d", p->lits.size(), n);
+  if (!p->pending.empty()) return set_error(SD_ERR_STATE, "sd_plan_set_literals: batches already submitted for this execution");
+  for (int i = 0; i < n; i++) {
+    p->lits[i] = vals[i];
+    p->lit_strs[i].assign(vals[i].s ? vals[i].s : "", vals[i].s ? (size_t)std::max(0, vals[i].slen) : 0);
+    p->lits[i].s = p->lit_strs[i].data();
+    p->lits[i].slen = (int32_t)p->lit_strs[i].size();
+  }
+  p->lits_set = true;
+  return 0;
+}
+
+int sd_plan_set_stream(sd_plan* p, void* cuda_stream) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  if (p->own_stream && p->stream) { cudaSetDevice(p->device); cudaStreamDestroy(p->stream); }
+  p->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  p->own_stream = false;
+  return 0;
+}
+
+const char* sd_plan_kernel_name(sd_plan* p) { return p ? p->kernel_name.c_str() : ""; }
+
+int sd_batch_submit(sd_plan* p, const sd_batch* b) {
+  if (!p || !b) return set_error(SD_ERR_INVALID, "sd_batch_submit: null argument");
+  if (!p->lits_set) return set_error(SD_ERR_STATE, "sd_batch_submit: literals not set");
+  if (b->ncols != (int)p->spec.cols.size()) return set_error(SD_ERR_INVALID, "sd_batch_submit: batch has %d columns, plan scans %zu", b->ncols, p->spec.cols.size());
+  SD_CUDA(cudaSetDevice(p->device));
+  p->metrics[2]++;   // columnBatchesSeen
+  // stats-row skipping before any byte moves (ColumnTableScan.scala:532-543)
+  if (b->stats_row && b->stats_len > 0 && p->spec.filter >= 0) {
+    StatEval ev{p->spec, p->lits, reinterpret_cast<const uint8_t*>(b->stats_row), b->stats_len, 1 + 3 * b->stats_ncols, b->num_rows};
+    Tri r;
+    if (ev.eval(p->spec.filter, &r) && !r.isnull && !r.v) { p->metrics[5]++; return 0; }
+  }
+  int rc = ensure_private_store(p);
+  if (rc) return rc;
+  const int64_t before = p->priv->h2d_bytes;
+  // the private store is indexed by scan column: buffers arrive in plan order already
+  sd_batch local = *b;
+  rc = store_put(p->priv, &local, nullptr);
+  if (rc) return rc;
+  p->metrics[10] += p->priv->h2d_bytes - before;
+  p->priv->batches.back()->positional = true;
+  const StoredBatch* sb = p->priv->batches.back().get();
+  // scan columns of the private store are positional: re-point table ordinals on the fly in build_scan
+  p->pending.push_back({sb});
+  p->pending_bytes += p->priv->h2d_bytes - before;
+  if (p->pending_bytes >= (int64_t(256) << 20)) return flush_pending(p);
+  return 0;
+}
+
+int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32_t nbuckets) {
+  if (!p || !s) return set_error(SD_ERR_INVALID, "sd_plan_scan_store: null argument");
+  if (!p->lits_set) return set_error(SD_ERR_STATE, "sd_plan_scan_store: literals not set");
+  if (s->device != p->device) return set_error(SD_ERR_INVALID, "store lives on device %d, plan on %d", s->device, p->device);
+  SD_CUDA(cudaSetDevice(p->device));
+  int rc = flush_pending(p);
+  if (rc) return rc;
+  for (auto& c : p->spec.cols) {
+    if (c.table_ordinal < 0 || c.table_ordinal >= (int)s->schema.size()) return set_error(SD_ERR_INVALID, "plan column ordinal %d outside the store schema", c.table_ordinal);
+    if (s->schema[c.table_ordinal].type != c.type || s->schema[c.table_ordinal].nullable != c.nullable)
+      return set_error(SD_ERR_INVALID, "plan column %d (type %d nullable %d) does not match the store schema (type %d nullable %d)", c.table_ordinal,
+                       c.type, c.nullable, s->schema[c.table_ordinal].type, s->schema[c.table_ordinal].nullable);
+  }
+  std::vector<int32_t> buckets(bucket_ids, bucket_ids + (bucket_ids ? nbuckets : 0));
+  const std::string lk = literal_key(p);
+  sd_plan::ScanCache& c = p->cache;
+  if (!(c.valid && c.store == s && c.version == s->version && c.buckets == buckets && c.lit_key == lk)) {
+    // (re)build: stats skipping + descriptors + tables, kept on the device for repeated executions
+    c.valid = false;
+    p->cache_arena.reset();
+    std::vector<const StoredBatch*> list;
+    int64_t seen = 0, skipped = 0;
+    for (auto& sbp : s->batches) {
+      const StoredBatch& sb = *sbp;
+      if (!buckets.empty() && std::find(buckets.begin(), buckets.end(), sb.bucket_id) == buckets.end()) continue;
+      seen++;
+      if (!batch_passes_stats(p, sb)) { skipped++; continue; }
+      list.push_back(&sb);
+    }
+    BuiltScan bs;
+    rc = build_scan(p, list, p->cache_arena, &bs);
+    if (rc) return rc;
+    c.store = s; c.version = s->version; c.buckets = buckets; c.lit_key = lk;
+    c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
+    c.rows = bs.rows; c.algo_bytes = bs.algo_bytes; c.seen = seen; c.skipped = skipped;
+    c.updated_cols = bs.updated_cols; c.deleted_batches = bs.deleted_batches;
+    c.valid = true;
+  }
+  p->metrics[2] += c.seen;
+  p->metrics[5] += c.skipped;
+  p->metrics[3] += c.updated_cols;
+  p->metrics[4] += c.deleted_batches;
+  p->metrics[9] += c.algo_bytes;
+  return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks);
+}
+
+int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+  if (!p || !out_len) return set_error(SD_ERR_INVALID, "sd_plan_finish: null argument");
+  SD_CUDA(cudaSetDevice(p->device));
+  int rc = flush_pending(p);
+  if (rc) return rc;
+  const PlanSpec& sp = p->spec;
+  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
+  const size_t ne = (size_t)p->ngroups * ns;
+  std::vector<uint64_t> h(ne);
+  unsigned long long counters[2] = {0, 0};
+  SD_CUDA(cudaMemcpyAsync(h.data(), p->d_result, ne * 8, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  if (p->have_timing) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms;
+  }
+  p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
+  p->metrics[8] = (int64_t)counters[0];
+  p->metrics[11] = (int64_t)counters[0];
+  // partial rows: UnsafeRow(group keys ++ aggregate buffers) (SnappyHashAggregateExec.scala:1148-1178)
+  std::vector<int> types;
+  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
+  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  std::vector<uint8_t> out;
+  int64_t nrows = 0;
+  for (int g = 0; g < p->ngroups; g++) {
+    const uint64_t* sv = &h[(size_t)g * ns];
+    if (nk > 0 && sv[sp.rows_slot] == 0) continue;   // group never seen
+    std::vector<HVal> vals;
+    int rem = g, idx[MAX_KEYS];
+    for (int k = nk - 1; k >= 0; k--) { idx[k] = rem % p->radix[k]; rem /= p->radix[k]; }
+    for (int k = 0; k < nk; k++) {
+      HVal v;
+      if (idx[k] == p->key_null_id[k]) v.isnull = true; else v.s = p->key_vals[k][idx[k]];
+      vals.push_back(v);
+    }
+    for (auto& m : sp.agg_map) {
+      HVal v;
+      const uint64_t raw = sv[m.value_slot];
+      const int64_t cnt = m.count_slot >= 0 ? (int64_t)sv[m.count_slot] : 1;
+      switch (m.fn) {
+        case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: v.i = (int64_t)raw; vals.push_back(v); break;
+        case SD_AGG_SUM:
+          if (m.buf_nullable && cnt == 0) v.isnull = true;
+          else if (m.buf_type == SD_DOUBLE) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
+          vals.push_back(v); break;
+        case SD_AGG_AVG: {
+          memcpy(&v.d, &raw, 8); vals.push_back(v);
+          HVal c; c.i = cnt; vals.push_back(c); break;
+        }
+        default:
+          if (m.buf_nullable && cnt == 0) v.isnull = true;
+          else if (type_is_fp(m.buf_type)) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
+          vals.push_back(v); break;
+      }
+    }
+    emit_unsafe_row(out, types, vals);
+    nrows++;
+  }
+  p->metrics[0] = nrows;
+  *out_len = (int64_t)out.size();
+  if (out_nrows) *out_nrows = nrows;
+  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", out.size());
+  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
+  return 0;
+}
+
+int sd_plan_reset(sd_plan* p) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  SD_CUDA(cudaSetDevice(p->device));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  p->pending.clear();
+  p->pending_bytes = 0;
+  p->result_init = false;
+  p->have_timing = false;
+  p->agg_ms = 0;
+  SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
+  memset(p->metrics, 0, sizeof(p->metrics));
+  p->scratch.reset();
+  if (p->priv) { p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0; }
+  // key dictionaries persist across executions of a cached plan only if the scan cache refers to them
+  if (!p->cache.valid) {
+    for (auto& m : p->key_ids) m.clear();
+    for (auto& v : p->key_vals) v.clear();
+    std::fill(p->key_null_id.begin(), p->key_null_id.end(), -1);
+  }
+  return 0;
+}
+
+int sd_plan_metrics(sd_plan* p, int64_t out[SD_NUM_METRICS]) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  memcpy(out, p->metrics, sizeof(p->metrics));
+  return 0;
+}
+
+void sd_plan_destroy(sd_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
+  if (p->ev_stop) cudaEventDestroy(p->ev_stop);
+  if (p->d_result) cudaFree(p->d_result);
+  if (p->d_partials) cudaFree(p->d_partials);
+  if (p->d_ticket) cudaFree(p->d_ticket);
+  if (p->d_counters) cudaFree(p->d_counters);
+  if (p->priv) sd_store_destroy(p->priv);
+  delete p;
+}
+
+// ---- dense partial table export/import for an on-device exchange (NCCL all-reduce) --------------
+int sd_plan_partials_layout(sd_plan* p, int32_t* ngroups, int32_t* nslots, int32_t* slot_is_f64) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  const int ns = (int)p->spec.slots.size();
+  if (ngroups) *ngroups = p->ngroups;
+  if (nslots) *nslots = ns;
+  if (slot_is_f64) for (int s = 0; s < ns; s++) { const int op = p->spec.slots[s].op; slot_is_f64[s] = op == SLOT_ADD_F64 ? 1 : (op == SLOT_ADD_I64 ? 0 : -1); }
+  return 0;
+}
+int sd_plan_export_partials(sd_plan* p, void* dev_out, int64_t cap_bytes) {
+  if (!p || !dev_out) return set_error(SD_ERR_INVALID, "null argument");
+  SD_CUDA(cudaSetDevice(p->device));
+  int rc = flush_pending(p);
+  if (rc) return rc;
+  if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
+  const size_t bytes = (size_t)p->ngroups * p->spec.slots.size() * 8;
+  if ((int64_t)bytes > cap_bytes) return set_error(SD_ERR_OVERFLOW, "export needs %zu bytes", bytes);
+  SD_CUDA(cudaMemcpyAsync(dev_out, p->d_result, bytes, cudaMemcpyDeviceToDevice, p->stream));
+  return 0;
+}
+int sd_plan_import_partials(sd_plan* p, const void* dev_in, int64_t bytes) {
+  if (!p || !dev_in) return set_error(SD_ERR_INVALID, "null argument");
+  SD_CUDA(cudaSetDevice(p->device));
+  const size_t want = (size_t)p->ngroups * p->spec.slots.size() * 8;
+  if ((size_t)bytes != want) return set_error(SD_ERR_INVALID, "import expects %zu bytes", want);
+  SD_CUDA(cudaMemcpyAsync(p->d_result, dev_in, want, cudaMemcpyDeviceToDevice, p->stream));
+  return 0;
+}
+
+// ---- row-buffer rows: the hybrid scan's first element (ColumnTableScan.scala:572-588) ----------------
+// nrows UnsafeRows of the plan's scan columns -> one Uncompressed/Dictionary pseudo-batch.
+int sd_rows_submit(sd_plan* p, const void* rows, int64_t len, int32_t nrows) {
+  if (!p || (!rows && nrows > 0)) return set_error(SD_ERR_INVALID, "sd_rows_submit: null argument");
+  if (nrows <= 0) return 0;
+  const int nc = (int)p->spec.cols.size();
+  std::vector<std::vector<uint8_t>> bufs(nc);
+  std::vector<std::vector<HVal>> colv(nc, std::vector<HVal>((size_t)nrows));
+  const uint8_t* r = reinterpret_cast<const uint8_t*>(rows);
+  int64_t pos = 0;
+  for (int i = 0; i < nrows; i++) {
+    if (pos + 8 > len) return set_error(SD_ERR_INVALID, "sd_rows_submit: truncated row stream");
+    const int64_t sz = rd_i64(r + pos);
+    if (sz < 0 || pos + 8 + sz > len) return set_error(SD_ERR_INVALID, "sd_rows_submit: bad row size");
+    for (int c = 0; c < nc; c++)
+      if (!unsafe_field(r + pos + 8, sz, nc, c, p->spec.cols[c].type, &colv[c][i])) return set_error(SD_ERR_INVALID, "sd_rows_submit: malformed UnsafeRow");
+    pos += 8 + sz;
+  }
+  for (int c = 0; c < nc; c++) {
+    const int t = p->spec.cols[c].type;
+    std::vector<uint64_t> nw(((size_t)nrows + 63) / 64, 0);
+    bool any_null = false;
+    for (int i = 0; i < nrows; i++) if (colv[c][i].isnull) { nw[i >> 6] |= 1ull << (i & 63); any_null = true; }
+    if (any_null && !p->spec.cols[c].nullable) return set_error(SD_ERR_INVALID, "NULL in NOT NULL column %d of the row buffer", c);
+    while (!nw.empty() && nw.back() == 0) nw.pop_back();
+    std::vector<uint8_t>& b = bufs[c];
+    auto put32 = [&](int32_t v) { b.insert(b.end(), reinterpret_cast<uint8_t*>(&v), reinterpret_cast<uint8_t*>(&v) + 4); };
+    if (t == SD_STRING) {   // first-seen dictionary
+      std::unordered_map<std::string, int> ids;
+      std::vector<std::string> vals;
+      std::vector<int32_t> idx;
+      for (int i = 0; i < nrows; i++) {
+        if (colv[c][i].isnull) continue;
+        auto it = ids.find(colv[c][i].s);
+        if (it == ids.end()) { it = ids.emplace(colv[c][i].s, (int)vals.size()).first; vals.push_back(colv[c][i].s); }
+        idx.push_back(it->second);
+      }
+      const bool big = vals.size() > 32767;
+      put32(big ? ENC_BIG_DICTIONARY : ENC_DICTIONARY);
+      put32((int32_t)nw.size() * 8);
+      b.insert(b.end(), reinterpret_cast<uint8_t*>(nw.data()), reinterpret_cast<uint8_t*>(nw.data()) + nw.size() * 8);
+      put32((int32_t)vals.size());
+      for (auto& s : vals) { put32((int32_t)s.size()); b.insert(b.end(), s.begin(), s.end()); }
+      for (int32_t x : idx) { if (big) put32(x); else { int16_t s16 = (int16_t)x; b.insert(b.end(), reinterpret_cast<uint8_t*>(&s16), reinterpret_cast<uint8_t*>(&s16) + 2); } }
+    } else {
+      put32(ENC_UNCOMPRESSED);
+      put32((int32_t)nw.size() * 8);
+      b.insert(b.end(), reinterpret_cast<uint8_t*>(nw.data()), reinterpret_cast<uint8_t*>(nw.data()) + nw.size() * 8);
+      for (int i = 0; i < nrows; i++) {
+        const HVal& v = colv[c][i];
+        if (v.isnull) continue;
+        switch (t) {
+          case SD_BOOLEAN: case SD_BYTE: b.push_back((uint8_t)v.i); break;
+          case SD_SHORT: { int16_t x = (int16_t)v.i; b.insert(b.end(), reinterpret_cast<uint8_t*>(&x), reinterpret_cast<uint8_t*>(&x) + 2); break; }
+          case SD_INT: case SD_DATE: put32((int32_t)v.i); break;
+          case SD_FLOAT: { float x = (float)v.d; b.insert(b.end(), reinterpret_cast<uint8_t*>(&x), reinterpret_cast<uint8_t*>(&x) + 4); break; }
+          case SD_DOUBLE: { double x = v.d; b.insert(b.end(), reinterpret_cast<uint8_t*>(&x), reinterpret_cast<uint8_t*>(&x) + 8); break; }
+          default: { int64_t x = v.i; b.insert(b.end(), reinterpret_cast<uint8_t*>(&x), reinterpret_cast<uint8_t*>(&x) + 8); break; }
+        }
+      }
+    }
+  }
+  std::vector<const void*> ptrs(nc);
+  std::vector<int64_t> lens(nc);
+  for (int c = 0; c < nc; c++) { ptrs[c] = bufs[c].data(); lens[c] = (int64_t)bufs[c].size(); }
+  sd_batch b;
+  memset(&b, 0, sizeof(b));
+  b.num_rows = nrows; b.ncols = nc; b.col_bufs = ptrs.data(); b.col_lens = lens.data(); b.bucket_id = -1; b.batch_id = -1;
+  const int64_t seen_before = p->metrics[2];
+  int rc = sd_batch_submit(p, &b);
+  p->metrics[2] = seen_before;       // the row buffer is not a column batch
+  if (!rc) p->metrics[1] += nrows;   // numRowsBuffer
+  return rc;
+}
+
+// ---- final merge (host; payload is a handful of rows) -------------------------------------------------
+int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                   int64_t* out_len, int64_t* out_nrows) {
+  PlanSpec sp;
+  std::string err;
+  int rc = analyze_plan(desc, sp, err);
+  if (rc) return set_error(rc, "sd_final_merge: %s", err.c_str());
+  const int nk = (int)sp.keys.size();
+  std::vector<int> types;
+  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
+  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  const int n = (int)types.size();
+  struct Group { std::vector<HVal> keys; std::vector<HVal> bufs; };
+  std::vector<Group> groups;   // insertion order
+  std::map<std::string, size_t> index;
+  const uint8_t* r = reinterpret_cast<const uint8_t*>(partial_rows);
+  int64_t pos = 0;
+  while (pos + 8 <= len) {
+    const int64_t sz = rd_i64(r + pos);
+    if (sz < 0 || pos + 8 + sz > len) return set_error(SD_ERR_INVALID, "sd_final_merge: bad row size");
+    std::vector<HVal> f((size_t)n);
+    for (int i = 0; i < n; i++) if (!unsafe_field(r + pos + 8, sz, n, i, types[i], &f[i])) return set_error(SD_ERR_INVALID, "sd_final_merge: malformed partial row");
+    std::string key;
+    for (int k = 0; k < nk; k++) {
+      key.push_back(f[k].isnull ? 'N' : 'V');
+      if (!f[k].isnull) {
+        if (types[k] == SD_STRING) { uint32_t l = (uint32_t)f[k].s.size(); key.append(reinterpret_cast<char*>(&l), 4); key.append(f[k].s); }
+        else if (type_is_fp(types[k])) { double d = f[k].d; if (d == 0.0) d = 0.0; if (std::isnan(d)) d = NAN; key.append(reinterpret_cast<char*>(&d), 8); }
+        else key.append(reinterpret_cast<const char*>(&f[k].i), 8);
+      }
+    }
+    auto it = index.find(key);
+    Group* g;
+    if (it == index.end()) {
+      index.emplace(key, groups.size());
+      groups.push_back(Group());
+      g = &groups.back();
+      g->keys.assign(f.begin(), f.begin() + nk);
+      g->bufs.assign(f.begin() + nk, f.end());
+    } else {
+      g = &groups[it->second];
+      int k = 0;
+      for (auto& m : sp.agg_map) {   // mergeExpressions of each function
+        HVal& b = g->bufs[k];
+        const HVal& in = f[nk + k];
+        switch (m.fn) {
+          case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: b.i += in.i; k++; break;
+          case SD_AGG_SUM:
+            if (!in.isnull) {
+              if (m.buf_type == SD_DOUBLE) b.d = (b.isnull ? 0.0 : b.d) + in.d;
+              else b.i = (int64_t)((uint64_t)(b.isnull ? 0 : b.i) + (uint64_t)in.i);
+              b.isnull = false;
+            }
+            k++; break;
+          case SD_AGG_AVG: b.d += in.d; g->bufs[k + 1].i += f[nk + k + 1].i; k += 2; break;
+          default:
+            if (!in.isnull) {
+              if (b.isnull) b = in;
+              else { const int c = cmp_hval(in, b, m.buf_type); if ((m.fn == SD_AGG_MIN && c < 0) || (m.fn == SD_AGG_MAX && c > 0)) b = in; }
+            }
+            k++; break;
+        }
+      }
+    }
+    pos += 8 + sz;
+  }
+  if (nk == 0 && groups.empty()) {   // no-key aggregate over no partitions: one row of empty buffers
+    Group g;
+    for (auto& m : sp.agg_map) {
+      HVal v;
+      if (m.fn == SD_AGG_SUM || m.fn == SD_AGG_MIN || m.fn == SD_AGG_MAX) v.isnull = true;
+      g.bufs.push_back(v);
+      if (m.fn == SD_AGG_AVG) g.bufs.push_back(HVal());
+    }
+    groups.push_back(g);
+  }
+  std::vector<int> otypes(types.begin(), types.begin() + nk);
+  for (auto& m : sp.agg_map) otypes.push_back(m.fn == SD_AGG_AVG ? (int)SD_DOUBLE : m.buf_type);
+  std::vector<uint8_t> out;
+  for (auto& g : groups) {
+    std::vector<HVal> vals(g.keys);
+    int k = 0;
+    for (auto& m : sp.agg_map) {
+      if (m.fn == SD_AGG_AVG) {   // Average.evaluateExpression: sum / count, NULL when count == 0
+        HVal v;
+        if (g.bufs[k + 1].i == 0) v.isnull = true; else v.d = g.bufs[k].d / (double)g.bufs[k + 1].i;
+        vals.push_back(v);
+        k += 2;
+      } else { vals.push_back(g.bufs[k]); k++; }
+    }
+    emit_unsafe_row(out, otypes, vals);
+  }
+  *out_len = (int64_t)out.size();
+  if (out_nrows) *out_nrows = (int64_t)groups.size();
+  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_final_merge: output needs %zu bytes", out.size());
+  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
+  return 0;
+}
+
+}  // extern "C"

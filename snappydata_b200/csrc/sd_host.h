@@ -1,0 +1,114 @@
+// sd_host.h -- internal host-side declarations shared by the engine translation units.
+#ifndef SD_HOST_H
+#define SD_HOST_H
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/snappy_gpu.h"
+#include "sd_codegen.h"
+#include "sd_device.h"
+
+namespace sd {
+
+// ---- errors -------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+#define SD_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return sd::set_error(SD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- kernel registry ------------------------------------------------------------------------------
+struct KernelEntry {
+  std::string signature;
+  const void* func;      // &scan_aggregate_kernel<PLAN> (runtime API launch)
+  void* drv_func;        // CUfunction for NVRTC-compiled plans
+  size_t tile_smem;      // sizeof(TileSmem<PLAN>) rounded up to 16
+  std::string origin;    // "aot" | "jit"
+};
+std::vector<KernelEntry>& kernel_registry();
+struct AotRegistrar {
+  AotRegistrar(const char* signature, const void* func, size_t tile_smem);
+};
+// set the dynamic shared-memory limit and query CTAs/SM; launch (runtime API for AOT, driver API for JIT)
+int kernel_prepare(const KernelEntry& k, size_t smem, int* ctas_per_sm);
+int kernel_launch(const KernelEntry& k, int grid, size_t smem, cudaStream_t stream, void** args);
+// NVRTC path (sd_jit.cpp): compile `spec.source` against the embedded kernel headers.
+int jit_compile(const PlanSpec& spec, int device, KernelEntry& out);
+
+// ---- device memory arena: bump allocation out of large slabs ---------------------------------------
+struct Arena {
+  int device = 0;
+  size_t slab_bytes = size_t(512) << 20;
+  std::vector<std::pair<uint8_t*, size_t>> slabs;
+  size_t cur_slab = 0;
+  size_t cur_off = 0;
+  size_t used = 0;
+  // returns p with (p + misalign) % align == 0, or nullptr (error set)
+  uint8_t* alloc(size_t n, size_t align = 256, size_t misalign = 0);
+  void reset();     // keep slabs, forget allocations
+  void release();   // free slabs
+  ~Arena() { release(); }
+};
+
+// ---- resident batches ------------------------------------------------------------------------------
+struct StoredDelta {
+  bool present = false;
+  DevDelta dev;                           // device pointers
+  int64_t len = 0;
+  std::vector<std::string> dict_strings;  // STRING values dictionary
+};
+
+struct StoredCol {
+  bool present = false;
+  std::string unsupported;                // non-empty: reason the GPU path cannot scan this column
+  int64_t len = 0;
+  int64_t algo_bytes = 0;                 // len - 8 - dictionary bytes
+  uint8_t* dev_base = nullptr;            // device copy of the whole buffer
+  int64_t body_off = 0;                   // offset of the first value / index
+  DevCol dev;                             // device view (delta pointers filled per plan)
+  std::vector<std::string> dict_strings;  // STRING dictionary (or distinct RLE run strings)
+  bool has_nulls = false;
+  StoredDelta delta[2];
+  DevDelta* dev_delta[2] = {nullptr, nullptr};   // DevDelta structs resident on the device
+  bool fast = false;                      // vector fast path applies
+};
+
+struct StoredBatch {
+  int32_t num_rows = 0;
+  int32_t bucket_id = 0;
+  int64_t batch_id = 0;
+  std::vector<StoredCol> cols;            // by table column
+  std::vector<uint8_t> stats;             // stats UnsafeRow (host copy)
+  int32_t stats_ncols = 0;
+  int32_t* dev_deletes = nullptr;
+  int32_t num_deletes = 0;
+  bool has_deltas = false;
+  bool positional = false;                // cols are indexed by the plan's scan column (private store)
+};
+
+}  // namespace sd
+
+struct sd_store {
+  int device = 0;
+  std::vector<sd_column> schema;
+  sd::Arena arena;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<std::unique_ptr<sd::StoredBatch>> batches;
+  int64_t version = 0;
+  int64_t h2d_bytes = 0;
+};
+
+namespace sd {
+// upload one batch (columns by table ordinal of `schema`) into the store's arena
+int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals /* nullptr: identity */);
+}
+
+#endif

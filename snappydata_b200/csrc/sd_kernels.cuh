@@ -1,0 +1,497 @@
+// sd_kernels.cuh -- the fused scan -> decode -> filter -> partial-aggregate kernel for sm_100a.
+//
+// One kernel template, specialised per plan by a small generated struct (PLAN) that supplies the
+// plan's column kinds and three inline functions: filter(), group() and slots() -- the B200
+// counterpart of the reference's WholeStageCodegen class for
+//   ColumnTableScan.doProduce            core/execution/columnar/ColumnTableScan.scala:186-672
+//   FilterExec.doConsume                 (Spark 2.1.1)
+//   SnappyHashAggregateExec.doConsume    core/execution/aggregate/SnappyHashAggregateExec.scala:252-263
+// Everything else here is hand-written: batch/tile scheduling, the per-encoding decoders
+// (Uncompressed / Dictionary / BigDictionary / BooleanBitSet / RunLength, nullable or not), the
+// update-delta overlay and delete mask, and the aggregation machinery.
+//
+// Roofline: the kernel is HBM-read bound (<= ~3 flops per loaded byte; no dense contraction, so
+// tensor cores do not apply).  Design for that bound:
+//   * every column read of the common case (NOT NULL or no nulls in the batch, Uncompressed or
+//     int16/int32 dictionary indexes, no deltas) is ONE fully coalesced, 16-byte-aligned,
+//     cache-streaming vector load per row pair per lane (16/8/4/2 bytes per lane);
+//   * all loads of a tile (every column, RPT rows) are issued before the first use, so each thread
+//     keeps NC * RPT/2 independent requests in flight;
+//   * a persistent grid of 148 * CTAS_PER_SM CTAs walks (batch, chunk) work items round-robin -- no
+//     per-batch launch, deterministic reduction order;
+//   * aggregation never touches global atomics on the hot path: registers (no keys) or per-thread
+//     private shared-memory tables laid out bank-conflict free (small group counts), reduced once per
+//     CTA, then by the last CTA in fixed order.
+//
+// Self-contained: includes only sd_device.h so NVRTC can compile it from an in-memory string.
+#ifndef SD_KERNELS_CUH
+#define SD_KERNELS_CUH
+
+#include "sd_device.h"
+
+namespace sd {
+
+// ---- kind -> register type --------------------------------------------------------------------
+template <int K> struct KindT;
+template <> struct KindT<K_I8> { typedef int8_t T; };
+template <> struct KindT<K_I16> { typedef int16_t T; };
+template <> struct KindT<K_I32> { typedef int32_t T; };
+template <> struct KindT<K_I64> { typedef int64_t T; };
+template <> struct KindT<K_F32> { typedef float T; };
+template <> struct KindT<K_F64> { typedef double T; };
+template <> struct KindT<K_BOOL> { typedef uint8_t T; };
+template <> struct KindT<K_CODE> { typedef int32_t T; };
+
+template <int... Is> struct Seq {};
+template <int N, int... Is> struct MakeSeq : MakeSeq<N - 1, N - 1, Is...> {};
+template <int... Is> struct MakeSeq<0, Is...> { typedef Seq<Is...> type; };
+
+// ---- NaN-safe total order of Spark's double/float comparisons (Utils.nanSafeCompareDoubles:
+//      NaN == NaN, NaN greater than everything, -0.0 == 0.0) ------------
+template <class F> __device__ __forceinline__ bool f_ge(F a, F b) { return (a >= b) || (a != a); }
+template <class F> __device__ __forceinline__ bool f_gt(F a, F b) { return (a > b) || ((a != a) && (b == b)); }
+template <class F> __device__ __forceinline__ bool f_le(F a, F b) { return f_ge(b, a); }
+template <class F> __device__ __forceinline__ bool f_lt(F a, F b) { return f_gt(b, a); }
+template <class F> __device__ __forceinline__ bool f_eq(F a, F b) { return (a == b) || ((a != a) && (b != b)); }
+
+// Java (int)/(long) casts of floating point: NaN -> 0, saturating
+__device__ __forceinline__ int64_t f64_to_i64(double d) { return (d != d) ? 0 : __double2ll_rz(d); }
+__device__ __forceinline__ int32_t f64_to_i32(double d) { return (d != d) ? 0 : __double2int_rz(d); }
+
+// three-valued logic helpers for generated predicates: 0 FALSE, 1 TRUE, 2 NULL
+__device__ __forceinline__ int tv_and(int a, int b) { return (a == 0 || b == 0) ? 0 : ((a == 2 || b == 2) ? 2 : 1); }
+__device__ __forceinline__ int tv_or(int a, int b) { return (a == 1 || b == 1) ? 1 : ((a == 2 || b == 2) ? 2 : 0); }
+__device__ __forceinline__ int tv_not(int a) { return a == 2 ? 2 : 1 - a; }
+
+// ---- slot (accumulator) algebra: every op is a commutative monoid over 8-byte words ------------
+__device__ __forceinline__ uint64_t f2u(double d) { return (uint64_t)__double_as_longlong(d); }
+__device__ __forceinline__ double u2f(uint64_t u) { return __longlong_as_double((long long)u); }
+
+__host__ __device__ constexpr uint64_t slot_identity(int op) {
+  return op == SLOT_ADD_F64 ? 0ull
+       : op == SLOT_ADD_I64 ? 0ull
+       : op == SLOT_MIN_I64 ? 0x7fffffffffffffffull
+       : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+       : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull   /* NaN: the greatest element of the order */
+       : 0xfff0000000000000ull;                        /* SLOT_MAX_F64: -inf */
+}
+__device__ __forceinline__ uint64_t slot_combine(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case SLOT_ADD_F64: return f2u(u2f(a) + u2f(b));
+    case SLOT_ADD_I64: return a + b;
+    case SLOT_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
+    case SLOT_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
+    case SLOT_MIN_F64: return f_lt(u2f(b), u2f(a)) ? b : a;
+    default: return f_gt(u2f(b), u2f(a)) ? b : a;
+  }
+}
+
+// ---- loads ------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T ld_at(const uint8_t* base, int64_t k) {
+  return *reinterpret_cast<const T*>(base + k * (int64_t)sizeof(T));
+}
+// RLE records are only naturally aligned to their 4-byte run length: assemble wider values bytewise
+template <class T> __device__ __forceinline__ T ld_unaligned(const uint8_t* p) {
+  T v;
+  uint8_t* o = reinterpret_cast<uint8_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)sizeof(T); i++) o[i] = p[i];
+  return v;
+}
+__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int lo, int hi, int32_t x) {
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// k-th stored (non-null) value of a column body.  Restates the decoder read methods:
+// Uncompressed (enc/Uncompressed.scala:74-98), Dictionary/BigDictionary
+// (enc/DictionaryEncoding.scala:118-137,148-166), BooleanBitSet (enc/BooleanBitSetEncoding.scala:57-59),
+// RunLength via host-built run-end prefix (enc/RunLengthEncoding.scala:112-172).
+template <int KIND>
+__device__ __forceinline__ typename KindT<KIND>::T decode_value(const uint8_t* data, const uint8_t* dict,
+                                                                const int32_t* run_ends, int enc, int nruns, int64_t k) {
+  typedef typename KindT<KIND>::T T;
+  if (enc == ENC_UNCOMPRESSED) {
+    if (KIND == K_BOOL) return (T)(data[k] == 1);
+    return ld_at<T>(data, k);
+  }
+  if (enc == ENC_DICTIONARY || enc == ENC_BIG_DICTIONARY) {
+    int idx = enc == ENC_DICTIONARY ? (int)ld_at<int16_t>(data, k) : ld_at<int32_t>(data, k);
+    if (KIND == K_CODE) return (T)idx;
+    return ld_at<T>(dict, idx);
+  }
+  if (enc == ENC_BOOLEAN_BITSET) return (T)((ld_at<uint64_t>(data, k >> 6) >> (k & 63)) & 1);
+  // ENC_RUN_LENGTH: first run whose exclusive end exceeds k
+  int run = lower_bound_i32(run_ends, 0, nruns, (int32_t)k + 1);
+  if (KIND == K_CODE) return (T)ld_at<int32_t>(dict, run);
+  return ld_unaligned<T>(data + (int64_t)run * (sizeof(T) + 4));
+}
+
+// value of an update-delta entry; K_CODE entries are translated to the batch's unified code space
+template <int KIND>
+__device__ __forceinline__ typename KindT<KIND>::T decode_delta_value(const DevDelta& d, int64_t k) {
+  typedef typename KindT<KIND>::T T;
+  if (KIND == K_CODE) {
+    int idx = d.enc == ENC_DICTIONARY ? (int)ld_at<int16_t>(d.data, k) : ld_at<int32_t>(d.data, k);
+    return (T)ld_at<int32_t>(d.dict, idx);
+  }
+  return decode_value<KIND>(d.data, d.dict, nullptr, d.enc, 0, k);
+}
+
+// ---- per-thread registers of one tile -----------------------------------------------------------
+template <class PLAN, int C>
+struct ColRegs {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  T v[RPT];
+  uint32_t nullmask;   // bit r: row r of this thread is NULL in column C
+};
+template <class PLAN, class S> struct AllCols;
+template <class PLAN, int... Cs> struct AllCols<PLAN, Seq<Cs...>> : ColRegs<PLAN, Cs>... {};
+
+template <class PLAN>
+struct TileSmem {
+  uint32_t delbits[TILE_ROWS / 32];
+  uint32_t updbits[PLAN::NC > 0 ? PLAN::NC : 1][TILE_ROWS / 32];
+  int32_t wprefix[PLAN::NC > 0 ? PLAN::NC : 1][TILE_WORDS];
+  int32_t drange[PLAN::NC > 0 ? PLAN::NC : 1][4];
+};
+
+// row r of a thread within tile: pair u = r/2 at tile + u*2*THREADS + 2*tid + (r&1)
+__device__ __forceinline__ int row_in_tile(int r) { return (r >> 1) * 2 * THREADS + 2 * (int)threadIdx.x + (r & 1); }
+
+// ---- fast path: coalesced vector loads ------------------------------------------------------------
+template <class PLAN, int C>
+__device__ __forceinline__ void load_col_fast(const DevCol& col, int64_t tile_start, ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  regs.nullmask = 0;
+#pragma unroll
+  for (int u = 0; u < RPT / 2; u++) {
+    const int64_t p = tile_start + u * 2 * THREADS + 2 * (int)threadIdx.x;   // even row index
+    if (K == K_CODE) {
+      if (col.enc == ENC_DICTIONARY) {
+        uint32_t x = __ldcs(reinterpret_cast<const uint32_t*>(col.data + p * 2));
+        regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
+        regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
+      } else {
+        int2 x = __ldcs(reinterpret_cast<const int2*>(col.data + p * 4));
+        regs.v[2 * u] = (T)x.x;
+        regs.v[2 * u + 1] = (T)x.y;
+      }
+    } else if (sizeof(T) == 8) {
+      longlong2 x = __ldcs(reinterpret_cast<const longlong2*>(col.data + p * 8));
+      regs.v[2 * u] = K == K_F64 ? (T)__longlong_as_double(x.x) : (T)x.x;
+      regs.v[2 * u + 1] = K == K_F64 ? (T)__longlong_as_double(x.y) : (T)x.y;
+    } else if (sizeof(T) == 4) {
+      int2 x = __ldcs(reinterpret_cast<const int2*>(col.data + p * 4));
+      regs.v[2 * u] = K == K_F32 ? (T)__int_as_float(x.x) : (T)x.x;
+      regs.v[2 * u + 1] = K == K_F32 ? (T)__int_as_float(x.y) : (T)x.y;
+    } else if (sizeof(T) == 2) {
+      uint32_t x = __ldcs(reinterpret_cast<const uint32_t*>(col.data + p * 2));
+      regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
+      regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
+    } else {
+      uint16_t x = __ldcs(reinterpret_cast<const uint16_t*>(col.data + p));
+      regs.v[2 * u] = K == K_BOOL ? (T)((x & 0xff) == 1) : (T)(int8_t)(x & 0xff);
+      regs.v[2 * u + 1] = K == K_BOOL ? (T)((x >> 8) == 1) : (T)(int8_t)(x >> 8);
+    }
+  }
+}
+
+// ---- general path: nulls, deltas, every encoding -------------------------------------------------
+template <class PLAN, int C>
+__device__ __forceinline__ void load_col_general(const DevCol& col, int tile, int64_t tile_start, int num_rows,
+                                                 const TileSmem<PLAN>& sm, ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  regs.nullmask = 0;
+  const bool has_delta = col.delta0 != nullptr || col.delta1 != nullptr;
+  const int tile_nulls = col.tile_nulls ? col.tile_nulls[tile] : 0;
+#pragma unroll
+  for (int r = 0; r < RPT; r++) {
+    const int li = row_in_tile(r);
+    const int64_t i = tile_start + li;
+    T v = (T)0;
+    bool isnull = false;
+    if (i < num_rows) {
+      const bool upd = has_delta && ((sm.updbits[C][li >> 5] >> (li & 31)) & 1u);
+      if (!upd) {   // base value: k = ordinal - nulls before it (ColumnTableScan.scala:794-815)
+        int64_t k = i;
+        if (col.nulls) {
+          const int w = (int)(i >> 6);
+          const uint64_t word = w < col.nwords ? col.nulls[w] : 0ull;
+          isnull = (word >> (i & 63)) & 1ull;
+          k = i - (tile_nulls + sm.wprefix[C][li >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull)));
+        }
+        if (!isnull) v = decode_value<K>(col.data, col.dict, col.run_ends, col.enc, col.nruns, k);
+      } else {      // depth-0 delta wins on equal position (enc/UpdatedColumnDecoder.scala:95-104)
+        const DevDelta* d = col.delta0;
+        int j = -1;
+        if (d) {
+          int q = lower_bound_i32(d->positions, sm.drange[C][0], sm.drange[C][1], (int32_t)i);
+          if (q < sm.drange[C][1] && d->positions[q] == (int32_t)i) j = q;
+        }
+        if (j < 0) {
+          d = col.delta1;
+          j = lower_bound_i32(d->positions, sm.drange[C][2], sm.drange[C][3], (int32_t)i);
+        }
+        int64_t k = j;
+        if (d->nulls) {   // null bits index the relative entry (enc/ColumnDeltaDecoder.scala:77-83)
+          const int w = j >> 6;
+          const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
+          isnull = (word >> (j & 63)) & 1ull;
+          int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
+          for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
+          k = j - before;
+        }
+        if (!isnull) v = decode_delta_value<K>(*d, k);
+      }
+      if (isnull && K == K_CODE) v = (T)col.dict_n;   // NULL code (ColumnTableScan.scala:706-716)
+    }
+    regs.v[r] = v;
+    regs.nullmask |= (isnull ? 1u : 0u) << r;
+  }
+}
+
+// tile preparation for the general path: null-word prefix sums, delete / update bitmaps
+template <class PLAN, int C>
+__device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
+  const int tid = threadIdx.x;
+  if (col.nulls && tid < TILE_WORDS) {   // warp 0, lanes 0..15: exclusive scan of per-word popcounts
+    const int w = (int)(tile_start >> 6) + tid;
+    const int pc = w < col.nwords ? __popcll(col.nulls[w]) : 0;
+    int inc = pc;
+#pragma unroll
+    for (int d = 1; d < TILE_WORDS; d <<= 1) {
+      int t = __shfl_up_sync(0xffffu, inc, d, TILE_WORDS);
+      if (tid >= d) inc += t;
+    }
+    sm.wprefix[C][tid] = inc - pc;
+  }
+  if (col.delta0 || col.delta1) {
+    const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
+#pragma unroll
+    for (int dd = 0; dd < 2; dd++) {
+      const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
+      int lo = 0, hi = 0;
+      if (d) {
+        lo = lower_bound_i32(d->positions, 0, d->n, ts);
+        hi = lower_bound_i32(d->positions, lo, d->n, te);
+        for (int j = lo + tid; j < hi; j += THREADS) {
+          const int li = d->positions[j] - ts;
+          atomicOr(&sm.updbits[C][li >> 5], 1u << (li & 31));
+        }
+      }
+      if (tid == 0) { sm.drange[C][2 * dd] = lo; sm.drange[C][2 * dd + 1] = hi; }
+    }
+  }
+}
+
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_all_fast(const DevBatch<PLAN::NC>& b, int64_t tile_start,
+                                              AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (load_col_fast<PLAN, Cs>(b.cols[Cs], tile_start, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void clear_upd_bits(const DevBatch<PLAN::NC>& b, TileSmem<PLAN>& sm, Seq<Cs...>) {
+  const int tid = threadIdx.x;
+  if (tid < TILE_ROWS / 32) {
+    sm.delbits[tid] = 0;
+    int dummy[] = {0, ((b.cols[Cs].delta0 || b.cols[Cs].delta1) ? (sm.updbits[Cs][tid] = 0, 0) : 0)...};
+    (void)dummy;
+  }
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void prep_all_general(const DevBatch<PLAN::NC>& b, int64_t tile_start, TileSmem<PLAN>& sm, Seq<Cs...>) {
+  int dummy[] = {0, (prep_col_general<PLAN, Cs>(b.cols[Cs], tile_start, sm), 0)...};
+  (void)dummy;
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_all_general(const DevBatch<PLAN::NC>& b, int tile, int64_t tile_start,
+                                                 const TileSmem<PLAN>& sm, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (load_col_general<PLAN, Cs>(b.cols[Cs], tile, tile_start, b.num_rows, sm,
+                                                static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void fill_row(const AllCols<PLAN, Seq<Cs...>>& regs, int r, typename PLAN::Row& row, Seq<Cs...>) {
+  int dummy[] = {0, (row.template set<Cs>(static_cast<const ColRegs<PLAN, Cs>&>(regs).v[r],
+                                          (static_cast<const ColRegs<PLAN, Cs>&>(regs).nullmask >> r) & 1u), 0)...};
+  (void)dummy;
+}
+
+// context handed to the generated row functions
+struct RowCtx {
+  const Literals* L;
+  const uint8_t* aux;   // per-batch tables of this plan (offset header, then tables)
+  const int32_t* radix;
+  // table t of the batch: aux + ((const int32_t*)aux)[t]
+  __device__ __forceinline__ const uint8_t* table(int t) const { return aux + reinterpret_cast<const int32_t*>(aux)[t]; }
+};
+
+// ================================================================================================
+// The kernel.  dynamic shared memory: [TileSmem<PLAN>] [private group tables | reduction scratch]
+// ================================================================================================
+template <class PLAN>
+__global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel(const ScanArgs args) {
+  typedef typename MakeSeq<PLAN::NC>::type ColSeq;
+  constexpr int NSLOT = PLAN::NSLOT;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  TileSmem<PLAN>& sm = *reinterpret_cast<TileSmem<PLAN>*>(smem_raw);
+  uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(TileSmem<PLAN>) + 15) & ~size_t(15)));
+  const int tid = threadIdx.x;
+  const int NE = args.ngroups * NSLOT;   // entries of the group table
+
+  // ---- accumulator init -------------------------------------------------------------------------
+  uint64_t acc[NSLOT > 0 ? NSLOT : 1];
+  if (PLAN::MODE == MODE_NOKEY) {
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
+  } else {
+    // private table of thread t: entry e at table[e * THREADS + t]: lanes hit distinct banks
+    for (int e = 0; e < NE; e++) table[e * THREADS + tid] = slot_identity(PLAN::slot_op(e % NSLOT));
+  }
+  unsigned long long n_scanned = 0, n_passed = 0;
+
+  RowCtx ctx;
+  ctx.L = &args.lits;
+  ctx.radix = args.radix;
+  const DevBatch<PLAN::NC>* batches = reinterpret_cast<const DevBatch<PLAN::NC>*>(args.batches);
+
+  // ---- persistent loop over (batch, chunk) work items, static round-robin -------------------------
+  for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
+    // batch of this chunk: last b with chunk_prefix[b] <= item
+    int lo = 0, hi = args.nbatches;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (args.chunk_prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    const DevBatch<PLAN::NC>& b = batches[lo];
+    const int chunk = item - args.chunk_prefix[lo];
+    const int num_rows = b.num_rows;
+    const bool fast = (b.flags & BATCH_ALL_FAST) != 0;
+    ctx.aux = b.aux;
+    const int tile0 = chunk * CHUNK_TILES;
+    const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
+    const int tile_end = min(tile0 + CHUNK_TILES, ntiles);
+
+    for (int tile = tile0; tile < tile_end; tile++) {
+      const int64_t tile_start = (int64_t)tile * TILE_ROWS;
+      AllCols<PLAN, ColSeq> regs;
+      uint32_t live = 0;   // bit r: row exists and is not deleted
+#pragma unroll
+      for (int r = 0; r < RPT; r++) live |= (tile_start + row_in_tile(r) < num_rows ? 1u : 0u) << r;
+
+      if (fast) {
+        load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
+      } else {
+        __syncthreads();                       // previous tile's readers are done with sm
+        clear_upd_bits<PLAN>(b, sm, ColSeq());
+        __syncthreads();
+        prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
+        if (b.deletes) {                       // delete mask -> tile bitmap (enc/ColumnDeleteDecoder.scala:49-55)
+          const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
+          const int dlo = lower_bound_i32(b.deletes, 0, b.num_deletes, ts);
+          for (int j = dlo + tid; j < b.num_deletes && b.deletes[j] < te; j += THREADS) {
+            const int li = b.deletes[j] - ts;
+            atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
+          }
+        }
+        __syncthreads();
+        load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
+        if (b.deletes) {
+#pragma unroll
+          for (int r = 0; r < RPT; r++) {
+            const int li = row_in_tile(r);
+            if ((sm.delbits[li >> 5] >> (li & 31)) & 1u) live &= ~(1u << r);
+          }
+        }
+      }
+
+      // ---- row at a time over registers: filter -> group -> accumulate -------------------------
+#pragma unroll
+      for (int r = 0; r < RPT; r++) {
+        if (!((live >> r) & 1u)) continue;
+        n_scanned++;
+        typename PLAN::Row row;
+        fill_row<PLAN>(regs, r, row, ColSeq());
+        if (!PLAN::filter(row, ctx)) continue;      // FilterExec: only TRUE passes
+        n_passed++;
+        uint64_t sv[NSLOT > 0 ? NSLOT : 1];
+        PLAN::slots(row, ctx, sv);
+        if (PLAN::MODE == MODE_NOKEY) {
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++) acc[s] = slot_combine(PLAN::slot_op(s), acc[s], sv[s]);
+        } else {
+          const int g = PLAN::group(row, ctx);
+          uint64_t* t = table + (size_t)g * NSLOT * THREADS + tid;
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++) t[s * THREADS] = slot_combine(PLAN::slot_op(s), t[s * THREADS], sv[s]);
+        }
+      }
+    }
+  }
+
+  // ---- CTA reduction (fixed order) -> partials[blockIdx] -------------------------------------------
+  __syncthreads();
+  uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (PLAN::MODE == MODE_NOKEY) {
+    uint64_t* scratch = table;   // [NSLOT][THREADS/32]
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+      uint64_t v = acc[s];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v = slot_combine(PLAN::slot_op(s), v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0) scratch[s * (THREADS / 32) + warp] = v;
+    }
+    __syncthreads();
+    if (tid < NSLOT) {
+      const int op = PLAN::slot_op_rt(tid);
+      uint64_t v = slot_identity(op);
+      for (int w = 0; w < THREADS / 32; w++) v = slot_combine(op, v, scratch[tid * (THREADS / 32) + w]);
+      my_partials[tid] = v;
+    }
+  } else {
+    for (int e = warp; e < NE; e += THREADS / 32) {
+      const int op = PLAN::slot_op_rt(e % NSLOT);
+      uint64_t v = slot_identity(op);
+#pragma unroll
+      for (int j = 0; j < THREADS / 32; j++) v = slot_combine(op, v, table[e * THREADS + lane + 32 * j]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v = slot_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0) my_partials[e] = v;
+    }
+  }
+  // metrics
+  {
+    unsigned long long a = n_scanned, p = n_passed;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); p += __shfl_xor_sync(0xffffffffu, p, d); }
+    if (lane == 0) { atomicAdd(&args.counters[0], a); atomicAdd(&args.counters[1], p); }
+  }
+
+  // ---- last CTA combines all CTA partials in CTA order into the running result ---------------------
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int e = tid; e < NE; e += THREADS) {
+      const int op = PLAN::slot_op_rt(e % NSLOT);
+      uint64_t v = slot_identity(op);
+      for (unsigned bk = 0; bk < gridDim.x; bk++) v = slot_combine(op, v, __ldcg(&args.partials[(size_t)bk * NE + e]));
+      args.result[e] = slot_combine(op, args.result[e], v);
+    }
+    if (tid == 0) *args.ticket = 0;
+  }
+}
+
+}  // namespace sd
+#endif

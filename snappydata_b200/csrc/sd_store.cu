@@ -1,0 +1,472 @@
+// sd_store.cu -- device-resident ColumnBatch store: header/dictionary parsing on the host (the
+// per-batch, per-column "decoder initialisation" the reference does in ColumnEncoding.getColumnDecoder
+// / initializeNulls / initializeCursor, enc/ColumnEncoding.scala:797-832,1042-1099,
+// enc/DictionaryEncoding.scala:85-116) and placement of the raw encoded bytes in HBM.
+//
+// HBM layout: the encoded bytes are copied VERBATIM (no re-encoding); only their placement is chosen
+// by the engine: every buffer is positioned so that its first value / first dictionary index is
+// 128-byte aligned, which makes every vector load of the scan kernel naturally aligned.  Null words get
+// an 8-byte aligned side copy plus a host-computed "nulls before tile" prefix (one int32 per 1024 rows).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sd_host.h"
+
+namespace sd {
+
+static thread_local std::string g_error;
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+const char* last_error_cstr() { return g_error.c_str(); }
+
+std::vector<KernelEntry>& kernel_registry() {
+  static std::vector<KernelEntry> r;
+  return r;
+}
+AotRegistrar::AotRegistrar(const char* signature, const void* func, size_t tile_smem) {
+  KernelEntry e;
+  e.signature = signature; e.func = func; e.drv_func = nullptr; e.tile_smem = (tile_smem + 15) & ~size_t(15); e.origin = "aot";
+  kernel_registry().push_back(e);
+}
+
+// ---- arena ------------------------------------------------------------------------------------------
+uint8_t* Arena::alloc(size_t n, size_t align, size_t misalign) {
+  if (n == 0) n = 1;
+  for (;;) {
+    if (cur_slab < slabs.size()) {
+      uint8_t* base = slabs[cur_slab].first;
+      size_t p = (size_t)(uintptr_t)(base + cur_off);
+      size_t want = (p + misalign + align - 1) / align * align - misalign;
+      if (want < p) want += align;
+      size_t off = want - (size_t)(uintptr_t)base;
+      if (off + n <= slabs[cur_slab].second) {
+        cur_off = off + n;
+        used += n;
+        return base + off;
+      }
+      cur_slab++;
+      cur_off = 0;
+      continue;
+    }
+    size_t sz = slab_bytes;
+    if (n + align + misalign + 256 > sz) sz = n + align + misalign + 256;
+    void* p = nullptr;
+    cudaSetDevice(device);
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+      set_error(SD_ERR_CUDA, "cudaMalloc(%zu) failed: %s", sz, cudaGetErrorString(e));
+      return nullptr;
+    }
+    slabs.push_back({(uint8_t*)p, sz});
+    cur_slab = slabs.size() - 1;
+    cur_off = 0;
+  }
+}
+void Arena::reset() { cur_slab = 0; cur_off = 0; used = 0; }
+void Arena::release() {
+  if (!slabs.empty()) cudaSetDevice(device);
+  for (auto& s : slabs) cudaFree(s.first);
+  slabs.clear();
+  reset();
+}
+
+// ---- little-endian host reads ----------------------------------------------------------------------
+static inline int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd_u64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+static int fixed_width_of(int t) {
+  switch (t) {
+    case SD_BOOLEAN: case SD_BYTE: return 1;
+    case SD_SHORT: return 2;
+    case SD_INT: case SD_DATE: case SD_FLOAT: return 4;
+    case SD_LONG: case SD_TIMESTAMP: case SD_DECIMAL: case SD_DOUBLE: return 8;
+  }
+  return 0;
+}
+
+template <class T>
+static int upload_vec(sd_store* s, const std::vector<T>& v, size_t align, const T** out) {
+  uint8_t* d = s->arena.alloc(v.size() * sizeof(T) + 16, align);
+  if (!d) return SD_ERR_CUDA;
+  if (!v.empty()) SD_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->copy_stream));
+  s->h2d_bytes += (int64_t)(v.size() * sizeof(T));
+  *out = reinterpret_cast<const T*>(d);
+  return 0;
+}
+static int upload_bytes(sd_store* s, const uint8_t* src, size_t n, size_t align, size_t misalign, uint8_t** out) {
+  uint8_t* d = s->arena.alloc(n + 160, align, misalign);   // tail padding: vector loads may overrun a partial pair
+  if (!d) return SD_ERR_CUDA;
+  if (n) SD_CUDA(cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, s->copy_stream));
+  s->h2d_bytes += (int64_t)n;
+  *out = d;
+  return 0;
+}
+
+// Parse [numElements][dictionary] at p; returns bytes consumed or -1.
+static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, int* n_out, std::vector<std::string>* strings) {
+  if (p + 4 > end) return -1;
+  const int n = rd_i32(p);
+  if (n < 0) return -1;
+  const uint8_t* q = p + 4;
+  if (type == SD_STRING) {
+    strings->clear();
+    strings->reserve(n);
+    for (int k = 0; k < n; k++) {
+      if (q + 4 > end) return -1;
+      const int l = rd_i32(q);
+      if (l < 0 || q + 4 + l > end) return -1;
+      strings->emplace_back(reinterpret_cast<const char*>(q + 4), (size_t)l);
+      q += 4 + l;
+    }
+  } else if (type == SD_INT || type == SD_DATE) {
+    q += 4 * (int64_t)n;
+  } else if (type == SD_LONG || type == SD_TIMESTAMP) {
+    q += 8 * (int64_t)n;   // written 8 bytes per entry (allocation slack stays at the tail)
+  } else return -2;
+  if (q > end) return -1;
+  *n_out = n;
+  return q - p;
+}
+
+static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type, int nullable, int num_rows, StoredCol& c) {
+  if (len < 8) return set_error(SD_ERR_INVALID, "column buffer shorter than its 8-byte header");
+  const int type_id = rd_i32(buf);
+  if (type_id < 0)
+    return set_error(SD_ERR_UNSUPPORTED, "compressed column buffer (codec %d): decompress before submit; on-device LZ4 is not built yet", -type_id);
+  if (type_id > ENC_BOOLEAN_BITSET) return set_error(SD_ERR_INVALID, "unknown encoding typeId %d", type_id);
+  const int null_bytes = rd_i32(buf + 4);
+  if (null_bytes < 0 || (null_bytes & 7) || 8 + (int64_t)null_bytes > len) return set_error(SD_ERR_INVALID, "bad null bitset size %d", null_bytes);
+  if (!nullable && null_bytes != 0)   // NotNullDecoder.initializeNulls (enc/ColumnEncoding.scala:1042-1050)
+    return set_error(SD_ERR_INVALID, "Nulls bitset of size %d found in NOT NULL column", null_bytes);
+  const int nwords = null_bytes >> 3;
+  c = StoredCol();
+  c.present = true;
+  c.len = len;
+  memset(&c.dev, 0, sizeof(c.dev));
+  c.dev.enc = type_id;
+  c.dev.nwords = nwords;
+  // nulls before each tile (the incremental numNulls bookkeeping of the generated loop,
+  // ColumnTableScan.scala:794-815, turned into a prefix the kernel can index)
+  const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
+  int64_t total_nulls = 0;
+  std::vector<int32_t> tile_nulls;
+  if (nwords) {
+    tile_nulls.resize(ntiles > 0 ? ntiles : 1, 0);
+    for (int w = 0; w < nwords; w++) {
+      if ((w % TILE_WORDS) == 0 && w / TILE_WORDS < ntiles) tile_nulls[w / TILE_WORDS] = (int32_t)total_nulls;
+      uint64_t word = rd_u64(buf + 8 + 8 * (int64_t)w);
+      if ((int64_t)(w + 1) * 64 > num_rows) {   // ignore bits beyond the batch
+        int valid = num_rows - w * 64;
+        word = valid <= 0 ? 0 : (valid >= 64 ? word : (word & ((1ull << valid) - 1)));
+      }
+      total_nulls += __builtin_popcountll(word);
+    }
+    for (int t = (nwords + TILE_WORDS - 1) / TILE_WORDS; t < ntiles; t++) tile_nulls[t] = (int32_t)total_nulls;
+  }
+  c.has_nulls = nwords > 0;
+  const int64_t nn = num_rows - total_nulls;   // stored (non-null) values
+  const uint8_t* end = buf + len;
+  int64_t body = 8 + null_bytes;
+  int64_t dict_bytes = 0;
+  const int w = fixed_width_of(type);
+  std::vector<int32_t> run_ends, run_codes;
+  switch (type_id) {
+    case ENC_UNCOMPRESSED:
+      if (type == SD_STRING) { c.unsupported = "Uncompressed variable-width STRING column (needs an offsets pass; not in the GPU path yet)"; break; }
+      if (body + nn * w > len) return set_error(SD_ERR_INVALID, "uncompressed column truncated: need %lld bytes, have %lld", (long long)(body + nn * w), (long long)len);
+      break;
+    case ENC_DICTIONARY: case ENC_BIG_DICTIONARY: {
+      int n = 0;
+      int64_t used = parse_dictionary(buf + body, end, type, &n, &c.dict_strings);
+      if (used == -2) return set_error(SD_ERR_INVALID, "DictionaryDecoder not supported for sd_type %d", type);
+      if (used < 0) return set_error(SD_ERR_INVALID, "truncated dictionary");
+      dict_bytes = used;
+      c.dev.dict_n = n;
+      body += used;
+      const int iw = type_id == ENC_DICTIONARY ? 2 : 4;
+      if (body + nn * iw > len) return set_error(SD_ERR_INVALID, "dictionary indexes truncated");
+      break;
+    }
+    case ENC_BOOLEAN_BITSET:
+      if (type != SD_BOOLEAN) return set_error(SD_ERR_INVALID, "BooleanBitSet encoding on a non-boolean column");
+      if (body + ((nn + 63) / 64) * 8 > len) return set_error(SD_ERR_INVALID, "boolean bitset truncated");
+      break;
+    case ENC_RUN_LENGTH: {
+      if (type == SD_BYTE || type == SD_BOOLEAN)
+        return set_error(SD_ERR_UNSUPPORTED, "RunLength BYTE/BOOLEAN: the reference decoder is inconsistent (enc/RunLengthEncoding.scala:99-110)");
+      if (!(type == SD_SHORT || type == SD_INT || type == SD_DATE || type == SD_LONG || type == SD_TIMESTAMP || type == SD_STRING))
+        return set_error(SD_ERR_INVALID, "RunLengthDecoder not supported for sd_type %d", type);
+      const uint8_t* q = buf + body;
+      int64_t covered = 0;
+      std::unordered_map<std::string, int> seen;
+      while (covered < nn) {
+        if (type == SD_STRING) {
+          if (q + 4 > end) return set_error(SD_ERR_INVALID, "RunLengthEncoding: reading next run after data end");
+          int l = rd_i32(q);
+          if (l < 0 || q + 8 + l > end) return set_error(SD_ERR_INVALID, "RunLengthEncoding: truncated string run");
+          std::string sv(reinterpret_cast<const char*>(q + 4), (size_t)l);
+          auto it = seen.find(sv);
+          int code;
+          if (it == seen.end()) { code = (int)c.dict_strings.size(); seen.emplace(sv, code); c.dict_strings.push_back(sv); } else code = it->second;
+          run_codes.push_back(code);
+          covered += rd_i32(q + 4 + l);
+          q += 8 + l;
+        } else {
+          if (q + w + 4 > end) return set_error(SD_ERR_INVALID, "RunLengthEncoding: reading next run after data end");
+          covered += rd_i32(q + w);
+          q += w + 4;
+        }
+        if (covered > INT32_MAX) return set_error(SD_ERR_INVALID, "run lengths overflow");
+        run_ends.push_back((int32_t)covered);
+      }
+      c.dev.nruns = (int)run_ends.size();
+      if (type == SD_STRING) c.dev.dict_n = (int)c.dict_strings.size();
+      break;
+    }
+  }
+  c.body_off = body;
+  c.algo_bytes = len - 8 - dict_bytes;
+  if (!c.unsupported.empty()) return 0;   // recorded; an error only if a plan scans this column
+
+  int rc = upload_bytes(s, buf, (size_t)len, 128, (size_t)body, &c.dev_base);
+  if (rc) return rc;
+  c.dev.data = c.dev_base + body;
+  if ((type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY) && type != SD_STRING) {
+    const int ew = (type == SD_INT || type == SD_DATE) ? 4 : 8;
+    c.dev.dict = c.dev_base + body - (int64_t)ew * c.dev.dict_n;   // ew-aligned because `body` is 128-aligned
+  }
+  if (nwords) {
+    uint8_t* dn = nullptr;
+    rc = upload_bytes(s, buf + 8, (size_t)null_bytes, 8, 0, &dn);
+    if (rc) return rc;
+    c.dev.nulls = reinterpret_cast<const uint64_t*>(dn);
+    rc = upload_vec(s, tile_nulls, 4, &c.dev.tile_nulls);
+    if (rc) return rc;
+  }
+  if (type_id == ENC_RUN_LENGTH) {
+    rc = upload_vec(s, run_ends, 4, &c.dev.run_ends);
+    if (rc) return rc;
+    if (type == SD_STRING) {
+      const int32_t* dc = nullptr;
+      rc = upload_vec(s, run_codes, 4, &dc);
+      if (rc) return rc;
+      c.dev.dict = reinterpret_cast<const uint8_t*>(dc);
+    }
+  }
+  const int kind = kind_of_type(type);
+  c.fast = !c.has_nulls && ((kind == K_CODE && (type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY)) ||
+                            (kind != K_CODE && type_id == ENC_UNCOMPRESSED));
+  return 0;
+}
+
+// update delta: header + relative null words, [numBaseRows][numDeltas][positions], pad to 8, values
+// (enc/ColumnDeltaEncoder.scala:300-331; decoder init enc/ColumnDeltaDecoder.scala:47-61)
+static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, StoredCol& col, int depth) {
+  StoredDelta& d = col.delta[depth];
+  if (len < 16) return set_error(SD_ERR_INVALID, "delta buffer too short");
+  const int type_id = rd_i32(buf);
+  if (type_id < 0) return set_error(SD_ERR_UNSUPPORTED, "compressed delta buffer");
+  const int null_bytes = rd_i32(buf + 4);
+  if (null_bytes < 0 || (null_bytes & 7) || 16 + (int64_t)null_bytes > len) return set_error(SD_ERR_INVALID, "bad delta null bitset size");
+  const uint8_t* cpos = buf + 8 + null_bytes;
+  const int n = rd_i32(cpos + 4);
+  if (n < 0 || 16 + (int64_t)null_bytes + 4 * (int64_t)n > len) return set_error(SD_ERR_INVALID, "delta positions truncated");
+  int64_t data_off = ((8 + null_bytes + 8 + 4 * (int64_t)n + 7) >> 3) << 3;   // round to nearest word
+  d = StoredDelta();
+  d.present = true;
+  d.len = len;
+  memset(&d.dev, 0, sizeof(d.dev));
+  d.dev.n = n; d.dev.enc = type_id; d.dev.nwords = null_bytes >> 3;
+  uint8_t* p = nullptr;
+  int rc = upload_bytes(s, cpos + 8, 4 * (size_t)n, 16, 0, &p);
+  if (rc) return rc;
+  d.dev.positions = reinterpret_cast<const int32_t*>(p);
+  if (null_bytes) {
+    rc = upload_bytes(s, buf + 8, (size_t)null_bytes, 8, 0, &p);
+    if (rc) return rc;
+    d.dev.nulls = reinterpret_cast<const uint64_t*>(p);
+  }
+  const uint8_t* end = buf + len;
+  int64_t body = data_off;
+  if (type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY) {
+    int dn = 0;
+    int64_t used = parse_dictionary(buf + body, end, type, &dn, &d.dict_strings);
+    if (used < 0) return set_error(SD_ERR_INVALID, "bad delta dictionary");
+    d.dev.dict_n = dn;
+    if (type != SD_STRING) {
+      const int ew = (type == SD_INT || type == SD_DATE) ? 4 : 8;
+      rc = upload_bytes(s, buf + body + 4, (size_t)ew * dn, 16, 0, &p);
+      if (rc) return rc;
+      d.dev.dict = p;
+    }
+    body += used;
+  } else if (type_id == ENC_UNCOMPRESSED) {
+    if (type == SD_STRING) { col.unsupported = "Uncompressed STRING update delta"; return 0; }
+  } else if (type_id == ENC_BOOLEAN_BITSET) {
+    if (type != SD_BOOLEAN) return set_error(SD_ERR_INVALID, "BooleanBitSet delta on a non-boolean column");
+  } else return set_error(SD_ERR_UNSUPPORTED, "RunLength-encoded update delta");
+  if (body > len) return set_error(SD_ERR_INVALID, "delta values truncated");
+  rc = upload_bytes(s, buf + body, (size_t)(len - body), 16, 0, &p);
+  if (rc) return rc;
+  d.dev.data = p;
+  return 0;
+}
+
+int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
+  if (!b || b->num_rows < 0) return set_error(SD_ERR_INVALID, "bad batch");
+  cudaSetDevice(s->device);
+  std::unique_ptr<StoredBatch> sb(new StoredBatch());
+  sb->num_rows = b->num_rows; sb->bucket_id = b->bucket_id; sb->batch_id = b->batch_id;
+  sb->cols.resize(s->schema.size());
+  for (int i = 0; i < b->ncols; i++) {
+    const int t = table_ordinals ? table_ordinals[i] : i;
+    if (t < 0 || t >= (int)s->schema.size()) return set_error(SD_ERR_INVALID, "table column %d outside the store schema", t);
+    const uint8_t* buf = reinterpret_cast<const uint8_t*>(b->col_bufs[i]);
+    if (!buf) continue;
+    StoredCol& c = sb->cols[t];
+    if (c.present) continue;   // same table column projected twice
+    int rc = upload_column(s, buf, b->col_lens[i], s->schema[t].type, s->schema[t].nullable, b->num_rows, c);
+    if (rc) return rc;
+    for (int depth = 0; depth < 2; depth++) {
+      const void* const* arr = depth == 0 ? b->delta0 : b->delta1;
+      const int64_t* lens = depth == 0 ? b->delta0_lens : b->delta1_lens;
+      if (arr && arr[i]) {
+        rc = upload_delta(s, reinterpret_cast<const uint8_t*>(arr[i]), lens[i], s->schema[t].type, c, depth);
+        if (rc) return rc;
+        sb->has_deltas = true;
+        c.fast = false;
+      }
+    }
+    // unified code space of a STRING column: base dictionary [0,n), NULL = n, then delta-only strings;
+    // delta dictionaries are translated to it so per-batch tables cover base and updated values alike
+    if (s->schema[t].type == SD_STRING && (c.delta[0].present || c.delta[1].present)) {
+      std::unordered_map<std::string, int> code;
+      for (size_t k = 0; k < c.dict_strings.size(); k++) code.emplace(c.dict_strings[k], (int)k);
+      const int base_n = c.dev.dict_n;
+      std::vector<std::string> extra;
+      for (int depth = 0; depth < 2; depth++) {
+        StoredDelta& d = c.delta[depth];
+        if (!d.present) continue;
+        std::vector<int32_t> map(d.dict_strings.size());
+        for (size_t k = 0; k < d.dict_strings.size(); k++) {
+          auto it = code.find(d.dict_strings[k]);
+          if (it == code.end()) {
+            const int nc = base_n + 1 + (int)extra.size();
+            extra.push_back(d.dict_strings[k]);
+            code.emplace(d.dict_strings[k], nc);
+            map[k] = nc;
+          } else map[k] = it->second;
+        }
+        const int32_t* dm = nullptr;
+        rc = upload_vec(s, map, 4, &dm);
+        if (rc) return rc;
+        d.dev.dict = reinterpret_cast<const uint8_t*>(dm);
+      }
+      // dict_strings becomes: base..., "" (NULL placeholder), extras...
+      if (!extra.empty()) {
+        c.dict_strings.resize(base_n);
+        c.dict_strings.push_back(std::string());
+        for (auto& e : extra) c.dict_strings.push_back(e);
+      }
+    }
+    for (int depth = 0; depth < 2; depth++) {
+      if (!c.delta[depth].present) continue;
+      std::vector<DevDelta> one(1, c.delta[depth].dev);
+      const DevDelta* dd = nullptr;
+      rc = upload_vec(s, one, 16, &dd);
+      if (rc) return rc;
+      c.dev_delta[depth] = const_cast<DevDelta*>(dd);
+    }
+    c.dev.delta0 = c.dev_delta[0];
+    c.dev.delta1 = c.dev_delta[1];
+  }
+  if (b->delete_buf) {   // [0][numBaseRows][numDeletes][positions]; the decoder walks to the buffer end
+    if (b->delete_len < 12) return set_error(SD_ERR_INVALID, "delete buffer too short");
+    const int n = (int)((b->delete_len - 12) / 4);
+    uint8_t* p = nullptr;
+    int rc = upload_bytes(s, reinterpret_cast<const uint8_t*>(b->delete_buf) + 12, 4 * (size_t)n, 16, 0, &p);
+    if (rc) return rc;
+    sb->dev_deletes = reinterpret_cast<int32_t*>(p);
+    sb->num_deletes = n;
+  }
+  if (b->stats_row && b->stats_len > 0) {
+    sb->stats.assign(reinterpret_cast<const uint8_t*>(b->stats_row), reinterpret_cast<const uint8_t*>(b->stats_row) + b->stats_len);
+    sb->stats_ncols = b->stats_ncols;
+  }
+  // ownership rule: the caller's buffers may be released when this call returns
+  SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+  s->batches.push_back(std::move(sb));
+  s->version++;
+  return 0;
+}
+
+}  // namespace sd
+
+// ---- C ABI: store ------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sd_last_error(void) { return sd::last_error_cstr(); }
+
+int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store** out) {
+  if (!out || ncols < 0 || (ncols > 0 && !schema)) return sd::set_error(SD_ERR_INVALID, "sd_store_create: bad arguments");
+  int ndev = 0;
+  SD_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return sd::set_error(SD_ERR_INVALID, "sd_store_create: device %d of %d", device, ndev);
+  SD_CUDA(cudaSetDevice(device));
+  sd_store* s = new sd_store();
+  s->device = device;
+  s->arena.device = device;
+  s->schema.assign(schema, schema + ncols);
+  cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete s; return sd::set_error(SD_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return 0;
+}
+
+int sd_store_put_batch(sd_store* s, const sd_batch* b) {
+  if (!s || !b) return sd::set_error(SD_ERR_INVALID, "sd_store_put_batch: null argument");
+  if (b->ncols != (int)s->schema.size()) return sd::set_error(SD_ERR_INVALID, "sd_store_put_batch: batch has %d columns, table schema %zu", b->ncols, s->schema.size());
+  return sd::store_put(s, b, nullptr);
+}
+
+int sd_store_num_batches(sd_store* s, int64_t* out) { *out = (int64_t)s->batches.size(); return 0; }
+int sd_store_bytes(sd_store* s, int64_t* out) { *out = (int64_t)s->arena.used; return 0; }
+
+void sd_store_destroy(sd_store* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+}
+
+int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id, int64_t* batch_id) {
+  if (!s || batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
+  const sd::StoredBatch& b = *s->batches[batch_index];
+  if (num_rows) *num_rows = b.num_rows;
+  if (bucket_id) *bucket_id = b.bucket_id;
+  if (batch_id) *batch_id = b.batch_id;
+  return 0;
+}
+
+int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, void* out, int64_t cap, int64_t* out_len) {
+  if (!s || batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
+  const sd::StoredBatch& b = *s->batches[batch_index];
+  if (table_col < 0 || table_col >= (int)b.cols.size() || !b.cols[table_col].present || !b.cols[table_col].dev_base)
+    return sd::set_error(SD_ERR_INVALID, "column %d not resident", table_col);
+  const sd::StoredCol& c = b.cols[table_col];
+  *out_len = c.len;
+  if (cap < c.len) return sd::set_error(SD_ERR_OVERFLOW, "buffer too small");
+  SD_CUDA(cudaSetDevice(s->device));
+  SD_CUDA(cudaMemcpy(out, c.dev_base, (size_t)c.len, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

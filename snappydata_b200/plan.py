@@ -185,3 +185,7 @@ def c1_plan() -> PlanDesc:
     b.filter(c1 > b.lit(SqlType.INT))
     b.count()
     return b.build()
+
+
+# plans compiled ahead of time into libsnappygpu.so (every other plan goes through NVRTC at plan time)
+AOT_PLANS = {"c1": c1_plan, "q6": q6_plan, "q1": q1_plan}

@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H Q1 / Q6 lineitem scan + filter + partial aggregate on N B200s vs the CPU path.
+
+Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` (under torchrun for
+N > 1) prints ONE JSON line on rank 0.  A "step" is one execution of the query over the whole
+(sharded) column table:
+
+  value   whole-job rows/s with the ColumnBatches resident in HBM (sd_plan_scan_store), including the
+          partial-row read-back and the cross-rank exchange + final merge
+  e2e     the same query through the reference-facing C-ABI with HOST buffers: every step submits every
+          ColumnBatch from pinned host memory (sd_batch_submit copies it to the device inside the call)
+          and reads the partial rows back
+  roofline.achieved   algorithmic bytes (40 B/row Q1, 28 B/row Q6, computed from the actual
+          buffers) / device time of the scan kernel (CUDA events around the launches, on the launching stream)
+  cpu_baseline        the reference-algorithm CPU restatement (oracle/, generated-loop layer) timed on this
+          box's host cores over a bounded sample of the same ColumnBatch bytes
+
+`--impl reference` times that CPU restatement as the reference arm (the reference itself is Scala on a
+Spark fork whose sources are absent and there is no JVM here: DESIGN.md).
+
+Workload: Q1 over an SF-100 lineitem column table (600,037,902 rows, 200,000-row batches, 24.0 GB of
+scanned column bytes), sharded by contiguous batch ranges over the ranks (strong scaling); Q6 over SF-10
+is measured in the same run and reported under "also".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SF100_ROWS = 600_037_902
+SF10_ROWS = 59_986_052
+ROWS_PER_BATCH = 200_000
+NBUCKETS = 128
+SEED_Q1, SEED_Q6 = 1, 6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="q1", choices=["q1", "q6"])
+    ap.add_argument("--rows", type=int, default=0, help="override total table rows (default SF-100 for q1, SF-10 for q6)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def shard_batches(total_rows, rank, world):
+    nb = (total_rows + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH
+    lo, hi = nb * rank // world, nb * (rank + 1) // world
+    first_row = lo * ROWS_PER_BATCH
+    nrows = min(total_rows, hi * ROWS_PER_BATCH) - first_row
+    return first_row, max(0, nrows), hi - lo
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    """`--impl reference`: the reference-algorithm CPU restatement (generated-loop layer of the oracle) over a
+    bounded sample of the workload, all host threads, one partition per thread like Spark local[N]."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from snappydata_b200 import lineitem, plan as P
+    q1 = args.workload == "q1"
+    desc = P.q1_plan() if q1 else P.q6_plan()
+    total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
+    cores = os.cpu_count() or 1
+    nsample = max(cores, min(64, (total + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH))
+    batches = lineitem.gen_table(total, ROWS_PER_BATCH, SEED_Q1 if q1 else SEED_Q6, NBUCKETS,
+                                 lineitem.Q1_COLUMN_MASK if q1 else lineitem.Q6_COLUMN_MASK, batches=range(nsample))
+    ba = oracle.BatchArray(batches, desc.table_cols)
+    rows = sum(b.num_rows for b in batches)
+
+    def step():
+        if q1:
+            oracle.run_q1(ba, P.Q1_LITERALS[0], cores)
+        else:
+            oracle.run_q6(ba, P.Q6_LITERALS, cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = rows * args.steps / dt
+    sample = f"first {nsample} batches ({rows} rows) of the {total}-row table per step"
+    print(json.dumps({
+        "impl": "reference", "metric": metric_name(q1), "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(q1, total, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference-algorithm CPU restatement (oracle/scan_oracle.c, generated-loop layer); the reference itself "
+                "cannot run here (Scala on an absent Spark fork, no JVM)"}))
+
+
+def metric_name(q1):
+    return ("rows/sec, TPC-H Q1 lineitem scan+filter+group-by aggregate over a column table" if q1
+            else "rows/sec, TPC-H Q6 lineitem scan+filter+aggregate over a column table")
+
+
+def workload_config(q1, total, gpus):
+    return {"workload": ("TPC-H Q1 on SF-100 lineitem column table" if q1 else "TPC-H Q6 on SF-10 lineitem column table"),
+            "rows": total, "rows_per_batch": ROWS_PER_BATCH, "bytes_per_row": 40 if q1 else 28,
+            "sharding": f"contiguous batch ranges over {gpus} rank(s), one partition per GPU",
+            "l2": "inputs per step (>= 3 GB per GPU) are larger than the 126 MB L2; no flush needed",
+            "literals": "Q1 cutoff 1997-10-02; Q6 1994-01-01, 0.05..0.07, 24"}
+
+
+# ---------------------------------------------------------------------------------------------------
+class QueryRun:
+    """One query over this rank's shard: resident store, plan, timing helpers."""
+
+    def __init__(self, api, torch, dist, q1, total_rows, rank, world, device):
+        from snappydata_b200 import capi, lineitem, plan as P
+        self.api, self.torch, self.dist, self.q1, self.rank, self.world = api, torch, dist, q1, rank, world
+        self.capi = capi
+        self.desc = P.q1_plan() if q1 else P.q6_plan()
+        self.lits = P.Q1_LITERALS if q1 else P.Q6_LITERALS
+        self.total_rows = total_rows
+        first_row, nrows, _ = shard_batches(total_rows, rank, world)
+        self.local_rows = nrows
+        self.store = capi.Store(api, lineitem.LINEITEM_SCHEMA, device)
+        self.store.gen_lineitem(first_row, nrows, ROWS_PER_BATCH, NBUCKETS, SEED_Q1 if q1 else SEED_Q6,
+                                lineitem.Q1_COLUMN_MASK if q1 else lineitem.Q6_COLUMN_MASK)
+        self.plan = capi.Plan(api, self.desc)
+        self.plan.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.launches = 0
+        self.kernel_ns = 0
+        self.algo_bytes = 0
+        self.final = None
+        if world > 1:
+            self.gather_in = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+            self.gather_out = torch.zeros(4096 * world, dtype=torch.uint8, device="cuda")
+            self.pin = torch.zeros(4096, dtype=torch.uint8).pin_memory()
+            self.pin_out = torch.zeros(4096 * world, dtype=torch.uint8).pin_memory()
+
+    def exchange_and_merge(self, raw):
+        """The one exchange of the query: all-gather of the partial rows over NCCL, then the final merge
+        (SnappyHashAggregateExec(Final) / CollectAggregateExec) -- identical on every rank."""
+        torch = self.torch
+        if self.world > 1:
+            n = len(raw)
+            assert n + 8 <= 4096
+            self.pin[:8] = torch.frombuffer(bytearray(n.to_bytes(8, "little")), dtype=torch.uint8)
+            if n:
+                self.pin[8:8 + n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            self.gather_in.copy_(self.pin, non_blocking=True)
+            self.dist.all_gather_into_tensor(self.gather_out, self.gather_in)
+            self.pin_out.copy_(self.gather_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            allb = bytes(self.pin_out.numpy())
+            raw = b"".join(allb[r * 4096 + 8: r * 4096 + 8 + int.from_bytes(allb[r * 4096: r * 4096 + 8], "little")]
+                           for r in range(self.world))
+        self.final = self.capi.final_merge(self.api, self.desc, raw)
+        return len(raw)
+
+    def step_resident(self):
+        p = self.plan
+        p.reset().set_literals(self.lits)
+        p.scan_store(self.store)
+        raw = p.finish_raw()
+        m = p.metrics()
+        self.launches += m["kernelLaunches"]
+        self.kernel_ns += m["aggTimeNs"]
+        self.algo_bytes += m["algorithmicBytes"]
+        return self.exchange_and_merge(raw)
+
+    # ---- end to end: host buffers -> sd_batch_submit ---------------------------------------------
+    def prepare_host_copy(self):
+        """Pinned host copy of this rank's ColumnBatch buffers + pre-marshalled sd_batch structs."""
+        torch, capi = self.torch, self.capi
+        from snappydata_b200.column_format import ColumnBatch
+        cols = self.desc.table_cols
+        self.host_keep, self.marshalled, self.h2d_bytes = [], [], 0
+        nb = self.store.num_batches()
+        sizes = []
+        for i in range(nb):
+            for c in cols:
+                ln = C.c_int64()
+                self.api.lib.sdx_store_get_buffer(self.store.h, i, c, None, 0, C.byref(ln))
+                sizes.append(ln.value)
+        total = sum((s + 63) // 64 * 64 for s in sizes)
+        arena = torch.empty(max(total, 64), dtype=torch.uint8).pin_memory()
+        base = arena.data_ptr()
+        off, k = 0, 0
+        for i in range(nb):
+            nrows, bucket, bid = self.store.batch_info(i)
+            bufs = [None] * 16
+            for c in cols:
+                ln = C.c_int64()
+                self.api.check(self.api.lib.sdx_store_get_buffer(self.store.h, i, c, base + off, sizes[k], C.byref(ln)))
+                bufs[c] = arena[off: off + sizes[k]].numpy()
+                self.h2d_bytes += sizes[k]
+                off += (sizes[k] + 63) // 64 * 64
+                k += 1
+            cb = ColumnBatch(num_rows=nrows, columns=bufs, stats=None, batch_id=bid, bucket_id=bucket)
+            self.marshalled.append(capi.MarshalledBatch(cb, cols))
+        self.host_keep.append(arena)
+        self.e2e_plan = capi.Plan(self.api, self.desc)
+        self.e2e_plan.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def step_e2e(self):
+        p = self.e2e_plan
+        p.reset().set_literals(self.lits)
+        sub, h = self.api.batch_submit, p.h
+        for mb in self.marshalled:
+            rc = sub(h, C.byref(mb.c))
+            if rc:
+                self.api.check(rc)
+        raw = p.finish_raw()
+        self.e2e_launches = p.metrics()["kernelLaunches"]
+        return self.exchange_and_merge(raw)
+
+    def cpu_baseline(self, seconds):
+        """Generated-loop restatement over a bounded sample of this rank's host copy, all host threads."""
+        from oracle import oracle
+        cores = os.cpu_count() or 1
+        nsample = min(len(self.marshalled), max(cores, 64))
+        ba = oracle.BatchArray.__new__(oracle.BatchArray)
+        ba.m = self.marshalled[:nsample]
+        ba.arr = (self.capi.sd_batch * nsample)(*[mb.c for mb in ba.m])
+        ba.n = nsample
+        rows = sum(mb.c.num_rows for mb in ba.m)
+        fn = (lambda: oracle.run_q1(ba, self.lits[0], cores)) if self.q1 else (lambda: oracle.run_q6(ba, self.lits, cores))
+        res = fn()
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            res = fn()
+            reps += 1
+            if time.perf_counter() - t0 > seconds or reps >= 200:
+                break
+        dt = time.perf_counter() - t0
+        return {"value": rows * reps / dt, "unit": "rows/s", "cores": cores, "kind": "port",
+                "sample": f"first {nsample} batches ({rows} rows) of rank 0's shard x {reps} passes in {dt:.1f} s"}, res
+
+
+def timed_steps(torch, dist, world, fn, warmup, steps):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from snappydata_b200 import capi
+    api = capi.product_api()
+    api.check(api.init(local_rank))
+
+    q1 = args.workload == "q1"
+    total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
+    main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed_steps(torch, dist, world, main_run.step_resident, args.warmup, args.steps)
+    clocks = sampler.stop() if sampler else None
+    # per-launch figures over warm-up + timed steps (same kernel, same data every step)
+    nsteps_all = args.warmup + args.steps
+    kernel_ms = main_run.kernel_ns / 1e6 / max(1, main_run.launches)
+    algo_per_launch = main_run.algo_bytes / max(1, main_run.launches)
+    launches_timed = main_run.launches * args.steps // nsteps_all
+    d2h_step = 0
+    final_rows = main_run.final
+
+    out = {"metric": metric_name(q1), "value": total * args.steps / (ms / 1e3), "unit": "rows/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(q1, total, world), "gpu_launches": launches_timed, "clocks": clocks}
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_per_launch / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "traffic": None, "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
+                       "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": algo_per_launch,
+                       "note": "per rank (rank 0); one launch scans the rank's whole shard"}
+    out["hbm_gbs_whole_job"] = total * (40 if q1 else 28) / (ms / args.steps / 1e3) / 1e9
+
+    if not args.no_e2e:
+        main_run.prepare_host_copy()
+        e_steps = max(1, args.e2e_steps)
+        ems = timed_steps(torch, dist, world, main_run.step_e2e, 1, e_steps)
+        out["e2e"] = {"value": total * e_steps / (ems / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.h2d_bytes,
+                      "d2h_bytes_per_step": 4096 if world > 1 else 1024, "ms_per_step": ems / e_steps, "steps": e_steps,
+                      "gpu_launches_per_step": main_run.e2e_launches,
+                      "note": "per-rank bytes; every ColumnBatch submitted from pinned host memory through sd_batch_submit each step"}
+        e2e_final = main_run.final
+        if rank == 0 and not args.no_cpu:
+            cb, res = main_run.cpu_baseline(args.cpu_seconds)
+            out["cpu_baseline"] = cb
+    if rank == 0:
+        out["result_check"] = {"groups": len(final_rows), "first_row": [x.decode() if isinstance(x, bytes) else x for x in final_rows[0]] if final_rows else None}
+
+    # ---- the other headline query in the same run --------------------------------------------------
+    if not args.no_also:
+        del main_run
+        torch.cuda.empty_cache()
+        oq1 = not q1
+        ototal = SF100_ROWS if oq1 else SF10_ROWS
+        other = QueryRun(api, torch, dist, oq1, ototal, rank, world, local_rank)
+        oms = timed_steps(torch, dist, world, other.step_resident, args.warmup, args.steps)
+        okms = other.kernel_ns / 1e6 / max(1, other.launches)
+        oalgo = other.algo_bytes / max(1, other.launches)
+        out["also"] = {"workload": workload_config(oq1, ototal, world)["workload"], "value": ototal * args.steps / (oms / 1e3),
+                       "unit": "rows/s", "ms_per_step": oms / args.steps,
+                       "roofline": {"bound": "hbm", "achieved": oalgo / (okms / 1e3) / 1e9 if okms > 0 else 0.0, "peak": peak,
+                                    "unit": "GB/s", "frac": (oalgo / (okms / 1e3) / 1e9 / peak) if okms > 0 else 0.0,
+                                    "kernel_ms_per_launch": okms}}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

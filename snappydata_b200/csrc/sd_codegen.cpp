@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -467,7 +468,7 @@ struct Gen {
         slt << NL << " ? " << ident << " : " << (f ? "sd::f2u((double)" + V + ")" : "(uint64_t)(int64_t)" + V) << ";\n";
       }
     }
-    sig << ";mode=" << p.mode << ";tables=" << p.tables.size();
+    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0);
     p.signature = sig.str();
     char hbuf[32];
     snprintf(hbuf, sizeof(hbuf), "%016llx", (unsigned long long)std::hash<std::string>()(p.signature));
@@ -484,7 +485,8 @@ struct Gen {
     o << "struct " << p.struct_name << " {\n";
     o << "  static constexpr int NC = " << nc << ";\n  static constexpr int NSLOT = " << ns << ";\n";
     o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : "sd::MODE_NOKEY") << ";\n";
-    o << "  static constexpr int MIN_CTAS = 2;\n";
+    o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
+    o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
     o << "0; }\n";
@@ -530,6 +532,18 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err) {
   if (out.aggs.empty() && out.keys.empty())
     { err = "projection-only plans (no aggregate) are not implemented in the GPU path yet"; return SD_ERR_UNSUPPORTED; }
   out.mode = out.keys.empty() ? MODE_NOKEY : MODE_GROUPS;
+  // tile shape: tunable per plan; SD_TUNE_RPT / SD_TUNE_MIN_CTAS override (variants then go through NVRTC)
+  {
+    int row_bytes = 0;
+    for (int k : out.kinds) row_bytes += (k == K_I64 || k == K_F64) ? 8 : (k == K_I32 || k == K_F32) ? 4 : (k == K_I16 || k == K_CODE) ? 2 : 1;
+    out.rpt = 4;
+    out.min_ctas = 2;
+    (void)row_bytes;
+    if (const char* e = getenv("SD_TUNE_RPT")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) out.rpt = v; }
+    if (const char* e = getenv("SD_TUNE_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) out.min_ctas = v; }
+    out.stages = 1;
+    if (const char* e = getenv("SD_TUNE_STAGES")) out.stages = atoi(e) > 0 ? 1 : 0;
+  }
   rc = g.build_slots();
   if (rc) return rc;
   return g.generate();

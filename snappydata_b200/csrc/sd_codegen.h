@@ -55,6 +55,9 @@ struct PlanSpec {
   std::vector<AggMap> agg_map;
   int rows_slot = -1;                // COUNT(*)-like slot that tells which groups exist
   int mode = 0;                      // MODE_NOKEY | MODE_GROUPS
+  int rpt = 4;                       // rows per thread per tile (2, 4, 8)
+  int min_ctas = 2;                  // __launch_bounds__ min CTAs per SM (= target CTAs per SM)
+  int stages = 1;                    // > 0: staged fast path (producer warp + cp.async.bulk ring); 0: direct loads
   std::string signature;             // canonical text of everything the generated code depends on
   std::string struct_name;           // Plan_<hash of signature>
   std::string source;                // the generated PLAN struct (CUDA C++)

@@ -29,19 +29,24 @@ enum : int32_t { ENC_UNCOMPRESSED = 0, ENC_RUN_LENGTH = 1, ENC_DICTIONARY = 2, E
 enum : int32_t { K_I8 = 0, K_I16 = 1, K_I32 = 2, K_I64 = 3, K_F32 = 4, K_F64 = 5, K_BOOL = 6, K_CODE = 7 };
 
 // ---- tiling ----------------------------------------------------------------------------------
-// A CTA of THREADS threads processes tiles of THREADS*RPT rows; thread t owns the row pairs
-// tile + u*2*THREADS + 2*t + {0,1}, u < RPT/2, so that every per-column load instruction is a fully
-// coalesced 16/8/4/2-byte-per-lane vector load.  A work item ("chunk") is CHUNK_TILES tiles of one
-// batch.
+// A CTA of THREADS threads processes tiles of THREADS*RPT rows (RPT = rows per thread per tile, a per-plan
+// tunable: 2, 4 or 8); thread t owns the row pairs tile + u*2*THREADS + 2*t + {0,1}, u < RPT/2, so that
+// every per-column load instruction is a fully coalesced 16/8/4/2-byte-per-lane vector load.  A work item
+// ("chunk") is CHUNK_ROWS rows of one batch.
 constexpr int THREADS = 256;
-constexpr int RPT = 4;                        // rows per thread per tile
-constexpr int TILE_ROWS = THREADS * RPT;      // 1024
-constexpr int CHUNK_TILES = 8;
-constexpr int CHUNK_ROWS = TILE_ROWS * CHUNK_TILES;   // 8192
-constexpr int TILE_WORDS = TILE_ROWS / 64;    // 16 null words per tile
+constexpr int CHUNK_ROWS = 8192;
+constexpr int NULL_PREFIX_ROWS = 512;         // granularity of the host-computed "nulls before" prefix
+constexpr int NULL_PREFIX_WORDS = NULL_PREFIX_ROWS / 64;
+constexpr int MAX_RPT = 8;
+
+// bytes one row of a column occupies in a stage of the shared-memory ring (K_CODE: room for int32 indexes)
+constexpr int kind_stage_width(int k) { return (k == K_I64 || k == K_F64) ? 8 : (k == K_I32 || k == K_F32 || k == K_CODE) ? 4 : (k == K_I16) ? 2 : 1; }
+constexpr int MAX_STAGES = 12;
 
 // bytes of TileSmem<PLAN> for a plan with nc scan columns (kept in sync with sd_kernels.cuh)
-constexpr int tile_smem_bytes(int nc) { return (TILE_ROWS / 32) * 4 + (nc > 0 ? nc : 1) * ((TILE_ROWS / 32) * 4 + TILE_WORDS * 4 + 16); }
+constexpr int tile_smem_bytes(int nc, int rpt) {
+  return (THREADS * rpt / 32) * 4 + (nc > 0 ? nc : 1) * ((THREADS * rpt / 32) * 4 + (THREADS * rpt / 64) * 4 + 16);
+}
 
 constexpr int MAX_LITERALS = 64;
 constexpr int MAX_KEYS = 4;
@@ -96,6 +101,12 @@ struct Literals {
 // aggregation strategy of a generated plan struct
 enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1 };
 
+// where the dense [group][slot] table of a MODE_GROUPS launch lives (chosen per launch from its size):
+//   TABLE_PRIVATE        one private copy per thread in shared memory, no atomics (few groups: TPC-H Q1)
+//   TABLE_SHARED_ATOMIC  one copy per CTA in shared memory, shared-memory atomics
+//   TABLE_GLOBAL_ATOMIC  the running result in global memory, global atomics (RED.ADD.F64 is native)
+enum : int32_t { TABLE_PRIVATE = 0, TABLE_SHARED_ATOMIC = 1, TABLE_GLOBAL_ATOMIC = 2 };
+
 // accumulator slot operations; every slot is 8 bytes
 enum : int32_t { SLOT_ADD_F64 = 0, SLOT_ADD_I64 = 1, SLOT_MIN_I64 = 2, SLOT_MAX_I64 = 3, SLOT_MIN_F64 = 4, SLOT_MAX_F64 = 5 };
 
@@ -108,7 +119,10 @@ struct ScanArgs {
   uint64_t* result;               // [ngroups * NSLOT] running result (combined into, not overwritten)
   unsigned int* ticket;           // CTA completion counter (reset by the last CTA)
   unsigned long long* counters;   // [0] rows scanned, [1] rows that passed the filter
-  int32_t ngroups;                // group slots of the private tables (1 without keys)
+  int32_t ngroups;                // group slots of the dense group table (1 without keys)
+  int32_t table_mode;             // TABLE_PRIVATE | TABLE_SHARED_ATOMIC | TABLE_GLOBAL_ATOMIC
+  int32_t ring_off;               // byte offset of [mbarriers][stage ring] in dynamic shared memory
+  int32_t nstages;                // stages of the ring actually allocated (<= MAX_STAGES)
   int32_t radix[MAX_KEYS];        // group index = ((g0 * radix[1] + g1) * radix[2] + g2) ...
   // projection mode
   uint8_t* out_rows;              // projected output (PROJECT mode)

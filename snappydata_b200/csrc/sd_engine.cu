@@ -407,8 +407,11 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       for (int ti = 0; ti < nt; ti++) {
         const TableSpec& ts = sp.tables[ti];
         const StoredCol& sc = sb.cols[sb.positional ? ts.col : sp.cols[ts.col].table_ordinal];
-        const int n = sc.dev.dict_n;                         // NULL code
-        const int ncodes = std::max((int)sc.dict_strings.size(), n + 1);
+        const int n = sc.dev.dict_n;                         // NULL code of a nullable column
+        const bool nullable = sp.cols[ts.col].nullable != 0;
+        // codes: [0,n) base dictionary; n = NULL (nullable columns) or an unused placeholder when update
+        // deltas appended strings; (n, ...) strings that occur only in update deltas
+        const int ncodes = std::max((int)sc.dict_strings.size(), nullable ? n + 1 : n);
         while (aux.size() % 4) aux.push_back(0);
         const int32_t off = (int32_t)(aux.size() - base);
         memcpy(aux.data() + base + 4 * (size_t)ti, &off, 4);
@@ -421,7 +424,7 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
         } else {
           for (int code = 0; code < ncodes; code++) {
             const bool isnull = code == n || code >= (int)sc.dict_strings.size();
-            const int32_t id = isnull ? key_null(p, ts.key) : key_id(p, ts.key, sc.dict_strings[code]);
+            const int32_t id = isnull ? (nullable ? key_null(p, ts.key) : 0) : key_id(p, ts.key, sc.dict_strings[code]);
             aux.insert(aux.end(), reinterpret_cast<const uint8_t*>(&id), reinterpret_cast<const uint8_t*>(&id) + 4);
           }
         }
@@ -464,10 +467,32 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     ngroups *= radix[k];
   }
   const size_t ne = (size_t)ngroups * ns;
-  size_t smem = p->kernel.tile_smem + (sp.mode == MODE_GROUPS ? ne * THREADS * 8 : (size_t)std::max(ns, 1) * (THREADS / 32) * 8);
-  if ((int)smem > p->smem_optin)
-    return set_error(SD_ERR_UNSUPPORTED, "group-by needs %zu bytes of per-CTA shared memory for %d groups x %d slots (limit %d); "
-                     "high-cardinality hash aggregation is not in the GPU path yet", smem, ngroups, ns, p->smem_optin);
+  // where the dense group table lives: per-thread private copies when they fit, one shared-memory copy
+  // per CTA with atomics while that fits, else global atomics on the running result.  What is left of the
+  // SM's shared memory (per target CTA) becomes the ring of the staged fast path.
+  const size_t tile_smem = p->kernel.tile_smem;
+  const int target_ctas = std::max(1, sp.min_ctas);
+  const size_t budget = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
+  const size_t ring_fixed = 2 * MAX_STAGES * 8;
+  const size_t min_ring = p->kernel.staged ? ring_fixed + 2 * p->kernel.stage_bytes + 128 : 0;
+  int table_mode = TABLE_PRIVATE;
+  size_t table_bytes = (size_t)std::max(ns, 1) * (THREADS / 32) * 8;
+  if (sp.mode == MODE_GROUPS) {
+    const size_t priv = ne * THREADS * 8, shared = ne * 8;
+    if (tile_smem + priv + min_ring <= budget) { table_mode = TABLE_PRIVATE; table_bytes = priv; }
+    else if (shared <= 64 * 1024 && tile_smem + shared + min_ring <= budget) { table_mode = TABLE_SHARED_ATOMIC; table_bytes = shared; }
+    else { table_mode = TABLE_GLOBAL_ATOMIC; table_bytes = 64; }
+  }
+  size_t ring_off = (tile_smem + table_bytes + 127) & ~size_t(127);
+  int nstages = 0;
+  size_t smem = ring_off;
+  if (p->kernel.staged) {
+    if (ring_off + min_ring > (size_t)p->smem_optin) return set_error(SD_ERR_UNSUPPORTED, "plan does not fit the shared-memory ring (%zu bytes per stage)", p->kernel.stage_bytes);
+    const size_t avail = std::max(budget, ring_off + min_ring) - ring_off - ring_fixed;
+    nstages = (int)std::min<size_t>(MAX_STAGES, avail / p->kernel.stage_bytes);
+    if (const char* e = getenv("SD_TUNE_NSTAGES")) { int v = atoi(e); if (v >= 2 && v <= nstages) nstages = v; }
+    smem = ring_off + ring_fixed + (size_t)nstages * p->kernel.stage_bytes;
+  }
   if (!p->result_init) {
     int rc = init_result(p, ngroups);
     if (rc) return rc;
@@ -488,7 +513,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   }
   const int occ = p->max_ctas_per_sm;
   const int grid = std::min(total_chunks, p->num_sms * occ);
-  if ((size_t)grid * ne > p->partials_cap) {
+  if (table_mode != TABLE_GLOBAL_ATOMIC && (size_t)grid * ne > p->partials_cap) {
     if (p->d_partials) cudaFree(p->d_partials);
     p->partials_cap = (size_t)grid * ne * 2;
     SD_CUDA(cudaMalloc(&p->d_partials, p->partials_cap * 8));
@@ -504,6 +529,9 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.ticket = p->d_ticket;
   args.counters = p->d_counters;
   args.ngroups = ngroups;
+  args.table_mode = table_mode;
+  args.ring_off = (int32_t)ring_off;
+  args.nstages = nstages;
   memcpy(args.radix, radix, sizeof(radix));
   for (size_t i = 0; i < p->lits.size(); i++) {
     args.lits.i[i] = p->lits[i].i;

@@ -31,14 +31,17 @@ struct KernelEntry {
   const void* func;      // &scan_aggregate_kernel<PLAN> (runtime API launch)
   void* drv_func;        // CUfunction for NVRTC-compiled plans
   size_t tile_smem;      // sizeof(TileSmem<PLAN>) rounded up to 16
+  int staged = 0;        // PLAN::STAGES > 0: producer warp + shared-memory ring (block = THREADS + 32)
+  size_t stage_bytes = 0;
   std::string origin;    // "aot" | "jit"
 };
 std::vector<KernelEntry>& kernel_registry();
 struct AotRegistrar {
-  AotRegistrar(const char* signature, const void* func, size_t tile_smem);
+  AotRegistrar(const char* signature, const void* func, size_t tile_smem, int staged, size_t stage_bytes);
 };
 // set the dynamic shared-memory limit and query CTAs/SM; launch (runtime API for AOT, driver API for JIT)
 int kernel_prepare(const KernelEntry& k, size_t smem, int* ctas_per_sm);
+inline int kernel_block_threads(const KernelEntry& k) { return THREADS + (k.staged ? 32 : 0); }
 int kernel_launch(const KernelEntry& k, int grid, size_t smem, cudaStream_t stream, void** args);
 // NVRTC path (sd_jit.cpp): compile `spec.source` against the embedded kernel headers.
 int jit_compile(const PlanSpec& spec, int device, KernelEntry& out);

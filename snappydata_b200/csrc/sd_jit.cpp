@@ -82,26 +82,29 @@ const char* drv_err(CUresult r) {
 int kernel_prepare(const KernelEntry& k, size_t smem, int* ctas_per_sm) {
   if (k.func) {
     SD_CUDA(cudaFuncSetAttribute(k.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k.func, THREADS, smem));
+    // ask for the largest shared-memory carveout so that several CTAs with private group tables fit per SM
+    SD_CUDA(cudaFuncSetAttribute(k.func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k.func, kernel_block_threads(k), smem));
     return 0;
   }
   Dyn& d = dyn();
   if (!d.ok || !k.drv_func) return set_error(SD_ERR_CUDA, "no kernel for this plan: %s", d.why.c_str());
   CUresult r = d.FuncSetAttribute((CUfunction)k.drv_func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
   if (r != CUDA_SUCCESS) return set_error(SD_ERR_CUDA, "cuFuncSetAttribute: %s", drv_err(r));
-  r = d.OccupancyMaxActiveBlocks(ctas_per_sm, (CUfunction)k.drv_func, THREADS, smem);
+  d.FuncSetAttribute((CUfunction)k.drv_func, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
+  r = d.OccupancyMaxActiveBlocks(ctas_per_sm, (CUfunction)k.drv_func, kernel_block_threads(k), smem);
   if (r != CUDA_SUCCESS) return set_error(SD_ERR_CUDA, "cuOccupancyMaxActiveBlocksPerMultiprocessor: %s", drv_err(r));
   return 0;
 }
 
 int kernel_launch(const KernelEntry& k, int grid, size_t smem, cudaStream_t stream, void** args) {
   if (k.func) {
-    SD_CUDA(cudaLaunchKernel(k.func, dim3(grid), dim3(THREADS), args, smem, stream));
+    SD_CUDA(cudaLaunchKernel(k.func, dim3(grid), dim3(kernel_block_threads(k)), args, smem, stream));
     return 0;
   }
   Dyn& d = dyn();
   if (!d.ok || !k.drv_func) return set_error(SD_ERR_CUDA, "no kernel for this plan: %s", d.why.c_str());
-  CUresult r = d.LaunchKernel((CUfunction)k.drv_func, grid, 1, 1, THREADS, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+  CUresult r = d.LaunchKernel((CUfunction)k.drv_func, grid, 1, 1, kernel_block_threads(k), 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return set_error(SD_ERR_CUDA, "cuLaunchKernel: %s", drv_err(r));
   return 0;
 }
@@ -146,8 +149,11 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out) {
   out.signature = spec.signature;
   out.func = nullptr;
   out.drv_func = (void*)fn;
-  out.tile_smem = ((size_t)tile_smem_bytes((int)spec.cols.size()) + 15) & ~size_t(15);
+  out.tile_smem = ((size_t)tile_smem_bytes((int)spec.cols.size(), spec.rpt) + 15) & ~size_t(15);
   out.origin = "jit";
+  out.staged = spec.stages > 0 ? 1 : 0;
+  out.stage_bytes = 0;
+  for (int k : spec.kinds) out.stage_bytes += (size_t)THREADS * spec.rpt * kind_stage_width(k);
   return 0;
 }
 

@@ -86,6 +86,26 @@ __device__ __forceinline__ uint64_t slot_combine(int op, uint64_t a, uint64_t b)
   }
 }
 
+// atomic version (shared or global address): used when the group table is shared by many threads
+__device__ __forceinline__ void slot_atomic(int op, uint64_t* p, uint64_t v) {
+  switch (op) {
+    case SLOT_ADD_F64: if (v != 0ull) atomicAdd(reinterpret_cast<double*>(p), u2f(v)); break;   // x + (+0.0) == x for every running sum
+    case SLOT_ADD_I64: if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); break;
+    case SLOT_MIN_I64: atomicMin(reinterpret_cast<long long*>(p), (long long)v); break;
+    case SLOT_MAX_I64: atomicMax(reinterpret_cast<long long*>(p), (long long)v); break;
+    default: {   // NaN-aware double min / max: CAS loop
+      unsigned long long* a = reinterpret_cast<unsigned long long*>(p);
+      unsigned long long old = *a, assumed;
+      do {
+        assumed = old;
+        const unsigned long long want = slot_combine(op, assumed, v);
+        if (want == assumed) break;
+        old = atomicCAS(a, assumed, want);
+      } while (old != assumed);
+    }
+  }
+}
+
 // ---- loads ------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T ld_at(const uint8_t* base, int64_t k) {
   return *reinterpret_cast<const T*>(base + k * (int64_t)sizeof(T));
@@ -145,7 +165,7 @@ __device__ __forceinline__ typename KindT<KIND>::T decode_delta_value(const DevD
 template <class PLAN, int C>
 struct ColRegs {
   typedef typename KindT<PLAN::kind(C)>::T T;
-  T v[RPT];
+  T v[PLAN::RPT];
   uint32_t nullmask;   // bit r: row r of this thread is NULL in column C
 };
 template <class PLAN, class S> struct AllCols;
@@ -153,6 +173,8 @@ template <class PLAN, int... Cs> struct AllCols<PLAN, Seq<Cs...>> : ColRegs<PLAN
 
 template <class PLAN>
 struct TileSmem {
+  static constexpr int TILE_ROWS = THREADS * PLAN::RPT;
+  static constexpr int TILE_WORDS = TILE_ROWS / 64;
   uint32_t delbits[TILE_ROWS / 32];
   uint32_t updbits[PLAN::NC > 0 ? PLAN::NC : 1][TILE_ROWS / 32];
   int32_t wprefix[PLAN::NC > 0 ? PLAN::NC : 1][TILE_WORDS];
@@ -169,7 +191,7 @@ __device__ __forceinline__ void load_col_fast(const DevCol& col, int64_t tile_st
   constexpr int K = PLAN::kind(C);
   regs.nullmask = 0;
 #pragma unroll
-  for (int u = 0; u < RPT / 2; u++) {
+  for (int u = 0; u < PLAN::RPT / 2; u++) {
     const int64_t p = tile_start + u * 2 * THREADS + 2 * (int)threadIdx.x;   // even row index
     if (K == K_CODE) {
       if (col.enc == ENC_DICTIONARY) {
@@ -209,9 +231,11 @@ __device__ __forceinline__ void load_col_general(const DevCol& col, int tile, in
   constexpr int K = PLAN::kind(C);
   regs.nullmask = 0;
   const bool has_delta = col.delta0 != nullptr || col.delta1 != nullptr;
-  const int tile_nulls = col.tile_nulls ? col.tile_nulls[tile] : 0;
+  // nulls before this tile: host prefix per NULL_PREFIX_ROWS rows (+ the words in between for big tiles
+  // are covered because the prefix index is taken at the tile start and tiles are multiples of it)
+  const int tile_nulls = col.tile_nulls ? col.tile_nulls[tile_start / NULL_PREFIX_ROWS] : 0;
 #pragma unroll
-  for (int r = 0; r < RPT; r++) {
+  for (int r = 0; r < PLAN::RPT; r++) {
     const int li = row_in_tile(r);
     const int64_t i = tile_start + li;
     T v = (T)0;
@@ -260,13 +284,14 @@ __device__ __forceinline__ void load_col_general(const DevCol& col, int tile, in
 template <class PLAN, int C>
 __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
   const int tid = threadIdx.x;
-  if (col.nulls && tid < TILE_WORDS) {   // warp 0, lanes 0..15: exclusive scan of per-word popcounts
+  constexpr int TILE_ROWS = TileSmem<PLAN>::TILE_ROWS, TILE_WORDS = TileSmem<PLAN>::TILE_WORDS;
+  if (col.nulls && tid < TILE_WORDS) {   // warp 0, lanes 0..TILE_WORDS-1: exclusive scan of per-word popcounts
     const int w = (int)(tile_start >> 6) + tid;
     const int pc = w < col.nwords ? __popcll(col.nulls[w]) : 0;
     int inc = pc;
 #pragma unroll
     for (int d = 1; d < TILE_WORDS; d <<= 1) {
-      int t = __shfl_up_sync(0xffffu, inc, d, TILE_WORDS);
+      int t = __shfl_up_sync((TILE_WORDS >= 32 ? 0xffffffffu : ((1u << TILE_WORDS) - 1u)), inc, d, TILE_WORDS);
       if (tid >= d) inc += t;
     }
     sm.wprefix[C][tid] = inc - pc;
@@ -299,7 +324,7 @@ __device__ __forceinline__ void load_all_fast(const DevBatch<PLAN::NC>& b, int64
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void clear_upd_bits(const DevBatch<PLAN::NC>& b, TileSmem<PLAN>& sm, Seq<Cs...>) {
   const int tid = threadIdx.x;
-  if (tid < TILE_ROWS / 32) {
+  if (tid < TileSmem<PLAN>::TILE_ROWS / 32) {
     sm.delbits[tid] = 0;
     int dummy[] = {0, ((b.cols[Cs].delta0 || b.cols[Cs].delta1) ? (sm.updbits[Cs][tid] = 0, 0) : 0)...};
     (void)dummy;
@@ -324,6 +349,128 @@ __device__ __forceinline__ void fill_row(const AllCols<PLAN, Seq<Cs...>>& regs, 
   (void)dummy;
 }
 
+
+// ---- shared-memory ring fed by bulk async copies (TMA unit, SASS: UBLKCP) ---------------------------
+// A producer thread issues one cp.async.bulk per column tile; completion is tracked by an mbarrier
+// (complete_tx byte counting).  Bytes in flight are then bounded by shared memory (up to ~200 KB per
+// SM), not by registers x resident warps -- which is what a pure HBM-read-bound scan needs.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// consumer-only CTA barrier (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+
+// byte offset of column C's tile inside a stage
+template <class PLAN>
+__host__ __device__ constexpr int stage_col_off(int c) {
+  int off = 0;
+  for (int i = 0; i < c; i++) off += THREADS * PLAN::RPT * kind_stage_width(PLAN::kind(i));
+  return off;
+}
+template <class PLAN>
+struct StageInfo {
+  static constexpr int BYTES = stage_col_off<PLAN>(PLAN::NC);
+};
+
+// element width of column C in this batch (dictionary indexes are int16 or int32)
+template <class PLAN, int C>
+__device__ __forceinline__ int col_width(const DevCol& col) {
+  return PLAN::kind(C) == K_CODE ? (col.enc == ENC_DICTIONARY ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
+}
+
+template <class PLAN, int C>
+__device__ __forceinline__ void issue_col_copy(const DevCol& col, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
+  const int w = col_width<PLAN, C>(col);
+  const uint32_t bytes = ((uint32_t)(rows * w) + 15u) & ~15u;   // buffers are padded: over-reading a partial tile is safe
+  bulk_g2s(stage + stage_col_off<PLAN>(C), col.data + tile_start * w, bytes, bar);
+}
+template <class PLAN, int C>
+__device__ __forceinline__ uint32_t col_copy_bytes(const DevCol& col, int rows) {
+  return ((uint32_t)(rows * col_width<PLAN, C>(col)) + 15u) & ~15u;
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void issue_tile_copies(const DevBatch<PLAN::NC>& b, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
+  uint32_t total = 0;
+  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(b.cols[Cs], rows), 0)...};
+  (void)d0;
+  mbar_expect_tx(bar, total);
+  int d1[] = {0, (issue_col_copy<PLAN, Cs>(b.cols[Cs], tile_start, rows, stage, bar), 0)...};
+  (void)d1;
+}
+
+// consumer: registers <- stage (conflict-free: consecutive lanes read consecutive 16/8/4/2 bytes)
+template <class PLAN, int C>
+__device__ __forceinline__ void load_col_staged(const DevCol& col, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  const uint8_t* base = stage + stage_col_off<PLAN>(C);
+  regs.nullmask = 0;
+#pragma unroll
+  for (int u = 0; u < PLAN::RPT / 2; u++) {
+    const int p = u * 2 * THREADS + 2 * (int)threadIdx.x;
+    if (K == K_CODE) {
+      if (col.enc == ENC_DICTIONARY) {
+        uint32_t x = *reinterpret_cast<const uint32_t*>(base + p * 2);
+        regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
+        regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
+      } else {
+        int2 x = *reinterpret_cast<const int2*>(base + p * 4);
+        regs.v[2 * u] = (T)x.x;
+        regs.v[2 * u + 1] = (T)x.y;
+      }
+    } else if (sizeof(T) == 8) {
+      longlong2 x = *reinterpret_cast<const longlong2*>(base + p * 8);
+      regs.v[2 * u] = K == K_F64 ? (T)__longlong_as_double(x.x) : (T)x.x;
+      regs.v[2 * u + 1] = K == K_F64 ? (T)__longlong_as_double(x.y) : (T)x.y;
+    } else if (sizeof(T) == 4) {
+      int2 x = *reinterpret_cast<const int2*>(base + p * 4);
+      regs.v[2 * u] = K == K_F32 ? (T)__int_as_float(x.x) : (T)x.x;
+      regs.v[2 * u + 1] = K == K_F32 ? (T)__int_as_float(x.y) : (T)x.y;
+    } else if (sizeof(T) == 2) {
+      uint32_t x = *reinterpret_cast<const uint32_t*>(base + p * 2);
+      regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
+      regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
+    } else {
+      uint16_t x = *reinterpret_cast<const uint16_t*>(base + p);
+      regs.v[2 * u] = K == K_BOOL ? (T)((x & 0xff) == 1) : (T)(int8_t)(x & 0xff);
+      regs.v[2 * u + 1] = K == K_BOOL ? (T)((x >> 8) == 1) : (T)(int8_t)(x >> 8);
+    }
+  }
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_all_staged(const DevBatch<PLAN::NC>& b, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (load_col_staged<PLAN, Cs>(b.cols[Cs], stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
+}
+
+// which batch a work item (chunk) belongs to: last b with chunk_prefix[b] <= item
+__device__ __forceinline__ int find_batch(const int32_t* chunk_prefix, int nbatches, int item) {
+  int lo = 0, hi = nbatches;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (chunk_prefix[mid] <= item) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // context handed to the generated row functions
 struct RowCtx {
   const Literals* L;
@@ -337,39 +484,79 @@ struct RowCtx {
 // The kernel.  dynamic shared memory: [TileSmem<PLAN>] [private group tables | reduction scratch]
 // ================================================================================================
 template <class PLAN>
-__global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel(const ScanArgs args) {
+__global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::MIN_CTAS) scan_aggregate_kernel(const ScanArgs args) {
   typedef typename MakeSeq<PLAN::NC>::type ColSeq;
   constexpr int NSLOT = PLAN::NSLOT;
+  constexpr int RPT = PLAN::RPT;
+  constexpr int TILE_ROWS = THREADS * RPT;
+  constexpr int CHUNK_TILES = CHUNK_ROWS / TILE_ROWS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem<PLAN>& sm = *reinterpret_cast<TileSmem<PLAN>*>(smem_raw);
   uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(TileSmem<PLAN>) + 15) & ~size_t(15)));
   const int tid = threadIdx.x;
   const int NE = args.ngroups * NSLOT;   // entries of the group table
+  const DevBatch<PLAN::NC>* batches = reinterpret_cast<const DevBatch<PLAN::NC>*>(args.batches);
+
+  // ---- staged fast path: [full barriers][empty barriers][ring of nstages stages] -----------------------
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + args.ring_off);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint8_t* ring = smem_raw + args.ring_off + 2 * MAX_STAGES * 8;
+  const int nstages = args.nstages;
+  if (PLAN::STAGES > 0) {
+    if (tid == 0) {
+      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], THREADS / 32); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // all THREADS + 32 threads: the only CTA-wide barrier the producer warp joins
+    if (tid >= THREADS) {
+      // ---- producer warp: one lane walks the same work sequence and keeps the ring full -----------
+      if (tid == THREADS) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
+          const int bi = find_batch(args.chunk_prefix, args.nbatches, item);
+          const DevBatch<PLAN::NC>& b = batches[bi];
+          if (!(b.flags & BATCH_ALL_FAST)) continue;
+          const int chunk = item - args.chunk_prefix[bi];
+          const int num_rows = b.num_rows;
+          const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
+          const int tile0 = chunk * CHUNK_TILES, tile_end = min(tile0 + CHUNK_TILES, ntiles);
+          for (int tile = tile0; tile < tile_end; tile++) {
+            const int64_t tile_start = (int64_t)tile * TILE_ROWS;
+            const int rows = min(TILE_ROWS, num_rows - (int)tile_start);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            issue_tile_copies<PLAN>(b, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      return;
+    }
+  }
+  int c_stage = 0;
+  uint32_t c_phase = 0;
 
   // ---- accumulator init -------------------------------------------------------------------------
   uint64_t acc[NSLOT > 0 ? NSLOT : 1];
   if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
-  } else {
+  } else if (args.table_mode == TABLE_PRIVATE) {
     // private table of thread t: entry e at table[e * THREADS + t]: lanes hit distinct banks
     for (int e = 0; e < NE; e++) table[e * THREADS + tid] = slot_identity(PLAN::slot_op(e % NSLOT));
+  } else if (args.table_mode == TABLE_SHARED_ATOMIC) {
+    for (int e = tid; e < NE; e += THREADS) table[e] = slot_identity(PLAN::slot_op_rt(e % NSLOT));
+    consumer_sync();
   }
   unsigned long long n_scanned = 0, n_passed = 0;
 
   RowCtx ctx;
   ctx.L = &args.lits;
   ctx.radix = args.radix;
-  const DevBatch<PLAN::NC>* batches = reinterpret_cast<const DevBatch<PLAN::NC>*>(args.batches);
 
   // ---- persistent loop over (batch, chunk) work items, static round-robin -------------------------
   for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
-    // batch of this chunk: last b with chunk_prefix[b] <= item
-    int lo = 0, hi = args.nbatches;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (args.chunk_prefix[mid] <= item) lo = mid; else hi = mid;
-    }
+    const int lo = find_batch(args.chunk_prefix, args.nbatches, item);
     const DevBatch<PLAN::NC>& b = batches[lo];
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
@@ -387,11 +574,19 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
       for (int r = 0; r < RPT; r++) live |= (tile_start + row_in_tile(r) < num_rows ? 1u : 0u) << r;
 
       if (fast) {
-        load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
+        if (PLAN::STAGES > 0) {
+          mbar_wait(&full_bar[c_stage], c_phase);
+          load_all_staged<PLAN>(b, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // this warp holds its rows in registers now
+          if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }
+        } else {
+          load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
+        }
       } else {
-        __syncthreads();                       // previous tile's readers are done with sm
+        consumer_sync();                       // previous tile's readers are done with sm
         clear_upd_bits<PLAN>(b, sm, ColSeq());
-        __syncthreads();
+        consumer_sync();
         prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
         if (b.deletes) {                       // delete mask -> tile bitmap (enc/ColumnDeleteDecoder.scala:49-55)
           const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
@@ -401,7 +596,7 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
             atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
           }
         }
-        __syncthreads();
+        consumer_sync();
         load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
         if (b.deletes) {
 #pragma unroll
@@ -428,16 +623,22 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
           for (int s = 0; s < NSLOT; s++) acc[s] = slot_combine(PLAN::slot_op(s), acc[s], sv[s]);
         } else {
           const int g = PLAN::group(row, ctx);
-          uint64_t* t = table + (size_t)g * NSLOT * THREADS + tid;
+          if (args.table_mode == TABLE_PRIVATE) {
+            uint64_t* t = table + (size_t)g * NSLOT * THREADS + tid;
 #pragma unroll
-          for (int s = 0; s < NSLOT; s++) t[s * THREADS] = slot_combine(PLAN::slot_op(s), t[s * THREADS], sv[s]);
+            for (int s = 0; s < NSLOT; s++) t[s * THREADS] = slot_combine(PLAN::slot_op(s), t[s * THREADS], sv[s]);
+          } else {
+            uint64_t* t = (args.table_mode == TABLE_SHARED_ATOMIC ? table : args.result) + (size_t)g * NSLOT;
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) slot_atomic(PLAN::slot_op(s), t + s, sv[s]);
+          }
         }
       }
     }
   }
 
   // ---- CTA reduction (fixed order) -> partials[blockIdx] -------------------------------------------
-  __syncthreads();
+  consumer_sync();
   uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
   const int lane = tid & 31, warp = tid >> 5;
   if (PLAN::MODE == MODE_NOKEY) {
@@ -449,14 +650,16 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
       for (int d = 16; d > 0; d >>= 1) v = slot_combine(PLAN::slot_op(s), v, __shfl_xor_sync(0xffffffffu, v, d));
       if (lane == 0) scratch[s * (THREADS / 32) + warp] = v;
     }
-    __syncthreads();
+    consumer_sync();
     if (tid < NSLOT) {
       const int op = PLAN::slot_op_rt(tid);
       uint64_t v = slot_identity(op);
       for (int w = 0; w < THREADS / 32; w++) v = slot_combine(op, v, scratch[tid * (THREADS / 32) + w]);
       my_partials[tid] = v;
     }
-  } else {
+  } else if (args.table_mode == TABLE_SHARED_ATOMIC) {
+    for (int e = tid; e < NE; e += THREADS) my_partials[e] = table[e];
+  } else if (args.table_mode == TABLE_PRIVATE) {
     for (int e = warp; e < NE; e += THREADS / 32) {
       const int op = PLAN::slot_op_rt(e % NSLOT);
       uint64_t v = slot_identity(op);
@@ -478,10 +681,10 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
   // ---- last CTA combines all CTA partials in CTA order into the running result ---------------------
   __shared__ bool is_last;
   __threadfence();
-  __syncthreads();
+  consumer_sync();
   if (tid == 0) is_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
+  consumer_sync();
+  if (is_last && !(PLAN::MODE == MODE_GROUPS && args.table_mode == TABLE_GLOBAL_ATOMIC)) {
     __threadfence();
     for (int e = tid; e < NE; e += THREADS) {
       const int op = PLAN::slot_op_rt(e % NSLOT);
@@ -489,8 +692,8 @@ __global__ void __launch_bounds__(THREADS, PLAN::MIN_CTAS) scan_aggregate_kernel
       for (unsigned bk = 0; bk < gridDim.x; bk++) v = slot_combine(op, v, __ldcg(&args.partials[(size_t)bk * NE + e]));
       args.result[e] = slot_combine(op, args.result[e], v);
     }
-    if (tid == 0) *args.ticket = 0;
   }
+  if (is_last && tid == 0) *args.ticket = 0;
 }
 
 }  // namespace sd

@@ -6,7 +6,7 @@
 // HBM layout: the encoded bytes are copied VERBATIM (no re-encoding); only their placement is chosen
 // by the engine: every buffer is positioned so that its first value / first dictionary index is
 // 128-byte aligned, which makes every vector load of the scan kernel naturally aligned.  Null words get
-// an 8-byte aligned side copy plus a host-computed "nulls before tile" prefix (one int32 per 1024 rows).
+// an 8-byte aligned side copy plus a host-computed "nulls before" prefix (one int32 per 512 rows).
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -31,9 +31,10 @@ std::vector<KernelEntry>& kernel_registry() {
   static std::vector<KernelEntry> r;
   return r;
 }
-AotRegistrar::AotRegistrar(const char* signature, const void* func, size_t tile_smem) {
+AotRegistrar::AotRegistrar(const char* signature, const void* func, size_t tile_smem, int staged, size_t stage_bytes) {
   KernelEntry e;
   e.signature = signature; e.func = func; e.drv_func = nullptr; e.tile_smem = (tile_smem + 15) & ~size_t(15); e.origin = "aot";
+  e.staged = staged; e.stage_bytes = stage_bytes;
   kernel_registry().push_back(e);
 }
 
@@ -155,13 +156,13 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
   c.dev.nwords = nwords;
   // nulls before each tile (the incremental numNulls bookkeeping of the generated loop,
   // ColumnTableScan.scala:794-815, turned into a prefix the kernel can index)
-  const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
+  const int ntiles = (num_rows + NULL_PREFIX_ROWS - 1) / NULL_PREFIX_ROWS;
   int64_t total_nulls = 0;
   std::vector<int32_t> tile_nulls;
   if (nwords) {
     tile_nulls.resize(ntiles > 0 ? ntiles : 1, 0);
     for (int w = 0; w < nwords; w++) {
-      if ((w % TILE_WORDS) == 0 && w / TILE_WORDS < ntiles) tile_nulls[w / TILE_WORDS] = (int32_t)total_nulls;
+      if ((w % NULL_PREFIX_WORDS) == 0 && w / NULL_PREFIX_WORDS < ntiles) tile_nulls[w / NULL_PREFIX_WORDS] = (int32_t)total_nulls;
       uint64_t word = rd_u64(buf + 8 + 8 * (int64_t)w);
       if ((int64_t)(w + 1) * 64 > num_rows) {   // ignore bits beyond the batch
         int valid = num_rows - w * 64;
@@ -169,7 +170,7 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
       }
       total_nulls += __builtin_popcountll(word);
     }
-    for (int t = (nwords + TILE_WORDS - 1) / TILE_WORDS; t < ntiles; t++) tile_nulls[t] = (int32_t)total_nulls;
+    for (int t = (nwords + NULL_PREFIX_WORDS - 1) / NULL_PREFIX_WORDS; t < ntiles; t++) tile_nulls[t] = (int32_t)total_nulls;
   }
   c.has_nulls = nwords > 0;
   const int64_t nn = num_rows - total_nulls;   // stored (non-null) values

@@ -7,6 +7,7 @@
 // ahead-of-time compiled benchmark plans (build step) and the NVRTC path for every other plan.
 #include "sd_codegen.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -468,7 +469,7 @@ struct Gen {
         slt << NL << " ? " << ident << " : " << (f ? "sd::f2u((double)" + V + ")" : "(uint64_t)(int64_t)" + V) << ";\n";
       }
     }
-    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0);
+    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups;
     p.signature = sig.str();
     char hbuf[32];
     snprintf(hbuf, sizeof(hbuf), "%016llx", (unsigned long long)std::hash<std::string>()(p.signature));
@@ -487,6 +488,7 @@ struct Gen {
     o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : "sd::MODE_NOKEY") << ";\n";
     o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
     o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
+    o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
     o << "0; }\n";
@@ -510,7 +512,7 @@ struct Gen {
 
 }  // namespace
 
-int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err) {
+int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const CodegenOptions* opt) {
   if (!d) { err = "null plan descriptor"; return SD_ERR_INVALID; }
   if (d->abi_version != SD_ABI_VERSION) { err = "sd_plan_desc.abi_version mismatch"; return SD_ERR_INVALID; }
   if (d->ncols < 0 || d->nexprs < 0 || d->nkeys < 0 || d->naggs < 0 || d->nproj < 0 || d->nliterals < 0) {
@@ -532,17 +534,24 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err) {
   if (out.aggs.empty() && out.keys.empty())
     { err = "projection-only plans (no aggregate) are not implemented in the GPU path yet"; return SD_ERR_UNSUPPORTED; }
   out.mode = out.keys.empty() ? MODE_NOKEY : MODE_GROUPS;
-  // tile shape: tunable per plan; SD_TUNE_RPT / SD_TUNE_MIN_CTAS override (variants then go through NVRTC)
+  // kernel shape (see tools/sweep.sh for the measurements behind the defaults): staged fast path on;
+  // 4 rows per thread per tile; narrow no-key scans run 3 CTAs per SM, register-table group-bys 1.
   {
     int row_bytes = 0;
-    for (int k : out.kinds) row_bytes += (k == K_I64 || k == K_F64) ? 8 : (k == K_I32 || k == K_F32) ? 4 : (k == K_I16 || k == K_CODE) ? 2 : 1;
+    for (int k : out.kinds) row_bytes += kind_stage_width(k);
+    CodegenOptions o;
+    if (opt) o = *opt;
+    out.reg_groups = out.mode == MODE_GROUPS ? std::max(0, o.reg_groups) : 0;
     out.rpt = 4;
-    out.min_ctas = 2;
-    (void)row_bytes;
+    out.min_ctas = out.reg_groups > 0 ? 1 : (row_bytes <= 28 ? 3 : 2);
+    out.stages = 1;
     if (const char* e = getenv("SD_TUNE_RPT")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) out.rpt = v; }
     if (const char* e = getenv("SD_TUNE_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) out.min_ctas = v; }
-    out.stages = 1;
     if (const char* e = getenv("SD_TUNE_STAGES")) out.stages = atoi(e) > 0 ? 1 : 0;
+    if (o.rpt == 2 || o.rpt == 4 || o.rpt == 8) out.rpt = o.rpt;
+    if (o.min_ctas >= 1) out.min_ctas = o.min_ctas;
+    if (o.stages >= 0) out.stages = o.stages > 0 ? 1 : 0;
+    if (out.stages == 0) out.reg_groups = 0;   // the register tables are reduced through the ring's memory
   }
   rc = g.build_slots();
   if (rc) return rc;
@@ -553,10 +562,12 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err) {
 
 // ---- C entry point: generated source + signature of a plan (build step, debugging, profiling) ------
 extern "C" int sd_plan_codegen(const sd_plan_desc* desc, char* source, int64_t source_cap, int64_t* source_len,
-                               char* signature, int64_t sig_cap, char* struct_name, int64_t name_cap) {
+                               char* signature, int64_t sig_cap, char* struct_name, int64_t name_cap, int32_t reg_groups) {
   sd::PlanSpec spec;
   std::string err;
-  int rc = sd::analyze_plan(desc, spec, err);
+  sd::CodegenOptions opt;
+  opt.reg_groups = reg_groups;
+  int rc = sd::analyze_plan(desc, spec, err, &opt);
   if (rc) {
     if (source && source_cap > 0) snprintf(source, (size_t)source_cap, "%s", err.c_str());
     return rc;

@@ -58,14 +58,23 @@ struct PlanSpec {
   int rpt = 4;                       // rows per thread per tile (2, 4, 8)
   int min_ctas = 2;                  // __launch_bounds__ min CTAs per SM (= target CTAs per SM)
   int stages = 1;                    // > 0: staged fast path (producer warp + cp.async.bulk ring); 0: direct loads
+  int reg_groups = 0;                // > 0: MODE_GROUPS table held in registers for up to this many groups
   std::string signature;             // canonical text of everything the generated code depends on
   std::string struct_name;           // Plan_<hash of signature>
   std::string source;                // the generated PLAN struct (CUDA C++)
   sd_plan_desc desc_view() const;    // a descriptor pointing into the vectors above
 };
 
+// kernel-shape options; -1 = heuristic default (overridable with SD_TUNE_RPT / SD_TUNE_MIN_CTAS / SD_TUNE_STAGES)
+struct CodegenOptions {
+  int rpt = -1;
+  int min_ctas = -1;
+  int stages = -1;
+  int reg_groups = 0;
+};
+
 // Analyse + generate.  Returns SD_OK or an sd_status with `err` set.
-int analyze_plan(const sd_plan_desc* desc, PlanSpec& out, std::string& err);
+int analyze_plan(const sd_plan_desc* desc, PlanSpec& out, std::string& err, const CodegenOptions* opt = nullptr);
 
 // Host evaluation of a string predicate node for one dictionary entry (used to fill truth tables):
 // returns 0 FALSE, 1 TRUE, 2 NULL.  `s == nullptr` means the NULL code.

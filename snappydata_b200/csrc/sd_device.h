@@ -105,7 +105,9 @@ enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1 };
 //   TABLE_PRIVATE        one private copy per thread in shared memory, no atomics (few groups: TPC-H Q1)
 //   TABLE_SHARED_ATOMIC  one copy per CTA in shared memory, shared-memory atomics
 //   TABLE_GLOBAL_ATOMIC  the running result in global memory, global atomics (RED.ADD.F64 is native)
-enum : int32_t { TABLE_PRIVATE = 0, TABLE_SHARED_ATOMIC = 1, TABLE_GLOBAL_ATOMIC = 2 };
+//   TABLE_REGS           one private copy per thread in REGISTERS (predicated accumulators; kernel variant with
+//                        PLAN::REG_GROUPS >= ngroups): leaves all shared memory to the staged ring
+enum : int32_t { TABLE_PRIVATE = 0, TABLE_SHARED_ATOMIC = 1, TABLE_GLOBAL_ATOMIC = 2, TABLE_REGS = 3 };
 
 // accumulator slot operations; every slot is 8 bytes
 enum : int32_t { SLOT_ADD_F64 = 0, SLOT_ADD_I64 = 1, SLOT_MIN_I64 = 2, SLOT_MAX_I64 = 3, SLOT_MIN_F64 = 4, SLOT_MAX_F64 = 5 };

@@ -229,10 +229,14 @@ struct StatEval {
 struct sd_plan {
   int device = 0;
   PlanSpec spec;
-  KernelEntry kernel;
+  KernelEntry kernel;             // generic kernel of the plan
+  KernelEntry kernel_reg;         // register-group-table variant (MODE_GROUPS, <= REG_GROUPS_MAX groups), lazily resolved
+  int kernel_reg_state = 0;       // 0 unknown, 1 available, -1 unavailable
+  const KernelEntry* active = nullptr;
   std::string kernel_name;
   int max_ctas_per_sm = 0;
   size_t last_smem = (size_t)-1;
+  const KernelEntry* last_kernel = nullptr;
   int num_sms = 0;
   int smem_optin = 0;
   // literals
@@ -359,6 +363,9 @@ int remap_result(sd_plan* p, const int32_t* old_radix, int old_groups, const int
   return 0;
 }
 
+constexpr int REG_GROUPS_MAX = 8;
+int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int device, KernelEntry* out, PlanSpec* spec_out);
+
 struct BuiltScan {
   const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
   int64_t rows = 0, algo_bytes = 0, updated_cols = 0, deleted_batches = 0;
@@ -467,32 +474,51 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     ngroups *= radix[k];
   }
   const size_t ne = (size_t)ngroups * ns;
-  // where the dense group table lives: per-thread private copies when they fit, one shared-memory copy
-  // per CTA with atomics while that fits, else global atomics on the running result.  What is left of the
-  // SM's shared memory (per target CTA) becomes the ring of the staged fast path.
-  const size_t tile_smem = p->kernel.tile_smem;
-  const int target_ctas = std::max(1, sp.min_ctas);
-  const size_t budget = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
-  const size_t ring_fixed = 2 * MAX_STAGES * 8;
-  const size_t min_ring = p->kernel.staged ? ring_fixed + 2 * p->kernel.stage_bytes + 128 : 0;
+  // Where the dense group table lives (decided per launch from its size):
+  //   registers (kernel variant, <= 8 groups) > per-thread private shared-memory copies > one shared-memory copy
+  //   per CTA with atomics > global atomics on the running result.
+  // What is left of the SM's shared memory (per target CTA) becomes the ring of the staged fast path.
+  const KernelEntry* k = &p->kernel;
   int table_mode = TABLE_PRIVATE;
+  int target_ctas = std::max(1, sp.min_ctas);
+  if (sp.mode == MODE_GROUPS && ngroups <= REG_GROUPS_MAX && p->kernel.staged && !getenv("SD_TUNE_NO_REG_GROUPS")) {
+    if (p->kernel_reg_state == 0) {
+      CodegenOptions opt;
+      opt.reg_groups = REG_GROUPS_MAX;
+      sd_plan_desc dv = sp.desc_view();
+      p->kernel_reg_state = resolve_kernel(dv, opt, p->device, &p->kernel_reg, nullptr) == 0 ? 1 : -1;
+    }
+    if (p->kernel_reg_state == 1 && 2 * p->kernel_reg.stage_bytes >= ne * THREADS * 8) {
+      k = &p->kernel_reg;
+      table_mode = TABLE_REGS;
+      target_ctas = 1;
+    }
+  }
+  const size_t tile_smem = k->tile_smem;
+  const size_t ring_fixed = 2 * MAX_STAGES * 8;
+  const size_t min_ring = k->staged ? ring_fixed + 2 * k->stage_bytes + 128 : 0;
   size_t table_bytes = (size_t)std::max(ns, 1) * (THREADS / 32) * 8;
-  if (sp.mode == MODE_GROUPS) {
+  if (sp.mode == MODE_GROUPS && table_mode != TABLE_REGS) {
     const size_t priv = ne * THREADS * 8, shared = ne * 8;
-    if (tile_smem + priv + min_ring <= budget) { table_mode = TABLE_PRIVATE; table_bytes = priv; }
-    else if (shared <= 64 * 1024 && tile_smem + shared + min_ring <= budget) { table_mode = TABLE_SHARED_ATOMIC; table_bytes = shared; }
+    // private copies are worth giving up CTAs per SM for; atomics are the last resort
+    while (target_ctas > 1 && tile_smem + priv + min_ring > (size_t)p->smem_optin / target_ctas - 1024) target_ctas--;
+    const size_t budget1 = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
+    if (tile_smem + priv + min_ring <= budget1) { table_mode = TABLE_PRIVATE; table_bytes = priv; }
+    else if (shared <= 64 * 1024 && tile_smem + shared + min_ring <= budget1) { table_mode = TABLE_SHARED_ATOMIC; table_bytes = shared; }
     else { table_mode = TABLE_GLOBAL_ATOMIC; table_bytes = 64; }
   }
+  const size_t budget = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
   size_t ring_off = (tile_smem + table_bytes + 127) & ~size_t(127);
   int nstages = 0;
   size_t smem = ring_off;
-  if (p->kernel.staged) {
-    if (ring_off + min_ring > (size_t)p->smem_optin) return set_error(SD_ERR_UNSUPPORTED, "plan does not fit the shared-memory ring (%zu bytes per stage)", p->kernel.stage_bytes);
+  if (k->staged) {
+    if (ring_off + min_ring > (size_t)p->smem_optin) return set_error(SD_ERR_UNSUPPORTED, "plan does not fit the shared-memory ring (%zu bytes per stage)", k->stage_bytes);
     const size_t avail = std::max(budget, ring_off + min_ring) - ring_off - ring_fixed;
-    nstages = (int)std::min<size_t>(MAX_STAGES, avail / p->kernel.stage_bytes);
+    nstages = (int)std::min<size_t>(MAX_STAGES, avail / k->stage_bytes);
     if (const char* e = getenv("SD_TUNE_NSTAGES")) { int v = atoi(e); if (v >= 2 && v <= nstages) nstages = v; }
-    smem = ring_off + ring_fixed + (size_t)nstages * p->kernel.stage_bytes;
+    smem = ring_off + ring_fixed + (size_t)nstages * k->stage_bytes;
   }
+  if (p->active != k) { p->active = k; p->kernel_name = k->origin + ":" + k->name + (table_mode == TABLE_REGS ? "+regtable" : ""); }
   if (!p->result_init) {
     int rc = init_result(p, ngroups);
     if (rc) return rc;
@@ -503,13 +529,14 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   p->ngroups = ngroups;
   memcpy(p->radix, radix, sizeof(radix));
 
-  if (smem != p->last_smem) {
+  if (smem != p->last_smem || k != p->last_kernel) {
     int occ = 0;
-    int rc = kernel_prepare(p->kernel, smem, &occ);
+    int rc = kernel_prepare(*k, smem, &occ);
     if (rc) return rc;
     if (occ < 1) return set_error(SD_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     p->max_ctas_per_sm = occ;
     p->last_smem = smem;
+    p->last_kernel = k;
   }
   const int occ = p->max_ctas_per_sm;
   const int grid = std::min(total_chunks, p->num_sms * occ);
@@ -540,7 +567,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   }
   void* kargs[] = {&args};
   if (!p->have_timing) SD_CUDA(cudaEventRecord(p->ev_start, p->stream));
-  { int rc = kernel_launch(p->kernel, grid, smem, p->stream, kargs); if (rc) return rc; }
+  { int rc = kernel_launch(*k, grid, smem, p->stream, kargs); if (rc) return rc; }
   SD_CUDA(cudaEventRecord(p->ev_stop, p->stream));
   p->have_timing = true;
   p->metrics[7]++;
@@ -569,6 +596,22 @@ bool batch_passes_stats(const sd_plan* p, const StoredBatch& sb) {
   Tri r;
   if (!ev.eval(p->spec.filter, &r)) return true;
   return r.isnull || r.v;   // only a definite FALSE skips the batch (:948-957)
+}
+
+// find the kernel for a codegen variant of the plan: ahead-of-time registry first, else NVRTC
+int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int device, KernelEntry* out, PlanSpec* spec_out) {
+  PlanSpec spec;
+  std::string err;
+  int rc = analyze_plan(&desc, spec, err, &opt);
+  if (rc) return set_error(rc, "%s", err.c_str());
+  for (auto& k : kernel_registry()) if (k.signature == spec.signature) { *out = k; if (spec_out) *spec_out = spec; return 0; }
+  KernelEntry k;
+  rc = jit_compile(spec, device, k);
+  if (rc) return rc;
+  kernel_registry().push_back(k);
+  *out = k;
+  if (spec_out) *spec_out = spec;
+  return 0;
 }
 
 int ensure_private_store(sd_plan* p) {
@@ -602,16 +645,14 @@ int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   p->device = t_device;
   SD_CUDA(cudaSetDevice(p->device));
   // kernel: ahead-of-time compiled plan, else NVRTC
-  bool found = false;
-  for (auto& k : kernel_registry()) if (k.signature == p->spec.signature) { p->kernel = k; found = true; break; }
-  if (!found) {
-    KernelEntry k;
-    rc = jit_compile(p->spec, p->device, k);
+  {
+    CodegenOptions opt;
+    sd_plan_desc dv = p->spec.desc_view();
+    rc = resolve_kernel(dv, opt, p->device, &p->kernel, nullptr);
     if (rc) return rc;
-    kernel_registry().push_back(k);
-    p->kernel = k;
+    p->active = &p->kernel;
   }
-  p->kernel_name = p->kernel.origin + ":" + p->spec.struct_name;
+  p->kernel_name = p->kernel.origin + ":" + p->kernel.name;
   cudaDeviceProp prop;
   SD_CUDA(cudaGetDeviceProperties(&prop, p->device));
   p->num_sms = prop.multiProcessorCount;

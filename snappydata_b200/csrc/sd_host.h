@@ -34,8 +34,10 @@ struct KernelEntry {
   int staged = 0;        // PLAN::STAGES > 0: producer warp + shared-memory ring (block = THREADS + 32)
   size_t stage_bytes = 0;
   std::string origin;    // "aot" | "jit"
+  std::string name;      // Plan_<fnv1a(signature)>: the generated struct's name
 };
 std::vector<KernelEntry>& kernel_registry();
+std::string plan_struct_name(const std::string& signature);
 struct AotRegistrar {
   AotRegistrar(const char* signature, const void* func, size_t tile_smem, int staged, size_t stage_bytes);
 };

@@ -151,6 +151,7 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out) {
   out.drv_func = (void*)fn;
   out.tile_smem = ((size_t)tile_smem_bytes((int)spec.cols.size(), spec.rpt) + 15) & ~size_t(15);
   out.origin = "jit";
+  out.name = spec.struct_name;
   out.staged = spec.stages > 0 ? 1 : 0;
   out.stage_bytes = 0;
   for (int k : spec.kinds) out.stage_bytes += (size_t)THREADS * spec.rpt * kind_stage_width(k);

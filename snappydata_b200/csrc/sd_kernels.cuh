@@ -538,7 +538,14 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 
   // ---- accumulator init -------------------------------------------------------------------------
   uint64_t acc[NSLOT > 0 ? NSLOT : 1];
-  if (PLAN::MODE == MODE_NOKEY) {
+  constexpr int RG = PLAN::MODE == MODE_GROUPS ? PLAN::REG_GROUPS : 0;   // > 0: group table in registers
+  uint64_t racc[RG > 0 ? RG : 1][NSLOT > 0 ? NSLOT : 1];
+  if (RG > 0) {
+#pragma unroll
+    for (int gi = 0; gi < RG; gi++)
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) racc[gi][s] = slot_identity(PLAN::slot_op(s));
+  } else if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
   } else if (args.table_mode == TABLE_PRIVATE) {
@@ -623,7 +630,15 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           for (int s = 0; s < NSLOT; s++) acc[s] = slot_combine(PLAN::slot_op(s), acc[s], sv[s]);
         } else {
           const int g = PLAN::group(row, ctx);
-          if (args.table_mode == TABLE_PRIVATE) {
+          if (RG > 0) {   // predicated register accumulators: no memory traffic, no dependent smem chains
+#pragma unroll
+            for (int gi = 0; gi < RG; gi++) {
+              if (g == gi) {
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) racc[gi][s] = slot_combine(PLAN::slot_op(s), racc[gi][s], sv[s]);
+              }
+            }
+          } else if (args.table_mode == TABLE_PRIVATE) {
             uint64_t* t = table + (size_t)g * NSLOT * THREADS + tid;
 #pragma unroll
             for (int s = 0; s < NSLOT; s++) t[s * THREADS] = slot_combine(PLAN::slot_op(s), t[s * THREADS], sv[s]);
@@ -659,7 +674,17 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     }
   } else if (args.table_mode == TABLE_SHARED_ATOMIC) {
     for (int e = tid; e < NE; e += THREADS) my_partials[e] = table[e];
-  } else if (args.table_mode == TABLE_PRIVATE) {
+  } else if (args.table_mode == TABLE_PRIVATE || RG > 0) {
+    if (RG > 0) {   // spill the register tables into the (now idle) ring in the private-table layout
+      table = reinterpret_cast<uint64_t*>(ring);
+#pragma unroll
+      for (int gi = 0; gi < RG; gi++)
+        if (gi < args.ngroups) {
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++) table[(gi * NSLOT + s) * THREADS + tid] = racc[gi][s];
+        }
+      consumer_sync();
+    }
     for (int e = warp; e < NE; e += THREADS / 32) {
       const int op = PLAN::slot_op_rt(e % NSLOT);
       uint64_t v = slot_identity(op);

@@ -31,10 +31,17 @@ std::vector<KernelEntry>& kernel_registry() {
   static std::vector<KernelEntry> r;
   return r;
 }
+std::string plan_struct_name(const std::string& signature) {
+  unsigned long long h = 1469598103934665603ull;
+  for (unsigned char ch : signature) { h ^= ch; h *= 1099511628211ull; }
+  char b[40];
+  snprintf(b, sizeof(b), "Plan_%016llx", h);
+  return b;
+}
 AotRegistrar::AotRegistrar(const char* signature, const void* func, size_t tile_smem, int staged, size_t stage_bytes) {
   KernelEntry e;
   e.signature = signature; e.func = func; e.drv_func = nullptr; e.tile_smem = (tile_smem + 15) & ~size_t(15); e.origin = "aot";
-  e.staged = staged; e.stage_bytes = stage_bytes;
+  e.staged = staged; e.stage_bytes = stage_bytes; e.name = plan_struct_name(e.signature);
   kernel_registry().push_back(e);
 }
 

@@ -313,8 +313,8 @@ struct Gen {
         if (e.type == SD_STRING) { o << "    const int32_t v" << N << " = 0; const bool n" << N << " = false;\n"; return 0; }
         std::string val = type_is_fp(e.type) ? "ctx.L->d[" + std::to_string(e.a) + "]" : "ctx.L->i[" + std::to_string(e.a) + "]";
         if (e.type == SD_BOOLEAN) val = "(" + val + " != 0)";
-        o << "    const " << T << " v" << N << " = (" << T << ")" << val << "; const bool n" << N << " = ((ctx.L->nullmask >> "
-          << e.a << ") & 1ull) != 0;\n";
+        o << "    const " << T << " v" << N << " = (" << T << ")" << val << "; const bool n" << N << " = "
+          << (p.lit_nullable ? "((ctx.L->nullmask >> " + std::to_string(e.a) + ") & 1ull) != 0" : std::string("false")) << ";\n";
         if (e.type == SD_BOOLEAN) o << "    const int t" << N << " = n" << N << " ? 2 : (v" << N << " ? 1 : 0);\n";
         return 0;
       }
@@ -375,7 +375,7 @@ struct Gen {
             const int s = e.b + k;
             std::string lv = type_is_fp(ot) ? std::string("(") + ctype_of(ot) + ")ctx.L->d[" + std::to_string(s) + "]"
                                             : std::string("(") + ctype_of(ot) + ")ctx.L->i[" + std::to_string(s) + "]";
-            std::string nn = "(((ctx.L->nullmask >> " + std::to_string(s) + ") & 1ull) == 0)";
+            std::string nn = p.lit_nullable ? "(((ctx.L->nullmask >> " + std::to_string(s) + ") & 1ull) == 0)" : std::string("true");
             std::string eq = type_is_fp(ot) ? "sd::f_eq(" + V(e.a) + ", " + lv + ")" : "(" + V(e.a) + " == " + lv + ")";
             any << (k ? " || " : "") << "(" << nn << " && " << eq << ")";
             anynull << (k ? " || " : "") << "!" << nn;
@@ -444,7 +444,7 @@ struct Gen {
         p.tables.push_back(TableSpec{TABLE_KEYMAP, e.a, -1, (int)k});
         const int t = (int)p.tables.size() - 1;
         keymap_table.push_back(t);
-        std::string term = "reinterpret_cast<const int32_t*>(ctx.table(" + std::to_string(t) + "))[r.c" + std::to_string(e.a) + "]";
+        std::string term = "ctx.key_id(" + std::to_string(t) + ", r.c" + std::to_string(e.a) + ")";
         g = k == 0 ? term : "(" + g + ") * ctx.radix[" + std::to_string(k) + "] + " + term;
       }
       grp << "    return " << g << ";\n";
@@ -469,7 +469,8 @@ struct Gen {
         slt << NL << " ? " << ident << " : " << (f ? "sd::f2u((double)" + V + ")" : "(uint64_t)(int64_t)" + V) << ";\n";
       }
     }
-    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups;
+    if ((int)p.tables.size() > MAX_TABLES) return fail(SD_ERR_UNSUPPORTED, "more than 16 dictionary lookup tables in one plan");
+    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups << ";litnull=" << p.lit_nullable;
     p.signature = sig.str();
     char hbuf[32];
     snprintf(hbuf, sizeof(hbuf), "%016llx", (unsigned long long)std::hash<std::string>()(p.signature));
@@ -489,6 +490,7 @@ struct Gen {
     o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
     o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
     o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
+    o << "  static constexpr int NTABLES = " << p.tables.size() << ";\n";
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
     o << "0; }\n";
@@ -542,8 +544,9 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
     CodegenOptions o;
     if (opt) o = *opt;
     out.reg_groups = out.mode == MODE_GROUPS ? std::max(0, o.reg_groups) : 0;
+    out.lit_nullable = o.lit_nullable ? 1 : 0;
     out.rpt = 4;
-    out.min_ctas = out.reg_groups > 0 ? 1 : (row_bytes <= 28 ? 3 : 2);
+    out.min_ctas = out.mode == MODE_GROUPS ? 1 : (row_bytes <= 28 ? 3 : 2);   // group tables want the SM's shared memory
     out.stages = 1;
     if (const char* e = getenv("SD_TUNE_RPT")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) out.rpt = v; }
     if (const char* e = getenv("SD_TUNE_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) out.min_ctas = v; }
@@ -562,11 +565,13 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
 
 // ---- C entry point: generated source + signature of a plan (build step, debugging, profiling) ------
 extern "C" int sd_plan_codegen(const sd_plan_desc* desc, char* source, int64_t source_cap, int64_t* source_len,
-                               char* signature, int64_t sig_cap, char* struct_name, int64_t name_cap, int32_t reg_groups) {
+                               char* signature, int64_t sig_cap, char* struct_name, int64_t name_cap, int32_t reg_groups,
+                               int32_t lit_nullable) {
   sd::PlanSpec spec;
   std::string err;
   sd::CodegenOptions opt;
   opt.reg_groups = reg_groups;
+  opt.lit_nullable = lit_nullable;
   int rc = sd::analyze_plan(desc, spec, err, &opt);
   if (rc) {
     if (source && source_cap > 0) snprintf(source, (size_t)source_cap, "%s", err.c_str());

@@ -58,6 +58,7 @@ struct PlanSpec {
   int rpt = 4;                       // rows per thread per tile (2, 4, 8)
   int min_ctas = 2;                  // __launch_bounds__ min CTAs per SM (= target CTAs per SM)
   int stages = 1;                    // > 0: staged fast path (producer warp + cp.async.bulk ring); 0: direct loads
+  int lit_nullable = 0;              // 1: literal slots may be NULL at run time (separate kernel variant)
   int reg_groups = 0;                // > 0: MODE_GROUPS table held in registers for up to this many groups
   std::string signature;             // canonical text of everything the generated code depends on
   std::string struct_name;           // Plan_<hash of signature>
@@ -71,6 +72,7 @@ struct CodegenOptions {
   int min_ctas = -1;
   int stages = -1;
   int reg_groups = 0;
+  int lit_nullable = 0;
 };
 
 // Analyse + generate.  Returns SD_OK or an sd_status with `err` set.

@@ -49,6 +49,7 @@ constexpr int tile_smem_bytes(int nc, int rpt) {
 }
 
 constexpr int MAX_LITERALS = 64;
+constexpr int MAX_TABLES = 16;   // per-batch lookup tables (truth tables + key maps) of one plan
 constexpr int MAX_KEYS = 4;
 
 // One update delta of one column (enc/ColumnDeltaEncoder.scala:300-331): ascending positions +

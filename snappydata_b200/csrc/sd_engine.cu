@@ -232,6 +232,8 @@ struct sd_plan {
   KernelEntry kernel;             // generic kernel of the plan
   KernelEntry kernel_reg;         // register-group-table variant (MODE_GROUPS, <= REG_GROUPS_MAX groups), lazily resolved
   int kernel_reg_state = 0;       // 0 unknown, 1 available, -1 unavailable
+  KernelEntry kernel_litnull;     // variant for executions with a NULL literal, lazily resolved
+  int kernel_litnull_state = 0;
   const KernelEntry* active = nullptr;
   std::string kernel_name;
   int max_ctas_per_sm = 0;
@@ -405,12 +407,14 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
     }
     if (sb.dev_deletes) out->algo_bytes += 12 + 4 * (int64_t)sb.num_deletes;
     hdr->flags = all_fast ? BATCH_ALL_FAST : 0;
-    // per-batch tables: [int32 offset x nt][tables], every table indexed by the unified dictionary code
+    // per-batch tables: [int32 offset x nt][pad 8][uint64 kpack x nt][tables]; every table is indexed by the
+    // unified dictionary code; key maps of <= 8 codes are also packed one byte per code into kpack
     if (nt) {
       while (aux.size() % 16) aux.push_back(0);
       aux_off[bi] = aux.size();
       const size_t base = aux.size();
-      aux.resize(base + 4 * (size_t)nt, 0);
+      const size_t kp_off = ((4 * (size_t)nt + 7) & ~size_t(7));
+      aux.resize(base + kp_off + 8 * (size_t)nt, 0xff);
       for (int ti = 0; ti < nt; ti++) {
         const TableSpec& ts = sp.tables[ti];
         const StoredCol& sc = sb.cols[sb.positional ? ts.col : sp.cols[ts.col].table_ordinal];
@@ -422,6 +426,9 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
         while (aux.size() % 4) aux.push_back(0);
         const int32_t off = (int32_t)(aux.size() - base);
         memcpy(aux.data() + base + 4 * (size_t)ti, &off, 4);
+        uint64_t kpack = ~0ull;
+        bool packable = ts.kind == TABLE_KEYMAP && ncodes <= 8;
+        uint8_t packed[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (ts.kind == TABLE_TRUTH) {
           for (int code = 0; code < ncodes; code++) {
             const bool isnull = code == n || code >= (int)sc.dict_strings.size();
@@ -433,8 +440,11 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
             const bool isnull = code == n || code >= (int)sc.dict_strings.size();
             const int32_t id = isnull ? (nullable ? key_null(p, ts.key) : 0) : key_id(p, ts.key, sc.dict_strings[code]);
             aux.insert(aux.end(), reinterpret_cast<const uint8_t*>(&id), reinterpret_cast<const uint8_t*>(&id) + 4);
+            if (packable) { if (id >= 255) packable = false; else packed[code] = (uint8_t)id; }
           }
+          if (packable) memcpy(&kpack, packed, 8);
         }
+        memcpy(aux.data() + base + kp_off + 8 * (size_t)ti, &kpack, 8);
       }
     }
     out->rows += sb.num_rows;
@@ -479,9 +489,25 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   //   per CTA with atomics > global atomics on the running result.
   // What is left of the SM's shared memory (per target CTA) becomes the ring of the staged fast path.
   const KernelEntry* k = &p->kernel;
+  {   // a NULL literal needs the variant whose generated code carries literal null flags
+    bool any_null = false;
+    for (auto& l : p->lits) any_null = any_null || l.is_null;
+    if (any_null) {
+      if (p->kernel_litnull_state == 0) {
+        CodegenOptions opt;
+        opt.lit_nullable = 1;
+        sd_plan_desc dv = sp.desc_view();
+        int rc = resolve_kernel(dv, opt, p->device, &p->kernel_litnull, nullptr);
+        if (rc) return rc;
+        p->kernel_litnull_state = 1;
+      }
+      k = &p->kernel_litnull;
+    }
+  }
   int table_mode = TABLE_PRIVATE;
   int target_ctas = std::max(1, sp.min_ctas);
-  if (sp.mode == MODE_GROUPS && ngroups <= REG_GROUPS_MAX && p->kernel.staged && !getenv("SD_TUNE_NO_REG_GROUPS")) {
+  if (sp.mode == MODE_GROUPS && ngroups <= REG_GROUPS_MAX && k == &p->kernel && p->kernel.staged && getenv("SD_TUNE_REG_GROUPS")) {
+    // experimental (opt-in): measured slower than the private shared-memory tables, see DESIGN.md
     if (p->kernel_reg_state == 0) {
       CodegenOptions opt;
       opt.reg_groups = REG_GROUPS_MAX;

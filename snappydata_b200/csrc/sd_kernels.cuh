@@ -392,33 +392,33 @@ struct StageInfo {
 
 // element width of column C in this batch (dictionary indexes are int16 or int32)
 template <class PLAN, int C>
-__device__ __forceinline__ int col_width(const DevCol& col) {
-  return PLAN::kind(C) == K_CODE ? (col.enc == ENC_DICTIONARY ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
+__device__ __forceinline__ int col_width(uint32_t c16) {
+  return PLAN::kind(C) == K_CODE ? (((c16 >> C) & 1u) ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
 }
 
 template <class PLAN, int C>
-__device__ __forceinline__ void issue_col_copy(const DevCol& col, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
-  const int w = col_width<PLAN, C>(col);
+__device__ __forceinline__ void issue_col_copy(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
+  const int w = col_width<PLAN, C>(c16);
   const uint32_t bytes = ((uint32_t)(rows * w) + 15u) & ~15u;   // buffers are padded: over-reading a partial tile is safe
   bulk_g2s(stage + stage_col_off<PLAN>(C), col.data + tile_start * w, bytes, bar);
 }
 template <class PLAN, int C>
-__device__ __forceinline__ uint32_t col_copy_bytes(const DevCol& col, int rows) {
-  return ((uint32_t)(rows * col_width<PLAN, C>(col)) + 15u) & ~15u;
+__device__ __forceinline__ uint32_t col_copy_bytes(uint32_t c16, int rows) {
+  return ((uint32_t)(rows * col_width<PLAN, C>(c16)) + 15u) & ~15u;
 }
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void issue_tile_copies(const DevBatch<PLAN::NC>& b, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
+__device__ __forceinline__ void issue_tile_copies(const DevBatch<PLAN::NC>& b, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
   uint32_t total = 0;
-  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(b.cols[Cs], rows), 0)...};
+  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(c16, rows), 0)...};
   (void)d0;
   mbar_expect_tx(bar, total);
-  int d1[] = {0, (issue_col_copy<PLAN, Cs>(b.cols[Cs], tile_start, rows, stage, bar), 0)...};
+  int d1[] = {0, (issue_col_copy<PLAN, Cs>(b.cols[Cs], c16, tile_start, rows, stage, bar), 0)...};
   (void)d1;
 }
 
 // consumer: registers <- stage (conflict-free: consecutive lanes read consecutive 16/8/4/2 bytes)
 template <class PLAN, int C>
-__device__ __forceinline__ void load_col_staged(const DevCol& col, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
+__device__ __forceinline__ void load_col_staged(uint32_t c16, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
   typedef typename KindT<PLAN::kind(C)>::T T;
   constexpr int K = PLAN::kind(C);
   const uint8_t* base = stage + stage_col_off<PLAN>(C);
@@ -427,7 +427,7 @@ __device__ __forceinline__ void load_col_staged(const DevCol& col, const uint8_t
   for (int u = 0; u < PLAN::RPT / 2; u++) {
     const int p = u * 2 * THREADS + 2 * (int)threadIdx.x;
     if (K == K_CODE) {
-      if (col.enc == ENC_DICTIONARY) {
+      if ((c16 >> C) & 1u) {
         uint32_t x = *reinterpret_cast<const uint32_t*>(base + p * 2);
         regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
         regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
@@ -456,8 +456,8 @@ __device__ __forceinline__ void load_col_staged(const DevCol& col, const uint8_t
   }
 }
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void load_all_staged(const DevBatch<PLAN::NC>& b, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
-  int dummy[] = {0, (load_col_staged<PLAN, Cs>(b.cols[Cs], stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+__device__ __forceinline__ void load_all_staged(uint32_t c16, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (load_col_staged<PLAN, Cs>(c16, stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
   (void)dummy;
 }
 
@@ -474,11 +474,37 @@ __device__ __forceinline__ int find_batch(const int32_t* chunk_prefix, int nbatc
 // context handed to the generated row functions
 struct RowCtx {
   const Literals* L;
-  const uint8_t* aux;   // per-batch tables of this plan (offset header, then tables)
   const int32_t* radix;
-  // table t of the batch: aux + ((const int32_t*)aux)[t]
-  __device__ __forceinline__ const uint8_t* table(int t) const { return aux + reinterpret_cast<const int32_t*>(aux)[t]; }
+  // per-batch tables of this plan, refreshed once per chunk:
+  //   aux = [int32 offset x NT][pad to 8][uint64 kpack x NT][tables...]
+  //   tbl[t]   : table t (truth table: uint8 per dictionary code; key map: int32 group id per code)
+  //   kpack[t] : key maps of <= 8 codes packed one byte per code (no memory access per row), else ~0
+  const uint8_t* tbl[MAX_TABLES];
+  uint64_t kpack[MAX_TABLES];
+  __device__ __forceinline__ const uint8_t* table(int t) const { return tbl[t]; }
+  __device__ __forceinline__ int key_id(int t, int code) const {
+    const uint64_t kp = kpack[t];
+    return kp != ~0ull ? (int)((kp >> (code * 8)) & 0xffull) : reinterpret_cast<const int32_t*>(tbl[t])[code];
+  }
 };
+template <int NT>
+__device__ __forceinline__ void load_tables(RowCtx& ctx, const uint8_t* aux) {
+  if (NT > 0) {
+    const int32_t* off = reinterpret_cast<const int32_t*>(aux);
+    const uint64_t* kp = reinterpret_cast<const uint64_t*>(aux + ((4 * NT + 7) & ~7));
+#pragma unroll
+    for (int t = 0; t < NT; t++) { ctx.tbl[t] = aux + __ldg(&off[t]); ctx.kpack[t] = __ldg(&kp[t]); }
+  }
+}
+
+// bit c set: K_CODE column c of this batch uses int16 dictionary indexes (else int32)
+template <class PLAN, int... Cs>
+__device__ __forceinline__ uint32_t code16_mask(const DevBatch<PLAN::NC>& b, Seq<Cs...>) {
+  uint32_t m = 0;
+  int dummy[] = {0, (PLAN::kind(Cs) == K_CODE ? (m |= (b.cols[Cs].enc == ENC_DICTIONARY ? 1u : 0u) << Cs, 0) : 0)...};
+  (void)dummy;
+  return m;
+}
 
 // ================================================================================================
 // The kernel.  dynamic shared memory: [TileSmem<PLAN>] [private group tables | reduction scratch]
@@ -521,11 +547,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
           const int tile0 = chunk * CHUNK_TILES, tile_end = min(tile0 + CHUNK_TILES, ntiles);
+          const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
           for (int tile = tile0; tile < tile_end; tile++) {
             const int64_t tile_start = (int64_t)tile * TILE_ROWS;
             const int rows = min(TILE_ROWS, num_rows - (int)tile_start);
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            issue_tile_copies<PLAN>(b, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
+            issue_tile_copies<PLAN>(b, c16, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -555,7 +582,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     for (int e = tid; e < NE; e += THREADS) table[e] = slot_identity(PLAN::slot_op_rt(e % NSLOT));
     consumer_sync();
   }
-  unsigned long long n_scanned = 0, n_passed = 0;
+  unsigned long long n_scanned = 0, n_passed = 0;   // flushed from 32-bit per-chunk counters
 
   RowCtx ctx;
   ctx.L = &args.lits;
@@ -568,7 +595,9 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
     const bool fast = (b.flags & BATCH_ALL_FAST) != 0;
-    ctx.aux = b.aux;
+    load_tables<PLAN::NTABLES>(ctx, b.aux);
+    const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
+    uint32_t c_scanned = 0, c_passed = 0;
     const int tile0 = chunk * CHUNK_TILES;
     const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
     const int tile_end = min(tile0 + CHUNK_TILES, ntiles);
@@ -583,7 +612,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
       if (fast) {
         if (PLAN::STAGES > 0) {
           mbar_wait(&full_bar[c_stage], c_phase);
-          load_all_staged<PLAN>(b, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
+          load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // this warp holds its rows in registers now
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }
@@ -615,14 +644,14 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
       }
 
       // ---- row at a time over registers: filter -> group -> accumulate -------------------------
+      c_scanned += __popc(live);
 #pragma unroll
       for (int r = 0; r < RPT; r++) {
         if (!((live >> r) & 1u)) continue;
-        n_scanned++;
         typename PLAN::Row row;
         fill_row<PLAN>(regs, r, row, ColSeq());
         if (!PLAN::filter(row, ctx)) continue;      // FilterExec: only TRUE passes
-        n_passed++;
+        c_passed++;
         uint64_t sv[NSLOT > 0 ? NSLOT : 1];
         PLAN::slots(row, ctx, sv);
         if (PLAN::MODE == MODE_NOKEY) {
@@ -650,6 +679,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
         }
       }
     }
+    n_scanned += c_scanned;
+    n_passed += c_passed;
   }
 
   // ---- CTA reduction (fixed order) -> partials[blockIdx] -------------------------------------------

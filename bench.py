@@ -134,7 +134,7 @@ def run_reference_arm(args):
     desc = P.q1_plan() if q1 else P.q6_plan()
     total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
     cores = os.cpu_count() or 1
-    nsample = max(cores, min(64, (total + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH))
+    nsample = min((total + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH, max(64, min(512, 4 * cores)))
     batches = lineitem.gen_table(total, ROWS_PER_BATCH, SEED_Q1 if q1 else SEED_Q6, NBUCKETS,
                                  lineitem.Q1_COLUMN_MASK if q1 else lineitem.Q6_COLUMN_MASK, batches=range(nsample))
     ba = oracle.BatchArray(batches, desc.table_cols)
@@ -195,6 +195,7 @@ class QueryRun:
                                 lineitem.Q1_COLUMN_MASK if q1 else lineitem.Q6_COLUMN_MASK)
         self.plan = capi.Plan(api, self.desc)
         self.plan.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.merge_plan = self.plan
         self.launches = 0
         self.kernel_ns = 0
         self.algo_bytes = 0
@@ -222,7 +223,7 @@ class QueryRun:
             allb = bytes(self.pin_out.numpy())
             raw = b"".join(allb[r * 4096 + 8: r * 4096 + 8 + int.from_bytes(allb[r * 4096: r * 4096 + 8], "little")]
                            for r in range(self.world))
-        self.final = self.capi.final_merge(self.api, self.desc, raw)
+        self.final = self.merge_plan.final_merge(raw)
         return len(raw)
 
     def step_resident(self):
@@ -286,7 +287,7 @@ class QueryRun:
         """Generated-loop restatement over a bounded sample of this rank's host copy, all host threads."""
         from oracle import oracle
         cores = os.cpu_count() or 1
-        nsample = min(len(self.marshalled), max(cores, 64))
+        nsample = min(len(self.marshalled), max(64, 16 * cores))
         ba = oracle.BatchArray.__new__(oracle.BatchArray)
         ba.m = self.marshalled[:nsample]
         ba.arr = (self.capi.sd_batch * nsample)(*[mb.c for mb in ba.m])

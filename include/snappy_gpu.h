@@ -201,6 +201,10 @@ void sd_store_destroy(sd_store* s);
 int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len,
                    void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
 
+/* the same merge reusing the analysis held by a plan handle (no per-call plan analysis) */
+int sd_plan_final_merge(sd_plan* p, const void* partial_rows, int64_t len,
+                        void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
+
 /* ---- export of the dense partial table for an on-device exchange (NCCL all-reduce over NVLink of
  *      per-GPU partials).  Writes nslots int64/double words per group into dev_out
  *      (device pointer) on the plan's stream.  Only for plans without string/hash keys. ---------- */

@@ -201,6 +201,7 @@ class Api:
         self.store_bytes = fn("store_bytes", C.c_int, vp, C.POINTER(i64), required=False)
         self.plan_scan_store = fn("plan_scan_store", C.c_int, vp, vp, C.POINTER(i32), i32, required=False)
         self.store_destroy = fn("store_destroy", None, vp, required=False)
+        self.plan_final_merge = fn("plan_final_merge", C.c_int, vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
         self.plan_partials_layout = fn("plan_partials_layout", C.c_int, vp, C.POINTER(i32), C.POINTER(i32),
                                        C.POINTER(i32), required=False)
         self.plan_export_partials = fn("plan_export_partials", C.c_int, vp, vp, i64, required=False)
@@ -351,13 +352,14 @@ class Plan:
         return self
 
     def finish_raw(self) -> bytes:
-        cap = 1 << 16
         while True:
-            buf = C.create_string_buffer(cap)
+            if getattr(self, "_out_buf", None) is None:
+                self._out_buf = C.create_string_buffer(1 << 14)
+            buf = self._out_buf
             out_len, out_rows = C.c_int64(), C.c_int64()
-            rc = self.api.plan_finish(self.h, buf, cap, C.byref(out_len), C.byref(out_rows))
+            rc = self.api.plan_finish(self.h, buf, len(buf), C.byref(out_len), C.byref(out_rows))
             if rc == SD_ERR_OVERFLOW:
-                cap = int(out_len.value) + 64
+                self._out_buf = C.create_string_buffer(int(out_len.value) + 64)
                 continue
             self.api.check(rc)
             return buf.raw[: out_len.value]
@@ -368,6 +370,16 @@ class Plan:
     def reset(self):
         self.api.check(self.api.plan_reset(self.h))
         return self
+
+    def final_merge(self, partial_raw: bytes) -> List[List[object]]:
+        """Final merge of partial rows (all partitions) reusing this handle's plan analysis."""
+        cap = max(1 << 14, 4 * len(partial_raw) + 1024)
+        if getattr(self, "_merge_buf", None) is None or len(self._merge_buf) < cap:
+            self._merge_buf = C.create_string_buffer(cap)
+        out_len, out_rows = C.c_int64(), C.c_int64()
+        self.api.check(self.api.plan_final_merge(self.h, _buf_ptr(partial_raw), len(partial_raw), self._merge_buf, cap,
+                                                 C.byref(out_len), C.byref(out_rows)))
+        return parse_row_stream(self._merge_buf.raw[: out_len.value], self.desc.final_schema())
 
     def metrics(self) -> Dict[str, int]:
         out = (C.c_int64 * SD_NUM_METRICS)()

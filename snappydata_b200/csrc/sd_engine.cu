@@ -257,7 +257,9 @@ struct sd_plan {
   int64_t pending_bytes = 0;
   // device state
   Arena scratch;                 // descriptors, aux tables (reset per execution)
-  uint64_t* d_result = nullptr;  // [result_cap]
+  uint64_t* d_result = nullptr;  // [result_cap] running result
+  uint64_t* h_pinned = nullptr;  // pinned host staging: identities out, result + counters back
+  size_t h_pinned_cap = 0;
   uint64_t* d_partials = nullptr;
   size_t partials_cap = 0;
   unsigned int* d_ticket = nullptr;
@@ -298,31 +300,37 @@ std::string literal_key(const sd_plan* p) {
 }
 
 int ensure_result(sd_plan* p, size_t entries) {
-  if (entries <= p->result_cap) return 0;
   SD_CUDA(cudaSetDevice(p->device));
-  uint64_t* nr = nullptr;
-  SD_CUDA(cudaMalloc(&nr, entries * 8));
-  if (p->d_result) cudaFree(p->d_result);
-  p->d_result = nr;
-  p->result_cap = entries;
-  p->result_init = false;
+  if (entries > p->result_cap) {
+    uint64_t* nr = nullptr;
+    SD_CUDA(cudaMalloc(&nr, entries * 8));
+    if (p->d_result) cudaFree(p->d_result);
+    p->d_result = nr;
+    p->result_cap = entries;
+    p->result_init = false;
+  }
+  if (entries + 8 > p->h_pinned_cap) {
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    p->h_pinned_cap = entries + 8;
+    SD_CUDA(cudaMallocHost(&p->h_pinned, p->h_pinned_cap * 8));
+  }
   return 0;
 }
 
-// (re)initialise the running result with the slot identities for `ngroups` groups
+// (re)initialise the running result with the slot identities for `ngroups` groups (async: the pinned
+// staging buffer outlives the copy)
 int init_result(sd_plan* p, int ngroups) {
   const int ns = (int)p->spec.slots.size();
   const size_t ne = (size_t)ngroups * ns;
   int rc = ensure_result(p, ne);
   if (rc) return rc;
-  std::vector<uint64_t> h(ne);
+  SD_CUDA(cudaStreamSynchronize(p->stream));   // the staging buffer may still be in use by a previous read-back
   for (size_t e = 0; e < ne; e++) {
     const int op = p->spec.slots[e % ns].op;
-    h[e] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
-         : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull : op == SLOT_MAX_F64 ? 0xfff0000000000000ull : 0ull;
+    p->h_pinned[e] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+                   : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull : op == SLOT_MAX_F64 ? 0xfff0000000000000ull : 0ull;
   }
-  SD_CUDA(cudaMemcpyAsync(p->d_result, h.data(), ne * 8, cudaMemcpyHostToDevice, p->stream));
-  SD_CUDA(cudaStreamSynchronize(p->stream));
+  SD_CUDA(cudaMemcpyAsync(p->d_result, p->h_pinned, ne * 8, cudaMemcpyHostToDevice, p->stream));
   p->result_init = true;
   return 0;
 }
@@ -352,6 +360,7 @@ int remap_result(sd_plan* p, const int32_t* old_radix, int old_groups, const int
   SD_CUDA(cudaMemcpy(oldh.data(), p->d_result, oldh.size() * 8, cudaMemcpyDeviceToHost));
   int rc = init_result(p, new_groups);
   if (rc) return rc;
+  SD_CUDA(cudaStreamSynchronize(p->stream));
   std::vector<uint64_t> newh((size_t)new_groups * ns);
   SD_CUDA(cudaMemcpy(newh.data(), p->d_result, newh.size() * 8, cudaMemcpyDeviceToHost));
   for (int g = 0; g < old_groups; g++) {
@@ -815,11 +824,13 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
   if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
   const size_t ne = (size_t)p->ngroups * ns;
-  std::vector<uint64_t> h(ne);
-  unsigned long long counters[2] = {0, 0};
-  SD_CUDA(cudaMemcpyAsync(h.data(), p->d_result, ne * 8, cudaMemcpyDeviceToHost, p->stream));
-  SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  rc = ensure_result(p, ne);
+  if (rc) return rc;
+  SD_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_result, ne * 8, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaMemcpyAsync(p->h_pinned + ne, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
   SD_CUDA(cudaStreamSynchronize(p->stream));
+  const uint64_t* h = p->h_pinned;
+  const unsigned long long counters[2] = {p->h_pinned[ne], p->h_pinned[ne + 1]};
   if (p->have_timing) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms;
@@ -911,6 +922,7 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->ev_start) cudaEventDestroy(p->ev_start);
   if (p->ev_stop) cudaEventDestroy(p->ev_stop);
   if (p->d_result) cudaFree(p->d_result);
+  if (p->h_pinned) cudaFreeHost(p->h_pinned);
   if (p->d_partials) cudaFree(p->d_partials);
   if (p->d_ticket) cudaFree(p->d_ticket);
   if (p->d_counters) cudaFree(p->d_counters);
@@ -1023,12 +1035,27 @@ int sd_rows_submit(sd_plan* p, const void* rows, int64_t len, int32_t nrows) {
 }
 
 // ---- final merge (host; payload is a handful of rows) -------------------------------------------------
+static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                            int64_t* out_len, int64_t* out_nrows);
+
 int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
                    int64_t* out_len, int64_t* out_nrows) {
   PlanSpec sp;
   std::string err;
   int rc = analyze_plan(desc, sp, err);
   if (rc) return set_error(rc, "sd_final_merge: %s", err.c_str());
+  return final_merge_impl(sp, partial_rows, len, out_rows, cap, out_len, out_nrows);
+}
+
+/* same merge, reusing the analysis of an existing plan handle (no per-call plan analysis) */
+int sd_plan_final_merge(sd_plan* p, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                        int64_t* out_len, int64_t* out_nrows) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  return final_merge_impl(p->spec, partial_rows, len, out_rows, cap, out_len, out_nrows);
+}
+
+static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                            int64_t* out_len, int64_t* out_nrows) {
   const int nk = (int)sp.keys.size();
   std::vector<int> types;
   for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);

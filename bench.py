@@ -114,11 +114,8 @@ class ClockSampler:
 
 
 def shard_batches(total_rows, rank, world):
-    nb = (total_rows + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH
-    lo, hi = nb * rank // world, nb * (rank + 1) // world
-    first_row = lo * ROWS_PER_BATCH
-    nrows = min(total_rows, hi * ROWS_PER_BATCH) - first_row
-    return first_row, max(0, nrows), hi - lo
+    from snappydata_b200.exchange import shard_batches as sb
+    return sb(total_rows, ROWS_PER_BATCH, rank, world)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -201,28 +198,14 @@ class QueryRun:
         self.algo_bytes = 0
         self.final = None
         if world > 1:
-            self.gather_in = torch.zeros(4096, dtype=torch.uint8, device="cuda")
-            self.gather_out = torch.zeros(4096 * world, dtype=torch.uint8, device="cuda")
-            self.pin = torch.zeros(4096, dtype=torch.uint8).pin_memory()
-            self.pin_out = torch.zeros(4096 * world, dtype=torch.uint8).pin_memory()
+            from snappydata_b200.exchange import PartialRowExchange
+            self.exchange = PartialRowExchange(torch, dist, world, "cuda")
 
     def exchange_and_merge(self, raw):
         """The one exchange of the query: all-gather of the partial rows over NCCL, then the final merge
         (SnappyHashAggregateExec(Final) / CollectAggregateExec) -- identical on every rank."""
-        torch = self.torch
         if self.world > 1:
-            n = len(raw)
-            assert n + 8 <= 4096
-            self.pin[:8] = torch.frombuffer(bytearray(n.to_bytes(8, "little")), dtype=torch.uint8)
-            if n:
-                self.pin[8:8 + n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-            self.gather_in.copy_(self.pin, non_blocking=True)
-            self.dist.all_gather_into_tensor(self.gather_out, self.gather_in)
-            self.pin_out.copy_(self.gather_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            allb = bytes(self.pin_out.numpy())
-            raw = b"".join(allb[r * 4096 + 8: r * 4096 + 8 + int.from_bytes(allb[r * 4096: r * 4096 + 8], "little")]
-                           for r in range(self.world))
+            raw = self.exchange.all_gather(raw)
         self.final = self.merge_plan.final_merge(raw)
         return len(raw)
 

@@ -1,0 +1,29 @@
+/*
+ * JVM binding of libsnappygpu.so (see include/snappy_gpu.h and jvm/native/snappy_gpu_jni.c).
+ * NOT COMPILED in this repository's container (no JDK/Scala toolchain); written against
+ * SnappyData 1.3.0 / snappy-spark 2.1.1.9 class names as they appear in /root/reference.
+ */
+package io.snappydata.gpu
+
+object SnappyGpuNative {
+  // loaded opportunistically like org.apache.spark.unsafe.Native
+  // (cluster/src/test/scala/org/apache/spark/unsafe/NativeUTF8StringPropertyCheckSuite.scala:58)
+  lazy val isLoaded: Boolean = try {
+    System.loadLibrary("snappygpujni"); true
+  } catch { case _: UnsatisfiedLinkError => false }
+
+  @native def init(device: Int): Int
+  @native def planCreate(planDescAddr: Long): Long
+  @native def planSetLiterals(plan: Long, literalsAddr: Long, n: Int): Unit
+  @native def batchSubmit(plan: Long, numRows: Int, nCols: Int,
+      colAddrs: Array[Long], colLens: Array[Long], heapCols: Array[Array[Byte]],
+      delta0Addrs: Array[Long], delta0Lens: Array[Long], delta1Addrs: Array[Long], delta1Lens: Array[Long],
+      deleteAddr: Long, deleteLen: Long, statsAddr: Long, statsLen: Long, statsNCols: Int,
+      bucketId: Int, batchId: Long): Unit
+  @native def rowsSubmit(plan: Long, rowsAddr: Long, len: Long, nrows: Int): Unit
+  @native def planFinish(plan: Long, outAddr: Long, cap: Long): Long
+  @native def planReset(plan: Long): Unit
+  @native def planMetrics(plan: Long, out: Array[Long]): Unit
+  @native def planDestroy(plan: Long): Unit
+  @native def finalMerge(planDescAddr: Long, rowsAddr: Long, len: Long, outAddr: Long, cap: Long): Long
+}

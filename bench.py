@@ -58,6 +58,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic_per_row(q1):
+    """DRAM bytes per row of the scan kernel from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["q1" if q1 else "q6"]
+        return (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["rows"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -351,8 +360,10 @@ def main():
            "config": workload_config(q1, total, world), "gpu_launches": launches_timed, "clocks": clocks}
     peak, peak_src = measured_peak_gbs()
     achieved = algo_per_launch / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
+    tpr = ncu_traffic_per_row(q1)
     out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                       "traffic": None, "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
+                       "traffic": (tpr * main_run.local_rows) if tpr else None,
+                       "traffic_source": "profiles/r01_traffic.json (ncu --set full, 200M-row launch) scaled by rows", "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
                        "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": algo_per_launch,
                        "note": "per rank (rank 0); one launch scans the rank's whole shard"}
     out["hbm_gbs_whole_job"] = total * (40 if q1 else 28) / (ms / args.steps / 1e3) / 1e9

@@ -371,15 +371,18 @@ class Plan:
         self.api.check(self.api.plan_reset(self.h))
         return self
 
-    def final_merge(self, partial_raw: bytes) -> List[List[object]]:
-        """Final merge of partial rows (all partitions) reusing this handle's plan analysis."""
+    def final_merge_raw(self, partial_raw: bytes) -> bytes:
+        """Final merge of partial rows (all partitions) reusing this handle's plan analysis -> final row stream."""
         cap = max(1 << 14, 4 * len(partial_raw) + 1024)
         if getattr(self, "_merge_buf", None) is None or len(self._merge_buf) < cap:
             self._merge_buf = C.create_string_buffer(cap)
         out_len, out_rows = C.c_int64(), C.c_int64()
         self.api.check(self.api.plan_final_merge(self.h, _buf_ptr(partial_raw), len(partial_raw), self._merge_buf, cap,
                                                  C.byref(out_len), C.byref(out_rows)))
-        return parse_row_stream(self._merge_buf.raw[: out_len.value], self.desc.final_schema())
+        return self._merge_buf.raw[: out_len.value]
+
+    def final_merge(self, partial_raw: bytes) -> List[List[object]]:
+        return parse_row_stream(self.final_merge_raw(partial_raw), self.desc.final_schema())
 
     def metrics(self) -> Dict[str, int]:
         out = (C.c_int64 * SD_NUM_METRICS)()

@@ -33,25 +33,28 @@ class PartialRowExchange:
         self.pin_out = torch.zeros(SLOT_BYTES * world, dtype=torch.uint8)
         if cuda:
             self.pin_in, self.pin_out = self.pin_in.pin_memory(), self.pin_out.pin_memory()
+        self.np_in = self.pin_in.numpy()      # views over the (pinned) staging buffers
+        self.np_out = self.pin_out.numpy()
+        self.len_view = self.np_in[:8].view("<i8")
         self.cuda = cuda
 
     def all_gather(self, raw: bytes) -> bytes:
         """-> concatenation of every rank's partial rows, in rank order."""
-        torch = self.torch
         n = len(raw)
         if n + 8 > SLOT_BYTES:
             raise ValueError(f"partial rows of one partition ({n} bytes) exceed the {SLOT_BYTES}-byte gather slot")
-        self.pin_in[:8] = torch.frombuffer(bytearray(n.to_bytes(8, "little")), dtype=torch.uint8)
+        self.len_view[0] = n
         if n:
-            self.pin_in[8:8 + n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            self.np_in[8:8 + n] = memoryview(raw)
         self.inp.copy_(self.pin_in, non_blocking=True)
         self.dist.all_gather_into_tensor(self.out, self.inp)
         self.pin_out.copy_(self.out, non_blocking=True)
         if self.cuda:
-            torch.cuda.current_stream().synchronize()
-        allb = bytes(self.pin_out.numpy())
+            self.torch.cuda.current_stream().synchronize()
+        o = self.np_out
         parts = []
         for r in range(self.world):
-            ln = int.from_bytes(allb[r * SLOT_BYTES: r * SLOT_BYTES + 8], "little")
-            parts.append(allb[r * SLOT_BYTES + 8: r * SLOT_BYTES + 8 + ln])
+            base = r * SLOT_BYTES
+            ln = int(o[base: base + 8].view("<i8")[0])
+            parts.append(o[base + 8: base + 8 + ln].tobytes())
         return b"".join(parts)

@@ -449,6 +449,24 @@ struct Gen {
       }
       grp << "    return " << g << ";\n";
     } else grp << "    return 0;\n";
+    std::ostringstream keyfn;
+    if (p.mode == MODE_HASH) {
+      std::fill(done.begin(), done.end(), 0);
+      for (size_t k = 0; k < p.keys.size(); k++) {
+        const sd_expr& e = p.exprs[p.keys[k]];
+        if (e.op == SD_OP_COL && e.type == SD_STRING) {   // dictionary column: query-global id from the per-batch key map
+          p.tables.push_back(TableSpec{TABLE_KEYMAP, e.a, -1, (int)k});
+          const int t = (int)p.tables.size() - 1;
+          keyfn << "    kc[" << k << "] = ctx.key_id(" << t << ", r.c" << e.a << ");\n";
+          if (p.cols[e.a].nullable) keyfn << "    if (r.n" << e.a << ") { knull |= " << (1u << k) << "u; kc[" << k << "] = 0; }\n";
+        } else {
+          int rc = emit_node(p.keys[k], done, keyfn);
+          if (rc) return rc;
+          const std::string N = std::to_string(p.keys[k]);
+          keyfn << "    kc[" << k << "] = n" << N << " ? 0 : (int64_t)v" << N << "; if (n" << N << ") knull |= " << (1u << k) << "u;\n";
+        }
+      }
+    }
 
     std::fill(done.begin(), done.end(), 0);
     sig << ";slots=";
@@ -486,7 +504,8 @@ struct Gen {
     o << "// signature: " << p.signature << "\n";
     o << "struct " << p.struct_name << " {\n";
     o << "  static constexpr int NC = " << nc << ";\n  static constexpr int NSLOT = " << ns << ";\n";
-    o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : "sd::MODE_NOKEY") << ";\n";
+    o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : p.mode == MODE_HASH ? "sd::MODE_HASH" : "sd::MODE_NOKEY") << ";\n";
+    o << "  static constexpr int NKEYS = " << p.keys.size() << ";\n";
     o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
     o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
     o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
@@ -505,6 +524,7 @@ struct Gen {
     o << "    }\n  };\n";
     o << "  __device__ static __forceinline__ bool filter(const Row& r, const sd::RowCtx& ctx) {\n" << filt.str() << "  }\n";
     o << "  __device__ static __forceinline__ int group(const Row& r, const sd::RowCtx& ctx) {\n" << grp.str() << "  }\n";
+    o << "  __device__ static __forceinline__ void keys(const Row& r, const sd::RowCtx& ctx, int64_t* kc, uint32_t& knull) {\n" << keyfn.str() << "  }\n";
     o << "  __device__ static __forceinline__ void slots(const Row& r, const sd::RowCtx& ctx, uint64_t* sv) {\n" << slt.str() << "  }\n";
     o << "};\n";
     p.source = o.str();
@@ -535,7 +555,17 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
   g.nullability();
   if (out.aggs.empty() && out.keys.empty())
     { err = "projection-only plans (no aggregate) are not implemented in the GPU path yet"; return SD_ERR_UNSUPPORTED; }
-  out.mode = out.keys.empty() ? MODE_NOKEY : MODE_GROUPS;
+  out.mode = MODE_NOKEY;
+  if (!out.keys.empty()) {
+    bool all_dict_strings = true;
+    for (int k : out.keys) {
+      const sd_expr& e = out.exprs[k];
+      if (!(e.op == SD_OP_COL && e.type == SD_STRING)) all_dict_strings = false;
+      if (e.type == SD_STRING && e.op != SD_OP_COL) { err = "STRING group key that is not a dictionary column"; return SD_ERR_UNSUPPORTED; }
+      if (type_is_fp(e.type)) { err = "FLOAT/DOUBLE group keys are not supported by the GPU path yet"; return SD_ERR_UNSUPPORTED; }
+    }
+    out.mode = (all_dict_strings && !(opt && opt->force_hash)) ? MODE_GROUPS : MODE_HASH;
+  }
   // kernel shape (see tools/sweep.sh for the measurements behind the defaults): staged fast path on;
   // 4 rows per thread per tile; narrow no-key scans run 3 CTAs per SM, register-table group-bys 1.
   {

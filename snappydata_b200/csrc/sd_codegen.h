@@ -54,7 +54,7 @@ struct PlanSpec {
   std::vector<SlotSpec> slots;
   std::vector<AggMap> agg_map;
   int rows_slot = -1;                // COUNT(*)-like slot that tells which groups exist
-  int mode = 0;                      // MODE_NOKEY | MODE_GROUPS
+  int mode = 0;                      // MODE_NOKEY | MODE_GROUPS | MODE_HASH
   int rpt = 4;                       // rows per thread per tile (2, 4, 8)
   int min_ctas = 2;                  // __launch_bounds__ min CTAs per SM (= target CTAs per SM)
   int stages = 1;                    // > 0: staged fast path (producer warp + cp.async.bulk ring); 0: direct loads
@@ -73,6 +73,7 @@ struct CodegenOptions {
   int stages = -1;
   int reg_groups = 0;
   int lit_nullable = 0;
+  int force_hash = 0;   // keyed plans: use the hash table even when all keys are dictionary strings
 };
 
 // Analyse + generate.  Returns SD_OK or an sd_status with `err` set.

@@ -100,7 +100,25 @@ struct Literals {
 };
 
 // aggregation strategy of a generated plan struct
-enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1 };
+//   MODE_NOKEY  no grouping keys: accumulators in registers
+//   MODE_GROUPS dictionary-STRING keys: dense [group][slot] table over query-global dictionary ids
+//   MODE_HASH   general keys (integral / date / timestamp / boolean / dictionary codes, nullable): open-addressing
+//               hash table in global memory (the role SHAMap / ByteBufferHashMap plays in the reference,
+//               encoders/.../collection/ByteBufferHashMap.scala:136-187)
+enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1, MODE_HASH = 2 };
+
+// Device hash table of MODE_HASH: entry e = state[e] (0 empty, 1 being written, 2 full), keys[e][NK] (int64 codes),
+// knull[e] (bit k: key k is NULL), vals[e][NSLOT].
+struct HashTable {
+  uint32_t* state;
+  int64_t* keys;
+  uint32_t* knull;
+  uint64_t* vals;
+  uint32_t mask;          // capacity - 1 (capacity is a power of two)
+  uint32_t max_probe;
+  uint32_t* overflow;     // set to 1 when an insert gives up: the host grows the table and replays
+  uint32_t* count;        // number of distinct keys inserted
+};
 
 // where the dense [group][slot] table of a MODE_GROUPS launch lives (chosen per launch from its size):
 //   TABLE_PRIVATE        one private copy per thread in shared memory, no atomics (few groups: TPC-H Q1)
@@ -126,6 +144,7 @@ struct ScanArgs {
   int32_t table_mode;             // TABLE_PRIVATE | TABLE_SHARED_ATOMIC | TABLE_GLOBAL_ATOMIC
   int32_t ring_off;               // byte offset of [mbarriers][stage ring] in dynamic shared memory
   int32_t nstages;                // stages of the ring actually allocated (<= MAX_STAGES)
+  HashTable hash;                 // MODE_HASH
   int32_t radix[MAX_KEYS];        // group index = ((g0 * radix[1] + g1) * radix[2] + g2) ...
   // projection mode
   uint8_t* out_rows;              // projected output (PROJECT mode)

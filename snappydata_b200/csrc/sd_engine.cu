@@ -280,6 +280,13 @@ struct sd_plan {
     int32_t radix[MAX_KEYS] = {1, 1, 1, 1}; int ngroups = 1; bool valid = false;
   } cache;
   Arena cache_arena;
+  // MODE_HASH group table + the launches of this execution (replayed after a grow)
+  HashTable hash = {};
+  uint32_t hash_capacity = 0;
+  uint64_t* d_hash_ident = nullptr;
+  bool hash_init = false;
+  struct Launch { const void* d_batches; const int32_t* d_prefix; int nbatches; int total_chunks; };
+  std::vector<Launch> launch_log;
   int64_t metrics[SD_NUM_METRICS] = {0};
   float agg_ms = 0;
   bool have_timing = false;
@@ -480,14 +487,58 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
   return 0;
 }
 
-int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks) {
+void hash_free(sd_plan* p) {
+  if (p->hash.state) cudaFree(p->hash.state);
+  if (p->hash.keys) cudaFree(p->hash.keys);
+  if (p->hash.knull) cudaFree(p->hash.knull);
+  if (p->hash.vals) cudaFree(p->hash.vals);
+  if (p->hash.overflow) cudaFree(p->hash.overflow);
+  p->hash = HashTable{};
+  p->hash_capacity = 0;
+}
+
+int hash_ensure(sd_plan* p, uint32_t capacity) {
+  const int ns = (int)p->spec.slots.size(), nk = std::max<int>(1, (int)p->spec.keys.size());
+  if (p->hash_capacity != capacity) {
+    hash_free(p);
+    SD_CUDA(cudaMalloc(&p->hash.state, (size_t)capacity * 4));
+    SD_CUDA(cudaMalloc(&p->hash.keys, (size_t)capacity * nk * 8));
+    SD_CUDA(cudaMalloc(&p->hash.knull, (size_t)capacity * 4));
+    SD_CUDA(cudaMalloc(&p->hash.vals, (size_t)capacity * ns * 8));
+    SD_CUDA(cudaMalloc(&p->hash.overflow, 64));
+    p->hash.count = p->hash.overflow + 8;
+    p->hash.mask = capacity - 1;
+    p->hash.max_probe = std::min<uint32_t>(capacity, 4096);
+    p->hash_capacity = capacity;
+    p->hash_init = false;
+  }
+  if (!p->d_hash_ident) {
+    std::vector<uint64_t> id(ns);
+    for (int s = 0; s < ns; s++) {
+      const int op = p->spec.slots[s].op;
+      id[s] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+            : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull : op == SLOT_MAX_F64 ? 0xfff0000000000000ull : 0ull;
+    }
+    SD_CUDA(cudaMalloc(&p->d_hash_ident, (size_t)std::max(ns, 1) * 8));
+    SD_CUDA(cudaMemcpy(p->d_hash_ident, id.data(), (size_t)ns * 8, cudaMemcpyHostToDevice));
+  }
+  if (!p->hash_init) {
+    int rc = hash_table_init(p->stream, p->hash, capacity, ns, p->d_hash_ident);
+    if (rc) return rc;
+    p->hash_init = true;
+  }
+  return 0;
+}
+
+int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks, bool replay = false) {
+  if (!replay && p->spec.mode == MODE_HASH) p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks});
   if (nbatches == 0 || total_chunks == 0) return 0;
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
   // group radices from the current key dictionaries
   int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
   int ngroups = 1;
-  for (int k = 0; k < nk; k++) {
+  for (int k = 0; k < nk && sp.mode == MODE_GROUPS; k++) {
     radix[k] = std::max<int>(1, (int)p->key_vals[k].size());
     if ((int64_t)ngroups * radix[k] > (1 << 20)) return set_error(SD_ERR_UNSUPPORTED, "group cardinality too high for the dense group table");
     ngroups *= radix[k];
@@ -554,7 +605,10 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     smem = ring_off + ring_fixed + (size_t)nstages * k->stage_bytes;
   }
   if (p->active != k) { p->active = k; p->kernel_name = k->origin + ":" + k->name + (table_mode == TABLE_REGS ? "+regtable" : ""); }
-  if (!p->result_init) {
+  if (sp.mode == MODE_HASH) {
+    int rc = hash_ensure(p, p->hash_capacity ? p->hash_capacity : (1u << 16));
+    if (rc) return rc;
+  } else if (!p->result_init) {
     int rc = init_result(p, ngroups);
     if (rc) return rc;
   } else if (ngroups != p->ngroups || memcmp(radix, p->radix, sizeof(radix)) != 0) {
@@ -594,6 +648,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.table_mode = table_mode;
   args.ring_off = (int32_t)ring_off;
   args.nstages = nstages;
+  args.hash = p->hash;
   memcpy(args.radix, radix, sizeof(radix));
   for (size_t i = 0; i < p->lits.size(); i++) {
     args.lits.i[i] = p->lits[i].i;
@@ -646,6 +701,101 @@ int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int devi
   kernel_registry().push_back(k);
   *out = k;
   if (spec_out) *spec_out = spec;
+  return 0;
+}
+
+// partial-row fields of one group from its slot values (shared by the dense and the hash paths)
+void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>& vals) {
+  for (auto& m : sp.agg_map) {
+    HVal v;
+    const uint64_t raw = sv[m.value_slot];
+    const int64_t cnt = m.count_slot >= 0 ? (int64_t)sv[m.count_slot] : 1;
+    switch (m.fn) {
+      case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: v.i = (int64_t)raw; vals.push_back(v); break;
+      case SD_AGG_SUM:
+        if (m.buf_nullable && cnt == 0) v.isnull = true;
+        else if (m.buf_type == SD_DOUBLE) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
+        vals.push_back(v); break;
+      case SD_AGG_AVG: {
+        memcpy(&v.d, &raw, 8); vals.push_back(v);
+        HVal c; c.i = cnt; vals.push_back(c); break;
+      }
+      default:
+        if (m.buf_nullable && cnt == 0) v.isnull = true;
+        else if (type_is_fp(m.buf_type)) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
+        vals.push_back(v); break;
+    }
+  }
+}
+
+// MODE_HASH: grow + replay on overflow, compact the occupied entries, emit partial rows
+int finish_hash(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+  const PlanSpec& sp = p->spec;
+  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  if (!p->hash_capacity) { int rc = hash_ensure(p, 1u << 16); if (rc) return rc; }
+  uint32_t flags[16];
+  for (;;) {
+    SD_CUDA(cudaMemcpyAsync(flags, p->hash.overflow, 64, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaStreamSynchronize(p->stream));
+    const uint32_t overflow = flags[0], count = flags[8];
+    if (!overflow && (uint64_t)count * 2 <= p->hash_capacity) break;
+    // too full (or an insert gave up): grow and replay every launch of this execution over the same bytes
+    if (p->hash_capacity >= (1u << 28)) return set_error(SD_ERR_UNSUPPORTED, "group-by hash table would exceed 2^28 entries");
+    uint32_t ncap = p->hash_capacity * 8;
+    while ((uint64_t)count * 4 > ncap && ncap < (1u << 28)) ncap *= 2;
+    int rc = hash_ensure(p, ncap);
+    if (rc) return rc;
+    SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
+    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, true); if (rc) return rc; }
+  }
+  const uint32_t count = flags[8];
+  // compact -> host
+  int64_t* d_keys = nullptr; uint32_t* d_knull = nullptr; uint64_t* d_vals = nullptr; uint32_t* d_cursor = nullptr;
+  const size_t n = std::max<uint32_t>(count, 1);
+  SD_CUDA(cudaMalloc(&d_keys, n * std::max(nk, 1) * 8));
+  SD_CUDA(cudaMalloc(&d_knull, n * 4));
+  SD_CUDA(cudaMalloc(&d_vals, n * ns * 8));
+  SD_CUDA(cudaMalloc(&d_cursor, 64));
+  int rc = hash_table_compact(p->stream, p->hash, p->hash_capacity, nk, ns, d_keys, d_knull, d_vals, d_cursor);
+  if (rc) return rc;
+  std::vector<int64_t> hk((size_t)count * nk);
+  std::vector<uint32_t> hn(count);
+  std::vector<uint64_t> hv((size_t)count * ns);
+  unsigned long long counters[2] = {0, 0};
+  if (count) {
+    SD_CUDA(cudaMemcpyAsync(hk.data(), d_keys, hk.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaMemcpyAsync(hn.data(), d_knull, hn.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaMemcpyAsync(hv.data(), d_vals, hv.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+  }
+  SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  cudaFree(d_keys); cudaFree(d_knull); cudaFree(d_vals); cudaFree(d_cursor);
+  if (p->have_timing) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms; }
+  p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
+  p->metrics[8] = (int64_t)counters[0];
+  p->metrics[11] = (int64_t)counters[0];
+  std::vector<int> types;
+  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
+  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  std::vector<uint8_t> out;
+  for (uint32_t g = 0; g < count; g++) {
+    std::vector<HVal> vals;
+    for (int k = 0; k < nk; k++) {
+      HVal v;
+      const int64_t code = hk[(size_t)g * nk + k];
+      if ((hn[g] >> k) & 1u) v.isnull = true;
+      else if (types[k] == SD_STRING) v.s = p->key_vals[k][(size_t)code];
+      else v.i = code;
+      vals.push_back(v);
+    }
+    append_agg_fields(sp, &hv[(size_t)g * ns], vals);
+    emit_unsafe_row(out, types, vals);
+  }
+  p->metrics[0] = count;
+  *out_len = (int64_t)out.size();
+  if (out_nrows) *out_nrows = count;
+  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", out.size());
+  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
   return 0;
 }
 
@@ -822,6 +972,7 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   if (rc) return rc;
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  if (sp.mode == MODE_HASH) return finish_hash(p, out_rows, cap, out_len, out_nrows);
   if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
   const size_t ne = (size_t)p->ngroups * ns;
   rc = ensure_result(p, ne);
@@ -855,26 +1006,7 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
       if (idx[k] == p->key_null_id[k]) v.isnull = true; else v.s = p->key_vals[k][idx[k]];
       vals.push_back(v);
     }
-    for (auto& m : sp.agg_map) {
-      HVal v;
-      const uint64_t raw = sv[m.value_slot];
-      const int64_t cnt = m.count_slot >= 0 ? (int64_t)sv[m.count_slot] : 1;
-      switch (m.fn) {
-        case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: v.i = (int64_t)raw; vals.push_back(v); break;
-        case SD_AGG_SUM:
-          if (m.buf_nullable && cnt == 0) v.isnull = true;
-          else if (m.buf_type == SD_DOUBLE) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
-          vals.push_back(v); break;
-        case SD_AGG_AVG: {
-          memcpy(&v.d, &raw, 8); vals.push_back(v);
-          HVal c; c.i = cnt; vals.push_back(c); break;
-        }
-        default:
-          if (m.buf_nullable && cnt == 0) v.isnull = true;
-          else if (type_is_fp(m.buf_type)) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
-          vals.push_back(v); break;
-      }
-    }
+    append_agg_fields(sp, sv, vals);
     emit_unsafe_row(out, types, vals);
     nrows++;
   }
@@ -893,6 +1025,8 @@ int sd_plan_reset(sd_plan* p) {
   p->pending.clear();
   p->pending_bytes = 0;
   p->result_init = false;
+  p->hash_init = false;
+  p->launch_log.clear();
   p->have_timing = false;
   p->agg_ms = 0;
   SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
@@ -924,6 +1058,8 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->d_result) cudaFree(p->d_result);
   if (p->h_pinned) cudaFreeHost(p->h_pinned);
   if (p->d_partials) cudaFree(p->d_partials);
+  hash_free(p);
+  if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);
   if (p->d_counters) cudaFree(p->d_counters);
   if (p->priv) sd_store_destroy(p->priv);

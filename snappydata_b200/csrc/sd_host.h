@@ -48,6 +48,11 @@ int kernel_launch(const KernelEntry& k, int grid, size_t smem, cudaStream_t stre
 // NVRTC path (sd_jit.cpp): compile `spec.source` against the embedded kernel headers.
 int jit_compile(const PlanSpec& spec, int device, KernelEntry& out);
 
+// ---- MODE_HASH group table housekeeping (sd_hash.cu) ------------------------------------------------
+int hash_table_init(cudaStream_t stream, const HashTable& t, uint32_t capacity, int nslot, const uint64_t* d_ident);
+int hash_table_compact(cudaStream_t stream, const HashTable& t, uint32_t capacity, int nk, int nslot, int64_t* out_keys,
+                       uint32_t* out_knull, uint64_t* out_vals, uint32_t* d_cursor);
+
 // ---- device memory arena: bump allocation out of large slabs ---------------------------------------
 struct Arena {
   int device = 0;

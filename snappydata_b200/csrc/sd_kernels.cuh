@@ -106,6 +106,43 @@ __device__ __forceinline__ void slot_atomic(int op, uint64_t* p, uint64_t v) {
   }
 }
 
+// ---- MODE_HASH: find-or-insert of a key tuple, then atomic slot updates ---------------------------------
+__device__ __forceinline__ uint64_t hash_mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  h *= 0xff51afd7ed558ccdull;
+  return h ^ (h >> 33);
+}
+template <int NK>
+__device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const int64_t* kc, uint32_t knull) {
+  uint64_t h = 0x2545f4914f6cdd1dull ^ knull;
+#pragma unroll
+  for (int k = 0; k < NK; k++) h = hash_mix64(h, (uint64_t)kc[k]);
+  uint32_t pos = (uint32_t)h & t.mask;
+  for (uint32_t probe = 0; probe < t.max_probe; probe++, pos = (pos + 1) & t.mask) {
+    uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);
+    if (st == 0u) {
+      st = atomicCAS(&t.state[pos], 0u, 1u);
+      if (st == 0u) {   // we own the entry: publish the key, then mark it full
+#pragma unroll
+        for (int k = 0; k < NK; k++) t.keys[(size_t)pos * NK + k] = kc[k];
+        t.knull[pos] = knull;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(&t.state[pos]) = 2u;
+        atomicAdd(t.count, 1u);
+        return pos;
+      }
+    }
+    while (st == 1u) { __nanosleep(20); st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]); }   // writer in flight
+    __threadfence();
+    bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
+#pragma unroll
+    for (int k = 0; k < NK; k++) same = same && *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]) == kc[k];
+    if (same) return pos;
+  }
+  atomicExch(t.overflow, 1u);
+  return -1;
+}
+
 // ---- loads ------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T ld_at(const uint8_t* base, int64_t k) {
   return *reinterpret_cast<const T*>(base + k * (int64_t)sizeof(T));
@@ -575,6 +612,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   } else if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
+  } else if (PLAN::MODE == MODE_HASH) {
+    // nothing per CTA: the table is global
   } else if (args.table_mode == TABLE_PRIVATE) {
     // private table of thread t: entry e at table[e * THREADS + t]: lanes hit distinct banks
     for (int e = 0; e < NE; e++) table[e * THREADS + tid] = slot_identity(PLAN::slot_op(e % NSLOT));
@@ -658,6 +697,18 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 #pragma unroll
           for (int s = 0; s < NSLOT; s++) acc[s] = slot_combine(PLAN::slot_op(s), acc[s], sv[s]);
         } else {
+          if (PLAN::MODE == MODE_HASH) {
+            int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
+            uint32_t knull = 0;
+            PLAN::keys(row, ctx, kc, knull);
+            const int64_t e = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1)>(args.hash, kc, knull);
+            if (e >= 0) {
+              uint64_t* t = args.hash.vals + (size_t)e * NSLOT;
+#pragma unroll
+              for (int s = 0; s < NSLOT; s++) slot_atomic(PLAN::slot_op(s), t + s, sv[s]);
+            }
+            continue;
+          }
           const int g = PLAN::group(row, ctx);
           if (RG > 0) {   // predicated register accumulators: no memory traffic, no dependent smem chains
 #pragma unroll
@@ -687,7 +738,9 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
   const int lane = tid & 31, warp = tid >> 5;
-  if (PLAN::MODE == MODE_NOKEY) {
+  if (PLAN::MODE == MODE_HASH) {
+    // results live in the global hash table
+  } else if (PLAN::MODE == MODE_NOKEY) {
     uint64_t* scratch = table;   // [NSLOT][THREADS/32]
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
@@ -740,7 +793,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   if (tid == 0) is_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
   consumer_sync();
-  if (is_last && !(PLAN::MODE == MODE_GROUPS && args.table_mode == TABLE_GLOBAL_ATOMIC)) {
+  if (is_last && PLAN::MODE != MODE_HASH && !(PLAN::MODE == MODE_GROUPS && args.table_mode == TABLE_GLOBAL_ATOMIC)) {
     __threadfence();
     for (int e = tid; e < NE; e += THREADS) {
       const int op = PLAN::slot_op_rt(e % NSLOT);

@@ -245,3 +245,55 @@ def test_errors_not_fallbacks(gpu_api):
     with pytest.raises(capi.SdError) as e:
         gp.submit(ColumnBatch(num_rows=5000, columns=[comp]))
     assert e.value.code == capi.SD_ERR_UNSUPPORTED
+
+
+# ---- MODE_HASH: general (non dictionary-string) group keys -------------------------------------------
+def test_group_by_nullable_int_key_hash_table(gpu_api, batches):
+    """Integer key with NULLs (SHAByteBufferTest.scala:225-331 shapes): the device hash table."""
+    b = PlanBuilder()
+    c = cols(b)
+    b.filter(c["c5"] >= b.lit(T.DATE))
+    b.group_by(c["c0"])
+    b.count().sum(c["c1"]).avg(c["c2"]).min(c["c7"]).max(c["c9"])
+    gp, _, got = both(gpu_api, b.build(), [9003], batches, 1)
+    assert any(r[0] is None for r in got) and len(got) > 1500
+
+
+def test_group_by_composite_keys_int_string_date_bool(gpu_api, batches):
+    b = PlanBuilder()
+    c = cols(b)
+    b.group_by(c["c6"], c["c3"], c["c5"], c["c4"])
+    b.count().sum(c["c2"]).max(c["c0"]).sum(c["c8"])
+    both(gpu_api, b.build(), [], batches, 4)
+
+
+def test_group_by_expression_key_and_long_key(gpu_api, batches):
+    b = PlanBuilder()
+    c = cols(b)
+    b.group_by((c["c0"] + c["c6"].cast(T.INT)), c["c11"])
+    b.count().sum(c["c1"])
+    both(gpu_api, b.build(), [], batches[:1], 2)
+
+
+def test_high_cardinality_group_by_grows_the_hash_table(gpu_api):
+    """More distinct keys than the initial table holds: the engine grows the table and replays the launches."""
+    r = np.random.default_rng(3)
+    n = 120_000
+    schema = [("k", T.LONG, False), ("v", T.DOUBLE, False), ("w", T.INT, True)]
+    bs = []
+    for i in range(3):
+        data = {"k": r.integers(0, 90_000, n).astype(np.int64) * 7919 - 10**9, "v": r.normal(0, 1, n), "w": r.integers(0, 5, n).astype(np.int32)}
+        bs.append(build_batch(n, schema, data, {"w": r.random(n) < 0.3}, batch_id=i))
+    b = PlanBuilder()
+    k = b.col(T.LONG, 0, False)
+    v = b.col(T.DOUBLE, 1, False)
+    w = b.col(T.INT, 2, True)
+    b.group_by(k)
+    b.count().sum(v).count(w).min(w)
+    gp, op, got = both(gpu_api, b.build(), [], bs, 1)
+    assert len(got) > 80_000
+    # and the store-resident path re-executes (cached descriptors, table re-initialised) with the same answer
+    gp.reset().set_literals([])
+    for x in bs:
+        gp.submit(x)
+    assert_rowsets_match(gp.finish(), got, 1)

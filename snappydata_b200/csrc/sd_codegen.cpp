@@ -449,6 +449,20 @@ struct Gen {
       }
       grp << "    return " << g << ";\n";
     } else grp << "    return 0;\n";
+    std::ostringstream projfn;
+    if (p.mode == MODE_PROJECT) {
+      std::fill(done.begin(), done.end(), 0);
+      sig << ";proj=";
+      for (size_t j = 0; j < p.proj.size(); j++) {
+        const sd_expr& e = p.exprs[p.proj[j]];
+        sig << (j ? "," : "") << expr_text(p, p.proj[j]);
+        int rc = emit_node(p.proj[j], done, projfn);
+        if (rc) return rc;
+        const std::string N = std::to_string(p.proj[j]);
+        projfn << "    pv[" << j << "] = " << (type_is_fp(e.type) ? "sd::f2u((double)v" + N + ")" : "(uint64_t)(int64_t)v" + N)
+               << "; if (n" << N << ") pnull |= " << (1u << j) << "u;\n";
+      }
+    }
     std::ostringstream keyfn;
     if (p.mode == MODE_HASH) {
       std::fill(done.begin(), done.end(), 0);
@@ -504,8 +518,9 @@ struct Gen {
     o << "// signature: " << p.signature << "\n";
     o << "struct " << p.struct_name << " {\n";
     o << "  static constexpr int NC = " << nc << ";\n  static constexpr int NSLOT = " << ns << ";\n";
-    o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : p.mode == MODE_HASH ? "sd::MODE_HASH" : "sd::MODE_NOKEY") << ";\n";
+    o << "  static constexpr int MODE = " << (p.mode == MODE_GROUPS ? "sd::MODE_GROUPS" : p.mode == MODE_HASH ? "sd::MODE_HASH" : p.mode == MODE_PROJECT ? "sd::MODE_PROJECT" : "sd::MODE_NOKEY") << ";\n";
     o << "  static constexpr int NKEYS = " << p.keys.size() << ";\n";
+    o << "  static constexpr int NPROJ = " << p.proj.size() << ";\n";
     o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
     o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
     o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
@@ -524,6 +539,7 @@ struct Gen {
     o << "    }\n  };\n";
     o << "  __device__ static __forceinline__ bool filter(const Row& r, const sd::RowCtx& ctx) {\n" << filt.str() << "  }\n";
     o << "  __device__ static __forceinline__ int group(const Row& r, const sd::RowCtx& ctx) {\n" << grp.str() << "  }\n";
+    o << "  __device__ static __forceinline__ void project(const Row& r, const sd::RowCtx& ctx, uint64_t* pv, uint32_t& pnull) {\n" << projfn.str() << "  }\n";
     o << "  __device__ static __forceinline__ void keys(const Row& r, const sd::RowCtx& ctx, int64_t* kc, uint32_t& knull) {\n" << keyfn.str() << "  }\n";
     o << "  __device__ static __forceinline__ void slots(const Row& r, const sd::RowCtx& ctx, uint64_t* sv) {\n" << slt.str() << "  }\n";
     o << "};\n";
@@ -553,9 +569,16 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
   if (rc) return rc;
   for (auto& c : out.cols) out.kinds.push_back(kind_of_type(c.type));
   g.nullability();
-  if (out.aggs.empty() && out.keys.empty())
-    { err = "projection-only plans (no aggregate) are not implemented in the GPU path yet"; return SD_ERR_UNSUPPORTED; }
-  out.mode = MODE_NOKEY;
+  const bool projection = out.aggs.empty() && out.keys.empty();
+  if (projection && out.proj.empty()) { err = "plan has neither aggregates nor projection columns"; return SD_ERR_INVALID; }
+  if (projection) {
+    if (out.proj.size() > 32) { err = "more than 32 projected columns"; return SD_ERR_UNSUPPORTED; }
+    for (int n : out.proj) {
+      const sd_expr& e = out.exprs[n];
+      if (e.type == SD_STRING && e.op != SD_OP_COL) { err = "projected STRING expression that is not a dictionary column"; return SD_ERR_UNSUPPORTED; }
+    }
+  }
+  out.mode = projection ? MODE_PROJECT : MODE_NOKEY;
   if (!out.keys.empty()) {
     bool all_dict_strings = true;
     for (int k : out.keys) {
@@ -586,8 +609,7 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
     if (o.stages >= 0) out.stages = o.stages > 0 ? 1 : 0;
     if (out.stages == 0) out.reg_groups = 0;   // the register tables are reduced through the ring's memory
   }
-  rc = g.build_slots();
-  if (rc) return rc;
+  if (!projection) { rc = g.build_slots(); if (rc) return rc; }
   return g.generate();
 }
 

@@ -105,7 +105,10 @@ struct Literals {
 //   MODE_HASH   general keys (integral / date / timestamp / boolean / dictionary codes, nullable): open-addressing
 //               hash table in global memory (the role SHAMap / ByteBufferHashMap plays in the reference,
 //               encoders/.../collection/ByteBufferHashMap.scala:136-187)
-enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1, MODE_HASH = 2 };
+//   MODE_PROJECT no aggregate: rows that pass the filter are emitted as fixed-width records
+//               [uint32 batch][uint32 null bits][8 bytes x NPROJ] (strings as dictionary codes; the host
+//               turns records into UnsafeRows)
+enum : int32_t { MODE_NOKEY = 0, MODE_GROUPS = 1, MODE_HASH = 2, MODE_PROJECT = 3 };
 
 // Device hash table of MODE_HASH: entry e = state[e] (0 empty, 1 being written, 2 full), keys[e][NK] (int64 codes),
 // knull[e] (bit k: key k is NULL), vals[e][NSLOT].
@@ -147,9 +150,11 @@ struct ScanArgs {
   HashTable hash;                 // MODE_HASH
   int32_t radix[MAX_KEYS];        // group index = ((g0 * radix[1] + g1) * radix[2] + g2) ...
   // projection mode
-  uint8_t* out_rows;              // projected output (PROJECT mode)
-  unsigned long long* out_count;
-  int64_t out_cap;
+  uint8_t* out_rows;              // MODE_PROJECT: output records
+  unsigned long long* out_count;  // MODE_PROJECT: records produced (may exceed out_cap: the host grows and replays)
+  int64_t out_cap;                // MODE_PROJECT: capacity in records
+  int32_t batch_base;             // MODE_PROJECT: ordinal of this launch's first batch within the execution
+  int32_t pad2_;
   Literals lits;
 };
 

@@ -278,6 +278,7 @@ struct sd_plan {
     const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
     int64_t rows = 0, algo_bytes = 0, seen = 0, skipped = 0, updated_cols = 0, deleted_batches = 0;
     int32_t radix[MAX_KEYS] = {1, 1, 1, 1}; int ngroups = 1; bool valid = false;
+    std::vector<const StoredBatch*> batches;
   } cache;
   Arena cache_arena;
   // MODE_HASH group table + the launches of this execution (replayed after a grow)
@@ -285,7 +286,14 @@ struct sd_plan {
   uint32_t hash_capacity = 0;
   uint64_t* d_hash_ident = nullptr;
   bool hash_init = false;
-  struct Launch { const void* d_batches; const int32_t* d_prefix; int nbatches; int total_chunks; };
+  struct Launch { const void* d_batches; const int32_t* d_prefix; int nbatches; int total_chunks; int batch_base; };
+  // MODE_PROJECT output records + the batches of this execution (records carry a batch ordinal)
+  uint8_t* d_out = nullptr;
+  int64_t out_cap = 0;
+  unsigned long long* d_out_count = nullptr;
+  std::vector<const StoredBatch*> exec_batches;
+  std::vector<uint8_t> finished_rows;   // rows of the last sd_plan_finish (re-served when the caller's buffer was too small)
+  int64_t finished_nrows = -1;
   std::vector<Launch> launch_log;
   int64_t metrics[SD_NUM_METRICS] = {0};
   float agg_ms = 0;
@@ -530,8 +538,27 @@ int hash_ensure(sd_plan* p, uint32_t capacity) {
   return 0;
 }
 
-int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks, bool replay = false) {
-  if (!replay && p->spec.mode == MODE_HASH) p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks});
+int ensure_out(sd_plan* p, int64_t cap_records) {
+  const int64_t rec = 8 + 8 * (int64_t)std::max<size_t>(p->spec.proj.size(), 1);
+  if (!p->d_out_count) { SD_CUDA(cudaMalloc(&p->d_out_count, 64)); SD_CUDA(cudaMemset(p->d_out_count, 0, 64)); }
+  if (cap_records > p->out_cap) {
+    if (p->d_out) cudaFree(p->d_out);
+    p->d_out = nullptr;
+    SD_CUDA(cudaMalloc(&p->d_out, (size_t)(cap_records * rec)));
+    p->out_cap = cap_records;
+  }
+  return 0;
+}
+
+int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks,
+                const std::vector<const StoredBatch*>* blist = nullptr, int replay_batch_base = -1) {
+  const bool replay = replay_batch_base >= 0;
+  int batch_base = replay ? replay_batch_base : (int)p->exec_batches.size();
+  if (!replay && (p->spec.mode == MODE_HASH || p->spec.mode == MODE_PROJECT)) {
+    p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks, batch_base});
+    if (blist) p->exec_batches.insert(p->exec_batches.end(), blist->begin(), blist->end());
+  }
+  p->finished_nrows = -1;
   if (nbatches == 0 || total_chunks == 0) return 0;
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
@@ -608,6 +635,9 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   if (sp.mode == MODE_HASH) {
     int rc = hash_ensure(p, p->hash_capacity ? p->hash_capacity : (1u << 16));
     if (rc) return rc;
+  } else if (sp.mode == MODE_PROJECT) {
+    int rc = ensure_out(p, p->out_cap ? p->out_cap : (int64_t(1) << 20));
+    if (rc) return rc;
   } else if (!p->result_init) {
     int rc = init_result(p, ngroups);
     if (rc) return rc;
@@ -649,6 +679,10 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.ring_off = (int32_t)ring_off;
   args.nstages = nstages;
   args.hash = p->hash;
+  args.out_rows = p->d_out;
+  args.out_count = p->d_out_count;
+  args.out_cap = p->out_cap;
+  args.batch_base = batch_base;
   memcpy(args.radix, radix, sizeof(radix));
   for (size_t i = 0; i < p->lits.size(); i++) {
     args.lits.i[i] = p->lits[i].i;
@@ -674,7 +708,7 @@ int flush_pending(sd_plan* p) {
   p->metrics[3] += bs.updated_cols;
   p->metrics[4] += bs.deleted_batches;
   p->metrics[9] += bs.algo_bytes;
-  rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks);
+  rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks, &list);
   p->pending.clear();
   p->pending_bytes = 0;
   return rc;
@@ -729,7 +763,7 @@ void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>
 }
 
 // MODE_HASH: grow + replay on overflow, compact the occupied entries, emit partial rows
-int finish_hash(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+int finish_hash(sd_plan* p) {
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
   if (!p->hash_capacity) { int rc = hash_ensure(p, 1u << 16); if (rc) return rc; }
@@ -746,7 +780,7 @@ int finish_hash(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64
     int rc = hash_ensure(p, ncap);
     if (rc) return rc;
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
-    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, true); if (rc) return rc; }
+    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
   }
   const uint32_t count = flags[8];
   // compact -> host
@@ -777,7 +811,8 @@ int finish_hash(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64
   std::vector<int> types;
   for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
   for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
-  std::vector<uint8_t> out;
+  std::vector<uint8_t>& out = p->finished_rows;
+  out.clear();
   for (uint32_t g = 0; g < count; g++) {
     std::vector<HVal> vals;
     for (int k = 0; k < nk; k++) {
@@ -791,11 +826,70 @@ int finish_hash(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64
     append_agg_fields(sp, &hv[(size_t)g * ns], vals);
     emit_unsafe_row(out, types, vals);
   }
-  p->metrics[0] = count;
-  *out_len = (int64_t)out.size();
-  if (out_nrows) *out_nrows = count;
-  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", out.size());
-  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
+  p->finished_nrows = count;
+  return 0;
+}
+
+// MODE_PROJECT: grow + replay when the record buffer was too small, then records -> UnsafeRows
+int finish_project(sd_plan* p) {
+  const PlanSpec& sp = p->spec;
+  const int np = (int)sp.proj.size();
+  const int64_t rec = 8 + 8 * (int64_t)np;
+  int rc = ensure_out(p, p->out_cap ? p->out_cap : 1024);
+  if (rc) return rc;
+  unsigned long long count = 0;
+  for (;;) {
+    SD_CUDA(cudaMemcpyAsync(&count, p->d_out_count, 8, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaStreamSynchronize(p->stream));
+    if ((int64_t)count <= p->out_cap) break;
+    rc = ensure_out(p, (int64_t)count + (int64_t)count / 8 + 1024);
+    if (rc) return rc;
+    SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
+    SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
+    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
+  }
+  std::vector<uint64_t> recs((size_t)count * (size_t)(rec / 8));
+  unsigned long long counters[2] = {0, 0};
+  if (count) SD_CUDA(cudaMemcpyAsync(recs.data(), p->d_out, (size_t)count * rec, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  if (p->have_timing) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms; }
+  p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
+  p->metrics[8] = (int64_t)counters[0];
+  p->metrics[11] = (int64_t)counters[0];
+  std::vector<int> types;
+  std::vector<int> str_col(np, -1);
+  for (int j = 0; j < np; j++) {
+    const sd_expr& e = sp.exprs[sp.proj[j]];
+    types.push_back(e.type);
+    if (e.type == SD_STRING) str_col[j] = e.a;
+  }
+  std::vector<uint8_t>& out = p->finished_rows;
+  out.clear();
+  out.reserve((size_t)count * (size_t)(16 + 8 * np));
+  std::vector<HVal> vals((size_t)np);
+  for (unsigned long long i = 0; i < count; i++) {
+    const uint64_t* r = &recs[(size_t)i * (size_t)(rec / 8)];
+    const uint32_t bidx = (uint32_t)(r[0] & 0xffffffffu), pnull = (uint32_t)(r[0] >> 32);
+    if (bidx >= p->exec_batches.size()) return set_error(SD_ERR_CUDA, "corrupt projection record (batch %u)", bidx);
+    const StoredBatch& sb = *p->exec_batches[bidx];
+    for (int j = 0; j < np; j++) {
+      HVal& v = vals[(size_t)j];
+      v = HVal();
+      if ((pnull >> j) & 1u) { v.isnull = true; continue; }
+      const uint64_t raw = r[1 + j];
+      if (types[j] == SD_STRING) {
+        const int c = str_col[j];
+        const StoredCol& sc = sb.cols[sb.positional ? c : sp.cols[c].table_ordinal];
+        const int64_t code = (int64_t)raw;
+        if (code < 0 || code >= (int64_t)sc.dict_strings.size() || code == sc.dev.dict_n) { if (code == sc.dev.dict_n) v.isnull = true; else return set_error(SD_ERR_CUDA, "dictionary code %lld out of range", (long long)code); }
+        else v.s = sc.dict_strings[(size_t)code];
+      } else if (type_is_fp(types[j])) memcpy(&v.d, &raw, 8);
+      else v.i = (int64_t)raw;
+    }
+    emit_unsafe_row(out, types, vals);
+  }
+  p->finished_nrows = (int64_t)count;
   return 0;
 }
 
@@ -955,6 +1049,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
     c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
     c.rows = bs.rows; c.algo_bytes = bs.algo_bytes; c.seen = seen; c.skipped = skipped;
     c.updated_cols = bs.updated_cols; c.deleted_batches = bs.deleted_batches;
+    c.batches = list;
     c.valid = true;
   }
   p->metrics[2] += c.seen;
@@ -962,7 +1057,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   p->metrics[3] += c.updated_cols;
   p->metrics[4] += c.deleted_batches;
   p->metrics[9] += c.algo_bytes;
-  return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks);
+  return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks, &c.batches);
 }
 
 int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
@@ -972,7 +1067,18 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   if (rc) return rc;
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
-  if (sp.mode == MODE_HASH) return finish_hash(p, out_rows, cap, out_len, out_nrows);
+  if (sp.mode == MODE_HASH || sp.mode == MODE_PROJECT) {
+    if (p->finished_nrows < 0) {
+      rc = sp.mode == MODE_HASH ? finish_hash(p) : finish_project(p);
+      if (rc) return rc;
+    }
+    p->metrics[0] = p->finished_nrows;
+    *out_len = (int64_t)p->finished_rows.size();
+    if (out_nrows) *out_nrows = p->finished_nrows;
+    if ((int64_t)p->finished_rows.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", p->finished_rows.size());
+    if (!p->finished_rows.empty()) memcpy(out_rows, p->finished_rows.data(), p->finished_rows.size());
+    return 0;
+  }
   if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
   const size_t ne = (size_t)p->ngroups * ns;
   rc = ensure_result(p, ne);
@@ -1027,6 +1133,9 @@ int sd_plan_reset(sd_plan* p) {
   p->result_init = false;
   p->hash_init = false;
   p->launch_log.clear();
+  p->exec_batches.clear();
+  p->finished_nrows = -1;
+  if (p->d_out_count) SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
   p->have_timing = false;
   p->agg_ms = 0;
   SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
@@ -1059,6 +1168,8 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->h_pinned) cudaFreeHost(p->h_pinned);
   if (p->d_partials) cudaFree(p->d_partials);
   hash_free(p);
+  if (p->d_out) cudaFree(p->d_out);
+  if (p->d_out_count) cudaFree(p->d_out_count);
   if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);
   if (p->d_counters) cudaFree(p->d_counters);

@@ -612,8 +612,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   } else if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
-  } else if (PLAN::MODE == MODE_HASH) {
-    // nothing per CTA: the table is global
+  } else if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
+    // nothing per CTA: the table / output buffer is global
   } else if (args.table_mode == TABLE_PRIVATE) {
     // private table of thread t: entry e at table[e * THREADS + t]: lanes hit distinct banks
     for (int e = 0; e < NE; e++) table[e * THREADS + tid] = slot_identity(PLAN::slot_op(e % NSLOT));
@@ -684,6 +684,41 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 
       // ---- row at a time over registers: filter -> group -> accumulate -------------------------
       c_scanned += __popc(live);
+      if (PLAN::MODE == MODE_PROJECT) {
+        // filter -> project: passing rows become fixed-width records; one atomic per warp per row slot
+        constexpr int NP = PLAN::NPROJ > 0 ? PLAN::NPROJ : 1;
+        constexpr int REC = 8 + 8 * NP;
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          bool pass = false;
+          uint64_t pv[NP];
+          uint32_t pnull = 0;
+          if ((live >> r) & 1u) {
+            typename PLAN::Row row;
+            fill_row<PLAN>(regs, r, row, ColSeq());
+            pass = PLAN::filter(row, ctx);
+            if (pass) PLAN::project(row, ctx, pv, pnull);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (m) {
+            const int lane_id = tid & 31, leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane_id == leader) base = atomicAdd(args.out_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+              c_passed++;
+              const unsigned long long idx = base + __popc(m & ((1u << lane_id) - 1u));
+              if ((int64_t)idx < args.out_cap) {
+                uint64_t* rec = reinterpret_cast<uint64_t*>(args.out_rows + idx * REC);
+                rec[0] = (uint64_t)(uint32_t)(args.batch_base + lo) | ((uint64_t)pnull << 32);
+#pragma unroll
+                for (int j = 0; j < PLAN::NPROJ; j++) rec[1 + j] = pv[j];
+              }
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int r = 0; r < RPT; r++) {
         if (!((live >> r) & 1u)) continue;
@@ -738,8 +773,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
   const int lane = tid & 31, warp = tid >> 5;
-  if (PLAN::MODE == MODE_HASH) {
-    // results live in the global hash table
+  if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
+    // results live in the global hash table / the output record buffer
   } else if (PLAN::MODE == MODE_NOKEY) {
     uint64_t* scratch = table;   // [NSLOT][THREADS/32]
 #pragma unroll
@@ -793,7 +828,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   if (tid == 0) is_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
   consumer_sync();
-  if (is_last && PLAN::MODE != MODE_HASH && !(PLAN::MODE == MODE_GROUPS && args.table_mode == TABLE_GLOBAL_ATOMIC)) {
+  if (is_last && PLAN::MODE != MODE_HASH && PLAN::MODE != MODE_PROJECT && !(PLAN::MODE == MODE_GROUPS && args.table_mode == TABLE_GLOBAL_ATOMIC)) {
     __threadfence();
     for (int e = tid; e < NE; e += THREADS) {
       const int op = PLAN::slot_op_rt(e % NSLOT);

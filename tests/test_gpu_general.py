@@ -297,3 +297,87 @@ def test_high_cardinality_group_by_grows_the_hash_table(gpu_api):
     for x in bs:
         gp.submit(x)
     assert_rowsets_match(gp.finish(), got, 1)
+
+
+# ---- MODE_PROJECT: filter + project, no aggregate (BASELINE.json configs[3]) -----------
+def _rowkey(r):
+    return tuple((0, 0) if v is None else (1, v) if isinstance(v, bytes) else (2, float(v)) for v in r)
+
+
+def make_wide_batch(n, seed, ncols=16, batch_id=0):
+    """c0..c{ncols-1} cycling (INT, DOUBLE, dictionary STRING with 1000 distinct 8-12 byte values); every 4th nullable."""
+    r = np.random.default_rng(seed)
+    schema, data, nulls = [], {}, {}
+    for i in range(ncols):
+        t = (T.INT, T.DOUBLE, T.STRING)[i % 3]
+        nullable = i % 4 == 0
+        name = f"c{i}"
+        schema.append((name, t, nullable))
+        if t == T.INT:
+            data[name] = r.integers(0, 1000, n).astype(np.int32)
+        elif t == T.DOUBLE:
+            data[name] = r.random(n) * 100.0
+        else:
+            data[name] = np.array([b"str%05d_" % x + b"x" * (x % 5) for x in r.integers(0, 1000, n)], dtype=object)
+        if nullable:
+            nulls[name] = r.random(n) < 0.1
+    return build_batch(n, schema, data, nulls, batch_id=batch_id), schema
+
+
+def test_projection_with_filter_wide_table(gpu_api):
+    bs, schema = [], None
+    for i, n in enumerate((20_000, 3_001, 1)):
+        b, schema = make_wide_batch(n, 50 + i, batch_id=i)
+        bs.append(b)
+    pb = PlanBuilder()
+    c = [pb.col(t, i, nullable) for i, (_, t, nullable) in enumerate(schema[:8])]
+    pb.filter((c[0] >= pb.lit(T.INT)) & (c[0] <= pb.lit(T.INT)) & c[2].eq(pb.lit(T.STRING)))
+    pb.project(*c)
+    desc = pb.build()
+    lit = bs[0]  # pick a string literal that exists
+    from snappydata_b200.column_format import decode_column
+    some = decode_column(bs[0].columns[2], T.STRING, bs[0].num_rows)[0][5]
+    for lits in ([0, 999, some], [100, 300, some], [0, 999, b"absent"]):
+        gp = capi.Plan(gpu_api, desc).set_literals(lits)
+        op = oracle.plan(desc).set_literals(lits)
+        for x in bs:
+            gp.submit(x)
+            op.submit(x)
+        got, want = sorted(gp.finish(), key=_rowkey), sorted(op.finish(), key=_rowkey)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g == w
+    # a looser filter: thousands of rows, NULLs in projected columns, projected expression
+    pb = PlanBuilder()
+    c = [pb.col(t, i, nullable) for i, (_, t, nullable) in enumerate(schema[:8])]
+    pb.filter(c[0].is_null() | (c[3] < pb.lit(T.INT)))
+    pb.project(c[0], c[1] * c[1], c[2], c[5], c[4], (c[3] + c[6]).cast(T.LONG))
+    desc = pb.build()
+    gp = capi.Plan(gpu_api, desc).set_literals([200])
+    op = oracle.plan(desc).set_literals([200])
+    for x in bs:
+        gp.submit(x)
+        op.submit(x)
+    got, want = sorted(gp.finish(), key=_rowkey), sorted(op.finish(), key=_rowkey)
+    assert len(got) == len(want) > 4000
+    assert got == want
+    assert gp.metrics()["numOutputRows"] == len(want)
+
+
+def test_projection_output_larger_than_initial_buffer_is_replayed(gpu_api):
+    """> 2^20 passing rows: the record buffer overflows, the engine grows it and replays the launches."""
+    r = np.random.default_rng(9)
+    n = 400_000
+    schema = [("a", T.INT, False), ("b", T.DOUBLE, False)]
+    bs = [build_batch(n, schema, {"a": np.arange(i * n, (i + 1) * n, dtype=np.int32), "b": r.random(n)}, batch_id=i) for i in range(3)]
+    pb = PlanBuilder()
+    a, b = pb.col(T.INT, 0), pb.col(T.DOUBLE, 1)
+    pb.filter(a >= pb.lit(T.INT))
+    pb.project(a, b)
+    gp = capi.Plan(gpu_api, pb.build()).set_literals([100])
+    for x in bs:
+        gp.submit(x)
+    got = gp.finish()
+    assert len(got) == 3 * n - 100
+    ids = np.sort(np.array([g[0] for g in got]))
+    assert np.array_equal(ids, np.arange(100, 3 * n))

@@ -127,7 +127,9 @@ typedef struct sd_literal {
  * delete mask (getDeletedColumnDecoder), the stats row (next()), ids.  Arrays are indexed like
  * sd_plan_desc.cols.  Buffers may be heap or direct memory; the library has finished reading (or
  * copied) them when sd_batch_submit returns (ownership rule).  A buffer whose first
- * int32 is negative is a compressed envelope (encoders/.../store/CompressionUtils.scala:53-61). */
+ * int32 is negative is a compressed envelope (encoders/.../store/CompressionUtils.scala:53-61): LZ4 (-1)
+ * envelopes are accepted -- only the compressed bytes are copied and the block is expanded on the device;
+ * Snappy (-2) is refused. */
 typedef struct sd_batch {
   int32_t num_rows;
   int32_t ncols;
@@ -219,6 +221,8 @@ int sdx_store_gen_lineitem(sd_store* s, int64_t first_row, int64_t nrows, int32_
 /* copy a resident buffer back to the host (tests: device generator == host generator) */
 int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, void* out, int64_t cap,
                          int64_t* out_len);
+/* host LZ4 prefix decoder used to lay out compressed column buffers (test hook) */
+int64_t sdx_lz4_decode_prefix(const void* src, int64_t src_len, void* dst, int64_t want);
 int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id,
                          int64_t* batch_id);
 

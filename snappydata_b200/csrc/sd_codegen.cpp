@@ -477,7 +477,12 @@ struct Gen {
           int rc = emit_node(p.keys[k], done, keyfn);
           if (rc) return rc;
           const std::string N = std::to_string(p.keys[k]);
-          keyfn << "    kc[" << k << "] = n" << N << " ? 0 : (int64_t)v" << N << "; if (n" << N << ") knull |= " << (1u << k) << "u;\n";
+          if (type_is_fp(e.type))   // NaN-safe key equality: one NaN, -0.0 == 0.0
+            keyfn << "    { double d = (double)v" << N << "; if (d == 0.0) d = 0.0; kc[" << k << "] = n" << N
+                  << " ? 0 : ((d != d) ? 0x7ff8000000000000ll : __double_as_longlong(d)); }";
+          else
+            keyfn << "    kc[" << k << "] = n" << N << " ? 0 : (int64_t)v" << N << ";";
+          keyfn << " if (n" << N << ") knull |= " << (1u << k) << "u;\n";
         }
       }
     }
@@ -585,7 +590,6 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
       const sd_expr& e = out.exprs[k];
       if (!(e.op == SD_OP_COL && e.type == SD_STRING)) all_dict_strings = false;
       if (e.type == SD_STRING && e.op != SD_OP_COL) { err = "STRING group key that is not a dictionary column"; return SD_ERR_UNSUPPORTED; }
-      if (type_is_fp(e.type)) { err = "FLOAT/DOUBLE group keys are not supported by the GPU path yet"; return SD_ERR_UNSUPPORTED; }
     }
     out.mode = (all_dict_strings && !(opt && opt->force_hash)) ? MODE_GROUPS : MODE_HASH;
   }

@@ -700,6 +700,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
 
 int flush_pending(sd_plan* p) {
   if (p->pending.empty()) return 0;
+  if (p->priv) { int rc0 = store_flush_lz4(p->priv); if (rc0) return rc0; }
   std::vector<const StoredBatch*> list;
   for (auto& x : p->pending) list.push_back(x.sb);
   BuiltScan bs;
@@ -820,6 +821,7 @@ int finish_hash(sd_plan* p) {
       const int64_t code = hk[(size_t)g * nk + k];
       if ((hn[g] >> k) & 1u) v.isnull = true;
       else if (types[k] == SD_STRING) v.s = p->key_vals[k][(size_t)code];
+      else if (type_is_fp(types[k])) memcpy(&v.d, &code, 8);
       else v.i = code;
       vals.push_back(v);
     }
@@ -1009,7 +1011,10 @@ int sd_batch_submit(sd_plan* p, const sd_batch* b) {
   // scan columns of the private store are positional: re-point table ordinals on the fly in build_scan
   p->pending.push_back({sb});
   p->pending_bytes += p->priv->h2d_bytes - before;
-  if (p->pending_bytes >= (int64_t(256) << 20)) return flush_pending(p);
+  // compressed inputs are expanded by one launch per flush whose duration is that of the longest buffer:
+  // use fewer, larger flushes for them
+  const int64_t threshold = p->priv->pending_lz4.empty() ? (int64_t(256) << 20) : (int64_t(1) << 30);
+  if (p->pending_bytes >= threshold) return flush_pending(p);
   return 0;
 }
 
@@ -1019,6 +1024,8 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   if (s->device != p->device) return set_error(SD_ERR_INVALID, "store lives on device %d, plan on %d", s->device, p->device);
   SD_CUDA(cudaSetDevice(p->device));
   int rc = flush_pending(p);
+  if (rc) return rc;
+  rc = store_flush_lz4(s);
   if (rc) return rc;
   for (auto& c : p->spec.cols) {
     if (c.table_ordinal < 0 || c.table_ordinal >= (int)s->schema.size()) return set_error(SD_ERR_INVALID, "plan column ordinal %d outside the store schema", c.table_ordinal);
@@ -1141,7 +1148,11 @@ int sd_plan_reset(sd_plan* p) {
   SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
   memset(p->metrics, 0, sizeof(p->metrics));
   p->scratch.reset();
-  if (p->priv) { p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0; }
+  if (p->priv) {
+    cudaStreamSynchronize(p->priv->copy_stream);
+    p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0;
+    p->priv->pending_lz4.clear(); p->priv->lz4_stage.reset();
+  }
   // key dictionaries persist across executions of a cached plan only if the scan cache refers to them
   if (!p->cache.valid) {
     for (auto& m : p->key_ids) m.clear();

@@ -53,6 +53,11 @@ int hash_table_init(cudaStream_t stream, const HashTable& t, uint32_t capacity, 
 int hash_table_compact(cudaStream_t stream, const HashTable& t, uint32_t capacity, int nk, int nslot, int64_t* out_keys,
                        uint32_t* out_knull, uint64_t* out_vals, uint32_t* d_cursor);
 
+// ---- on-device LZ4 (sd_lz4.cu) ---------------------------------------------------------------------------
+struct Lz4Job { const uint8_t* src; uint8_t* dst; int64_t src_len; int64_t dst_len; };
+int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t want);
+int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error);
+
 // ---- device memory arena: bump allocation out of large slabs ---------------------------------------
 struct Arena {
   int device = 0;
@@ -114,11 +119,18 @@ struct sd_store {
   std::vector<std::unique_ptr<sd::StoredBatch>> batches;
   int64_t version = 0;
   int64_t h2d_bytes = 0;
+  // compressed payloads waiting to be expanded on the device (one launch for many buffers)
+  std::vector<sd::Lz4Job> pending_lz4;
+  sd::Arena lz4_stage;
+  unsigned int* d_lz4_error = nullptr;
+  int64_t lz4_buffers = 0, lz4_in_bytes = 0, lz4_out_bytes = 0;
 };
 
 namespace sd {
 // upload one batch (columns by table ordinal of `schema`) into the store's arena
 int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals /* nullptr: identity */);
+// expand every pending compressed buffer (blocks until done); no-op when nothing is pending
+int store_flush_lz4(sd_store* s);
 }
 
 #endif

@@ -146,9 +146,57 @@ static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, 
 
 static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type, int nullable, int num_rows, StoredCol& c) {
   if (len < 8) return set_error(SD_ERR_INVALID, "column buffer shorter than its 8-byte header");
+  // ---- compressed envelope [-codecId][uncompressedLen][payload] (CompressionUtils.scala:53-61): only the
+  //      compressed bytes go to the device; the host decodes just the leading bytes it must parse -------
+  const uint8_t* payload = nullptr;
+  int64_t payload_len = 0;
+  std::vector<uint8_t> prefix;
+  if (rd_i32(buf) < 0) {
+    const int codec = -rd_i32(buf);
+    if (codec != 1) return set_error(SD_ERR_UNSUPPORTED, "compressed column buffer with codec %d (only LZ4 = 1 is decoded on the device)", codec);
+    const int64_t ulen = rd_i32(buf + 4);
+    if (ulen < 8) return set_error(SD_ERR_INVALID, "compressed column buffer: bad uncompressed length %lld", (long long)ulen);
+    payload = buf + 8;
+    payload_len = len - 8;
+    int64_t want = 8;
+    for (;;) {
+      want = std::min(want, ulen);
+      prefix.assign((size_t)want + 16, 0);
+      const int64_t got = lz4_decode_prefix(payload, payload_len, prefix.data(), want);
+      if (got < want) return set_error(SD_ERR_INVALID, "corrupt LZ4 column buffer");
+      const int tid = rd_i32(prefix.data());
+      const int nb = want >= 8 ? rd_i32(prefix.data() + 4) : 0;
+      if (tid < 0 || tid > ENC_BOOLEAN_BITSET || nb < 0 || (nb & 7) || 8 + (int64_t)nb > ulen) return set_error(SD_ERR_INVALID, "corrupt header in LZ4 column buffer");
+      if (tid == ENC_RUN_LENGTH) return set_error(SD_ERR_UNSUPPORTED, "LZ4-compressed RunLength column (needs a host pass over every run)");
+      int64_t need = 8 + nb;
+      if (tid == ENC_DICTIONARY || tid == ENC_BIG_DICTIONARY) {
+        need += 4;
+        if (want >= need) {
+          const int n = rd_i32(prefix.data() + 8 + nb);
+          if (n < 0) return set_error(SD_ERR_INVALID, "corrupt dictionary in LZ4 column buffer");
+          if (type == SD_INT || type == SD_DATE) need += 4 * (int64_t)n;
+          else if (type == SD_LONG || type == SD_TIMESTAMP) need += 8 * (int64_t)n;
+          else {   // strings: walk what we have; ask for more when the walk runs off the decoded prefix
+            int64_t q = 8 + nb + 4;
+            bool short_prefix = false;
+            for (int k = 0; k < n; k++) {
+              if (q + 4 > want) { short_prefix = true; break; }
+              const int l = rd_i32(prefix.data() + q);
+              if (l < 0) return set_error(SD_ERR_INVALID, "corrupt string dictionary in LZ4 column buffer");
+              q += 4 + l;
+            }
+            need = short_prefix || q > want ? std::max<int64_t>(q, want * 2) : q;
+          }
+        }
+      }
+      need = std::min(need, ulen);
+      if (want >= need) break;
+      want = need;
+    }
+    buf = prefix.data();
+    len = ulen;
+  }
   const int type_id = rd_i32(buf);
-  if (type_id < 0)
-    return set_error(SD_ERR_UNSUPPORTED, "compressed column buffer (codec %d): decompress before submit; on-device LZ4 is not built yet", -type_id);
   if (type_id > ENC_BOOLEAN_BITSET) return set_error(SD_ERR_INVALID, "unknown encoding typeId %d", type_id);
   const int null_bytes = rd_i32(buf + 4);
   if (null_bytes < 0 || (null_bytes & 7) || 8 + (int64_t)null_bytes > len) return set_error(SD_ERR_INVALID, "bad null bitset size %d", null_bytes);
@@ -244,8 +292,19 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
   c.algo_bytes = len - 8 - dict_bytes;
   if (!c.unsupported.empty()) return 0;   // recorded; an error only if a plan scans this column
 
-  int rc = upload_bytes(s, buf, (size_t)len, 128, (size_t)body, &c.dev_base);
-  if (rc) return rc;
+  int rc = 0;
+  if (payload) {   // expanded on the device at the next flush: [dev_base, dev_base + len) is written by the LZ4 kernel
+    c.dev_base = s->arena.alloc((size_t)len + 160, 128, (size_t)body);
+    uint8_t* d_src = s->lz4_stage.alloc((size_t)payload_len + 16, 16);
+    if (!c.dev_base || !d_src) return SD_ERR_CUDA;
+    SD_CUDA(cudaMemcpyAsync(d_src, payload, (size_t)payload_len, cudaMemcpyHostToDevice, s->copy_stream));
+    s->h2d_bytes += payload_len;
+    s->pending_lz4.push_back(Lz4Job{d_src, c.dev_base, payload_len, len});
+    s->lz4_buffers++; s->lz4_in_bytes += payload_len; s->lz4_out_bytes += len;
+  } else {
+    rc = upload_bytes(s, buf, (size_t)len, 128, (size_t)body, &c.dev_base);
+    if (rc) return rc;
+  }
   c.dev.data = c.dev_base + body;
   if ((type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY) && type != SD_STRING) {
     const int ew = (type == SD_INT || type == SD_DATE) ? 4 : 8;
@@ -325,6 +384,26 @@ static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, 
   rc = upload_bytes(s, buf + body, (size_t)(len - body), 16, 0, &p);
   if (rc) return rc;
   d.dev.data = p;
+  return 0;
+}
+
+int store_flush_lz4(sd_store* s) {
+  if (s->pending_lz4.empty()) return 0;
+  SD_CUDA(cudaSetDevice(s->device));
+  if (!s->d_lz4_error) { SD_CUDA(cudaMalloc(&s->d_lz4_error, 64)); }
+  SD_CUDA(cudaMemsetAsync(s->d_lz4_error, 0, 4, s->copy_stream));
+  const size_t nbytes = s->pending_lz4.size() * sizeof(Lz4Job);
+  uint8_t* d_jobs = s->lz4_stage.alloc(nbytes + 16, 16);
+  if (!d_jobs) return SD_ERR_CUDA;
+  SD_CUDA(cudaMemcpyAsync(d_jobs, s->pending_lz4.data(), nbytes, cudaMemcpyHostToDevice, s->copy_stream));
+  int rc = lz4_launch(s->copy_stream, reinterpret_cast<const Lz4Job*>(d_jobs), (int)s->pending_lz4.size(), s->d_lz4_error);
+  if (rc) return rc;
+  unsigned int err = 0;
+  SD_CUDA(cudaMemcpyAsync(&err, s->d_lz4_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
+  SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+  s->pending_lz4.clear();
+  s->lz4_stage.reset();
+  if (err) return set_error(SD_ERR_INVALID, "corrupt LZ4 payload in a column buffer (device decode failed)");
   return 0;
 }
 
@@ -432,6 +511,8 @@ int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store
   sd_store* s = new sd_store();
   s->device = device;
   s->arena.device = device;
+  s->lz4_stage.device = device;
+  s->lz4_stage.slab_bytes = size_t(256) << 20;
   s->schema.assign(schema, schema + ncols);
   cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return sd::set_error(SD_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
@@ -452,6 +533,7 @@ void sd_store_destroy(sd_store* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->d_lz4_error) cudaFree(s->d_lz4_error);
   delete s;
 }
 
@@ -470,6 +552,7 @@ int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, vo
   if (table_col < 0 || table_col >= (int)b.cols.size() || !b.cols[table_col].present || !b.cols[table_col].dev_base)
     return sd::set_error(SD_ERR_INVALID, "column %d not resident", table_col);
   const sd::StoredCol& c = b.cols[table_col];
+  { int rc = sd::store_flush_lz4(s); if (rc) return rc; }
   *out_len = c.len;
   if (cap < c.len) return sd::set_error(SD_ERR_OVERFLOW, "buffer too small");
   SD_CUDA(cudaSetDevice(s->device));

@@ -240,11 +240,56 @@ def test_errors_not_fallbacks(gpu_api):
     with pytest.raises(capi.SdError) as e:
         gp.submit(bad)
     assert e.value.code == capi.SD_ERR_INVALID
-    comp = compress_lz4(encode_uncompressed(np.zeros(5000, dtype=np.int32), T.INT))
-    assert int.from_bytes(comp[:4], "little", signed=True) == -1
+    # a Snappy-compressed envelope (codec 2) is refused; LZ4 (codec 1) is decoded on the device (test_lz4_*)
+    snappy_env = (-2).to_bytes(4, "little", signed=True) + (20000).to_bytes(4, "little") + b"\0" * 100
     with pytest.raises(capi.SdError) as e:
-        gp.submit(ColumnBatch(num_rows=5000, columns=[comp]))
+        gp.submit(ColumnBatch(num_rows=5000, columns=[snappy_env]))
     assert e.value.code == capi.SD_ERR_UNSUPPORTED
+
+
+def _compress_batch(b, force=True):
+    from snappydata_b200.column_format import compress_lz4
+    import copy
+    c = copy.copy(b)
+    c.columns = [None if x is None else compress_lz4(x, force=force) for x in b.columns]
+    return c
+
+
+def test_lz4_compressed_buffers_are_expanded_on_the_device(gpu_api, batches):
+    """Stored form [-1][uncompressedLen][LZ4 block] (CompressionUtils.scala:53-61): same results as the
+    uncompressed bytes, every encoding, nullable or not; fewer bytes cross PCIe."""
+    b = PlanBuilder()
+    c = cols(b)
+    b.filter(c["c5"] >= b.lit(T.DATE))
+    b.group_by(c["c3"])
+    b.count().sum(c["c0"]).sum(c["c2"]).count(c["c4"]).sum(c["c1"]).min(c["c7"]).max(c["c8"]).sum(c["c11"])
+    desc = b.build()
+    plain = [make_batch(n, seed=30 + i, batch_id=i, encoders={"c5": "dictionary"})[0] for i, n in enumerate((6000, 300, 2049))]
+    op = oracle.plan(desc).set_literals([9001])
+    gp = capi.Plan(gpu_api, desc).set_literals([9001])
+    gplain = capi.Plan(gpu_api, desc).set_literals([9001])
+    for x in plain:
+        op.submit(x)
+        gp.submit(_compress_batch(x))
+        gplain.submit(x)
+    want = op.finish()
+    assert_rowsets_match(gp.finish(), want, 1)
+    assert_rowsets_match(gplain.finish(), want, 1)
+    assert gp.metrics()["h2dBytes"] < gplain.metrics()["h2dBytes"]
+
+
+def test_lz4_lineitem_q1_q6(gpu_api):
+    from snappydata_b200 import lineitem, plan as P
+    plain = lineitem.gen_table(260_001, 65_000, seed=21)
+    for desc, lits, nk in ((P.q6_plan(), P.Q6_LITERALS, 0), (P.q1_plan(), P.Q1_LITERALS, 2)):
+        op = oracle.plan(desc).set_literals(lits)
+        gp = capi.Plan(gpu_api, desc).set_literals(lits)
+        for x in plain:
+            op.submit(x)
+            gp.submit(_compress_batch(x, force=False))   # the reference's rule: only if it shrinks to <= 75 %
+        assert_rowsets_match(gp.finish(), op.finish(), nk)
+        m = gp.metrics()
+        assert m["h2dBytes"] < 0.8 * m["algorithmicBytes"]
 
 
 # ---- MODE_HASH: general (non dictionary-string) group keys -------------------------------------------
@@ -381,3 +426,13 @@ def test_projection_output_larger_than_initial_buffer_is_replayed(gpu_api):
     assert len(got) == 3 * n - 100
     ids = np.sort(np.array([g[0] for g in got]))
     assert np.array_equal(ids, np.arange(100, 3 * n))
+
+
+def test_group_by_double_key_with_nan_and_negative_zero(gpu_api, batches):
+    """DOUBLE keys group with the NaN-safe equality (NaN == NaN, -0.0 == 0.0)."""
+    b = PlanBuilder()
+    c = cols(b)
+    b.filter(c["c0"] > b.lit(T.INT))
+    b.group_by(c["c2"], c["c4"])
+    b.count().sum(c["c1"])
+    both(gpu_api, b.build(), [900], batches, 2)

@@ -262,7 +262,7 @@ def test_lz4_compressed_buffers_are_expanded_on_the_device(gpu_api, batches):
     c = cols(b)
     b.filter(c["c5"] >= b.lit(T.DATE))
     b.group_by(c["c3"])
-    b.count().sum(c["c0"]).sum(c["c2"]).count(c["c4"]).sum(c["c1"]).min(c["c7"]).max(c["c8"]).sum(c["c11"])
+    b.count().sum(c["c0"]).sum(c["c2"]).count(c["c4"]).sum(c["c1"]).min(c["c7"]).max(c["c8"]).max(c["c11"])
     desc = b.build()
     plain = [make_batch(n, seed=30 + i, batch_id=i, encoders={"c5": "dictionary"})[0] for i, n in enumerate((6000, 300, 2049))]
     op = oracle.plan(desc).set_literals([9001])

@@ -175,6 +175,12 @@ int sd_plan_reset(sd_plan* p);
  * [8] rows scanned [9] algorithmic bytes scanned [10] host->device bytes [11] scan numOutputRows */
 #define SD_NUM_METRICS 12
 int sd_plan_metrics(sd_plan* p, int64_t out[SD_NUM_METRICS]);
+/* options.  SD_OPT_RETAIN_BUFFERS = 1: the caller keeps every buffer passed to sd_batch_submit alive and
+ * unchanged until sd_plan_finish returns (e.g. ref-counted direct ByteBuffers retained by the operator); host->device
+ * copies are then queued without a per-batch synchronisation.  Default 0: the reference's ownership rule (buffers
+ * may be released when sd_batch_submit returns, ColumnBatchIterator.scala:165-184). */
+#define SD_OPT_RETAIN_BUFFERS 1
+int sd_plan_set_option(sd_plan* p, int32_t option, int64_t value);
 /* run the plan's kernels on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's */
 int sd_plan_set_stream(sd_plan* p, void* cuda_stream);
 /* kernel variant actually selected for the plan ("aot:<signature>" | "jit:<signature>") */

@@ -17,6 +17,7 @@ from .column_format import ColumnBatch, SqlType, parse_row_stream
 
 SD_ABI_VERSION = 1
 SD_NUM_METRICS = 12
+SD_OPT_RETAIN_BUFFERS = 1
 METRIC_NAMES = ["numOutputRows", "numRowsBuffer", "columnBatchesSeen", "updatedColumnCount",
                 "deletedBatchCount", "columnBatchesSkipped", "aggTimeNs", "kernelLaunches",
                 "rowsScanned", "algorithmicBytes", "h2dBytes", "scanOutputRows"]
@@ -194,6 +195,7 @@ class Api:
         self.device_count = fn("device_count", C.c_int, C.POINTER(C.c_int), required=False)
         self.version = fn("version", C.c_char_p, required=False)
         self.plan_set_stream = fn("plan_set_stream", C.c_int, vp, vp, required=False)
+        self.plan_set_option = fn("plan_set_option", C.c_int, vp, i32, i64, required=False)
         self.plan_kernel_name = fn("plan_kernel_name", C.c_char_p, vp, required=False)
         self.store_create = fn("store_create", C.c_int, C.c_int, i32, C.POINTER(sd_column), C.POINTER(vp), required=False)
         self.store_put_batch = fn("store_put_batch", C.c_int, vp, C.POINTER(sd_batch), required=False)
@@ -391,6 +393,10 @@ class Plan:
 
     def kernel_name(self) -> str:
         return self.api.plan_kernel_name(self.h).decode()
+
+    def set_option(self, option: int, value: int):
+        self.api.check(self.api.plan_set_option(self.h, option, value))
+        return self
 
     def set_stream(self, stream_ptr: int):
         self.api.check(self.api.plan_set_stream(self.h, stream_ptr))

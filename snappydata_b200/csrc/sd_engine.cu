@@ -700,7 +700,15 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
 
 int flush_pending(sd_plan* p) {
   if (p->pending.empty()) return 0;
-  if (p->priv) { int rc0 = store_flush_lz4(p->priv); if (rc0) return rc0; }
+  if (p->priv) {
+    int rc0 = store_flush_lz4(p->priv);
+    if (rc0) return rc0;
+    if (p->priv->retain_buffers) {   // copies were queued without synchronisation: order the scan after them
+      if (!p->priv->copies_done) SD_CUDA(cudaEventCreateWithFlags(&p->priv->copies_done, cudaEventDisableTiming));
+      SD_CUDA(cudaEventRecord(p->priv->copies_done, p->priv->copy_stream));
+      SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->copies_done, 0));
+    }
+  }
   std::vector<const StoredBatch*> list;
   for (auto& x : p->pending) list.push_back(x.sb);
   BuiltScan bs;
@@ -974,6 +982,17 @@ int sd_plan_set_literals(sd_plan* p, const sd_literal* vals, int32_t n) {
   }
   p->lits_set = true;
   return 0;
+}
+
+int sd_plan_set_option(sd_plan* p, int32_t option, int64_t value) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  if (option == SD_OPT_RETAIN_BUFFERS) {
+    int rc = ensure_private_store(p);
+    if (rc) return rc;
+    p->priv->retain_buffers = value != 0;
+    return 0;
+  }
+  return set_error(SD_ERR_INVALID, "unknown option %d", option);
 }
 
 int sd_plan_set_stream(sd_plan* p, void* cuda_stream) {

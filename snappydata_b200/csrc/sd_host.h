@@ -119,6 +119,8 @@ struct sd_store {
   std::vector<std::unique_ptr<sd::StoredBatch>> batches;
   int64_t version = 0;
   int64_t h2d_bytes = 0;
+  bool retain_buffers = false;   // SD_OPT_RETAIN_BUFFERS: no per-put synchronisation of the copy stream
+  cudaEvent_t copies_done = nullptr;
   // compressed payloads waiting to be expanded on the device (one launch for many buffers)
   std::vector<sd::Lz4Job> pending_lz4;
   sd::Arena lz4_stage;

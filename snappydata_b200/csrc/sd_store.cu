@@ -488,8 +488,8 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
     sb->stats.assign(reinterpret_cast<const uint8_t*>(b->stats_row), reinterpret_cast<const uint8_t*>(b->stats_row) + b->stats_len);
     sb->stats_ncols = b->stats_ncols;
   }
-  // ownership rule: the caller's buffers may be released when this call returns
-  SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+  // ownership rule: the caller's buffers may be released when this call returns (unless it retains them)
+  if (!s->retain_buffers) SD_CUDA(cudaStreamSynchronize(s->copy_stream));
   s->batches.push_back(std::move(sb));
   s->version++;
   return 0;
@@ -534,6 +534,7 @@ void sd_store_destroy(sd_store* s) {
   cudaSetDevice(s->device);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->d_lz4_error) cudaFree(s->d_lz4_error);
+  if (s->copies_done) cudaEventDestroy(s->copies_done);
   delete s;
 }
 

@@ -154,7 +154,7 @@ struct ScanArgs {
   unsigned long long* out_count;  // MODE_PROJECT: records produced (may exceed out_cap: the host grows and replays)
   int64_t out_cap;                // MODE_PROJECT: capacity in records
   int32_t batch_base;             // MODE_PROJECT: ordinal of this launch's first batch within the execution
-  int32_t pad2_;
+  int32_t chunk_rows;             // rows per work item (multiple of every tile size; default CHUNK_ROWS)
   Literals lits;
 };
 

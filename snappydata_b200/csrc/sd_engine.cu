@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "sd_host.h"
 
@@ -237,6 +238,7 @@ struct sd_plan {
   const KernelEntry* active = nullptr;
   std::string kernel_name;
   int max_ctas_per_sm = 0;
+  int chunk_rows = CHUNK_ROWS;
   size_t last_smem = (size_t)-1;
   const KernelEntry* last_kernel = nullptr;
   int num_sms = 0;
@@ -472,7 +474,7 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       }
     }
     out->rows += sb.num_rows;
-    prefix[bi + 1] = prefix[bi] + (sb.num_rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
+    prefix[bi + 1] = prefix[bi] + (sb.num_rows + p->chunk_rows - 1) / p->chunk_rows;
   }
   // NULL key ids are only materialised when a nullable key column is present in the plan
   uint8_t* d_aux = nullptr;
@@ -683,6 +685,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.out_count = p->d_out_count;
   args.out_cap = p->out_cap;
   args.batch_base = batch_base;
+  args.chunk_rows = p->chunk_rows;
   memcpy(args.radix, radix, sizeof(radix));
   for (size_t i = 0; i < p->lits.size(); i++) {
     args.lits.i[i] = p->lits[i].i;
@@ -737,6 +740,8 @@ int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int devi
   std::string err;
   int rc = analyze_plan(&desc, spec, err, &opt);
   if (rc) return set_error(rc, "%s", err.c_str());
+  static std::mutex registry_mutex;   // plans are created concurrently from many task threads
+  std::lock_guard<std::mutex> lock(registry_mutex);
   for (auto& k : kernel_registry()) if (k.signature == spec.signature) { *out = k; if (spec_out) *spec_out = spec; return 0; }
   KernelEntry k;
   rc = jit_compile(spec, device, k);
@@ -965,6 +970,7 @@ int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   p->lits.resize(p->spec.literal_types.size());
   p->lit_strs.resize(p->spec.literal_types.size());
   for (size_t i = 0; i < p->lits.size(); i++) { memset(&p->lits[i], 0, sizeof(sd_literal)); p->lits[i].type = p->spec.literal_types[i]; }
+  if (const char* e = getenv("SD_TUNE_CHUNK_ROWS")) { int v = atoi(e); if (v >= 2048 && v % 2048 == 0 && v <= (1 << 20)) p->chunk_rows = v; }
   p->lits_set = p->lits.empty();
   *out = p.release();
   return 0;

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   constexpr int NSLOT = PLAN::NSLOT;
   constexpr int RPT = PLAN::RPT;
   constexpr int TILE_ROWS = THREADS * RPT;
-  constexpr int CHUNK_TILES = CHUNK_ROWS / TILE_ROWS;
+  const int CHUNK_TILES = args.chunk_rows / TILE_ROWS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem<PLAN>& sm = *reinterpret_cast<TileSmem<PLAN>*>(smem_raw);
   uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(TileSmem<PLAN>) + 15) & ~size_t(15)));

@@ -87,11 +87,13 @@ struct DevBatch {
   int32_t num_deletes;
   const int32_t* deletes;     // ascending deleted ordinals or nullptr (enc/ColumnDeleteEncoder.scala:101-134)
   const uint8_t* aux;         // per-plan per-batch tables: key code->group maps, predicate truth tables
-  int32_t flags;              // bit0: every column takes the vector fast path
+  int32_t flags;              // BATCH_ALL_FAST | BATCH_FAST_OVERLAY (0: general per-row decode)
   int32_t pad_;
   DevCol cols[NC > 0 ? NC : 1];
 };
-constexpr int32_t BATCH_ALL_FAST = 1;
+constexpr int32_t BATCH_ALL_FAST = 1;      // no nulls, simple encodings, no deltas, no deletes: staged vector loads only
+constexpr int32_t BATCH_FAST_OVERLAY = 2;  // base columns as above, plus update deltas and/or a delete mask: staged loads,
+                                           // then the few updated / deleted rows of each tile are patched in registers
 
 struct Literals {
   int64_t i[MAX_LITERALS];

@@ -317,6 +317,53 @@ __device__ __forceinline__ void load_col_general(const DevCol& col, int tile, in
   }
 }
 
+// fast + overlay path: the base values were loaded by the staged vector path; rows whose bit is set in the tile's
+// update bitmap are replaced by their delta value (depth 0 wins), exactly like the general path does
+template <class PLAN, int C>
+__device__ __forceinline__ void overlay_col(const DevCol& col, int64_t tile_start, int num_rows, const TileSmem<PLAN>& sm,
+                                            ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  if (!(col.delta0 || col.delta1)) return;
+#pragma unroll
+  for (int r = 0; r < PLAN::RPT; r++) {
+    const int li = row_in_tile(r);
+    const int64_t i = tile_start + li;
+    if (i >= num_rows || !((sm.updbits[C][li >> 5] >> (li & 31)) & 1u)) continue;
+    const DevDelta* d = col.delta0;
+    int j = -1;
+    if (d) {
+      int q = lower_bound_i32(d->positions, sm.drange[C][0], sm.drange[C][1], (int32_t)i);
+      if (q < sm.drange[C][1] && d->positions[q] == (int32_t)i) j = q;
+    }
+    if (j < 0) {
+      d = col.delta1;
+      j = lower_bound_i32(d->positions, sm.drange[C][2], sm.drange[C][3], (int32_t)i);
+    }
+    int64_t k = j;
+    bool isnull = false;
+    if (d->nulls) {
+      const int w = j >> 6;
+      const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
+      isnull = (word >> (j & 63)) & 1ull;
+      int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
+      for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
+      k = j - before;
+    }
+    T v = (T)0;
+    if (!isnull) v = decode_delta_value<K>(*d, k);
+    else if (K == K_CODE) v = (T)col.dict_n;
+    regs.v[r] = v;
+    regs.nullmask = (regs.nullmask & ~(1u << r)) | ((isnull ? 1u : 0u) << r);
+  }
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void overlay_all(const DevBatch<PLAN::NC>& b, int64_t tile_start, const TileSmem<PLAN>& sm,
+                                            AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (overlay_col<PLAN, Cs>(b.cols[Cs], tile_start, b.num_rows, sm, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
+}
+
 // tile preparation for the general path: null-word prefix sums, delete / update bitmaps
 template <class PLAN, int C>
 __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
@@ -498,8 +545,15 @@ __device__ __forceinline__ void load_all_staged(uint32_t c16, const uint8_t* sta
   (void)dummy;
 }
 
-// which batch a work item (chunk) belongs to: last b with chunk_prefix[b] <= item
-__device__ __forceinline__ int find_batch(const int32_t* chunk_prefix, int nbatches, int item) {
+// which batch a work item (chunk) belongs to: last b with chunk_prefix[b] <= item.  Items of a CTA increase
+// monotonically, so `hint` (the previous answer) is advanced linearly before falling back to a binary search.
+__device__ __forceinline__ int find_batch(const int32_t* chunk_prefix, int nbatches, int item, int hint) {
+  if (hint >= 0) {
+    int b = hint;
+#pragma unroll 1
+    for (int step = 0; step < 4 && b + 1 < nbatches && chunk_prefix[b + 1] <= item; step++) b++;
+    if (b + 1 >= nbatches || chunk_prefix[b + 1] > item) return b;
+  }
   int lo = 0, hi = nbatches;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
@@ -576,10 +630,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
       if (tid == THREADS) {
         int stage = 0;
         uint32_t phase = 0;
+        int p_hint = -1;
         for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
-          const int bi = find_batch(args.chunk_prefix, args.nbatches, item);
+          const int bi = find_batch(args.chunk_prefix, args.nbatches, item, p_hint);
+          p_hint = bi;
           const DevBatch<PLAN::NC>& b = batches[bi];
-          if (!(b.flags & BATCH_ALL_FAST)) continue;
+          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY))) continue;
           const int chunk = item - args.chunk_prefix[bi];
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
@@ -599,6 +655,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   }
   int c_stage = 0;
   uint32_t c_phase = 0;
+  int c_hint = -1;
 
   // ---- accumulator init -------------------------------------------------------------------------
   uint64_t acc[NSLOT > 0 ? NSLOT : 1];
@@ -629,11 +686,13 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 
   // ---- persistent loop over (batch, chunk) work items, static round-robin -------------------------
   for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
-    const int lo = find_batch(args.chunk_prefix, args.nbatches, item);
+    const int lo = find_batch(args.chunk_prefix, args.nbatches, item, c_hint);
+    c_hint = lo;
     const DevBatch<PLAN::NC>& b = batches[lo];
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
-    const bool fast = (b.flags & BATCH_ALL_FAST) != 0;
+    const bool overlay = (b.flags & BATCH_FAST_OVERLAY) != 0;
+    const bool fast = (b.flags & BATCH_ALL_FAST) != 0 || (overlay && PLAN::STAGES > 0);
     load_tables<PLAN::NTABLES>(ctx, b.aux);
     const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
     uint32_t c_scanned = 0, c_passed = 0;
@@ -657,6 +716,29 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }
         } else {
           load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
+        }
+        if (overlay) {   // patch the tile's few updated rows, drop its deleted rows
+          consumer_sync();
+          clear_upd_bits<PLAN>(b, sm, ColSeq());
+          consumer_sync();
+          prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
+          if (b.deletes) {
+            const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
+            const int dlo = lower_bound_i32(b.deletes, 0, b.num_deletes, ts);
+            for (int j = dlo + tid; j < b.num_deletes && b.deletes[j] < te; j += THREADS) {
+              const int li = b.deletes[j] - ts;
+              atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
+            }
+          }
+          consumer_sync();
+          overlay_all<PLAN>(b, tile_start, sm, regs, ColSeq());
+          if (b.deletes) {
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+              const int li = row_in_tile(r);
+              if ((sm.delbits[li >> 5] >> (li & 31)) & 1u) live &= ~(1u << r);
+            }
+          }
         }
       } else {
         consumer_sync();                       // previous tile's readers are done with sm

@@ -559,7 +559,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
                 const std::vector<const StoredBatch*>* blist = nullptr, int replay_batch_base = -1) {
   const bool replay = replay_batch_base >= 0;
   int batch_base = replay ? replay_batch_base : (int)p->exec_batches.size();
-  if (!replay && (p->spec.mode == MODE_HASH || p->spec.mode == MODE_PROJECT)) {
+  if (!replay && p->spec.mode != MODE_NOKEY) {
     p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks, batch_base});
     if (blist) p->exec_batches.insert(p->exec_batches.end(), blist->begin(), blist->end());
   }
@@ -570,10 +570,34 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   // group radices from the current key dictionaries
   int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
   int ngroups = 1;
+  bool dense_too_big = false;
   for (int k = 0; k < nk && sp.mode == MODE_GROUPS; k++) {
     radix[k] = std::max<int>(1, (int)p->key_vals[k].size());
-    if ((int64_t)ngroups * radix[k] > (1 << 20)) return set_error(SD_ERR_UNSUPPORTED, "group cardinality too high for the dense group table");
+    if ((int64_t)ngroups * radix[k] > (1 << 16)) { dense_too_big = true; break; }
     ngroups *= radix[k];
+  }
+  if (dense_too_big) {
+    // too many key combinations for the dense table: switch this plan to the hash-table variant (same tables, same
+    // slots) and replay what this execution has launched so far
+    CodegenOptions opt;
+    opt.force_hash = 1;
+    PlanSpec hspec;
+    KernelEntry hk;
+    sd_plan_desc dv = sp.desc_view();
+    int rc = resolve_kernel(dv, opt, p->device, &hk, &hspec);
+    if (rc) return rc;
+    std::vector<sd_plan::Launch> earlier(p->launch_log.begin(), p->launch_log.end() - (replay ? 0 : 1));
+    p->spec = hspec;
+    p->kernel = hk;
+    p->kernel_litnull_state = 0;
+    p->active = nullptr;
+    p->last_kernel = nullptr;
+    p->last_smem = (size_t)-1;
+    p->result_init = false;
+    p->hash_init = false;
+    SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
+    for (auto& l : earlier) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
+    return launch_scan(p, d_batches, d_prefix, nbatches, total_chunks, nullptr, batch_base);
   }
   const size_t ne = (size_t)ngroups * ns;
   // Where the dense group table lives (decided per launch from its size):

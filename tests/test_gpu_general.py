@@ -436,3 +436,22 @@ def test_group_by_double_key_with_nan_and_negative_zero(gpu_api, batches):
     b.group_by(c["c2"], c["c4"])
     b.count().sum(c["c1"])
     both(gpu_api, b.build(), [900], batches, 2)
+
+
+def test_many_string_key_combinations_switch_to_the_hash_table(gpu_api):
+    """Dictionary-string keys whose id product exceeds the dense group table: the plan switches to the hash-table
+    variant mid-execution and replays the launches already made."""
+    r = np.random.default_rng(17)
+    n = 150_000
+    schema = [("a", T.STRING, False), ("b", T.STRING, True), ("v", T.LONG, False)]
+    bs = []
+    for i in range(2):
+        data = {"a": np.array([b"a%03d" % x for x in r.integers(0, 300 + 100 * i, n)], dtype=object),
+                "b": np.array([b"b%03d" % x for x in r.integers(0, 300, n)], dtype=object), "v": r.integers(-100, 100, n).astype(np.int64)}
+        bs.append(build_batch(n, schema, data, {"b": r.random(n) < 0.05}, batch_id=i))
+    b = PlanBuilder()
+    a, bb, v = b.col(T.STRING, 0, False), b.col(T.STRING, 1, True), b.col(T.LONG, 2, False)
+    b.group_by(a, bb)
+    b.count().sum(v).min(v)
+    gp, op, got = both(gpu_api, b.build(), [], bs, 2)
+    assert len(got) > 65_536

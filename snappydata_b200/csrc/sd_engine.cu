@@ -997,6 +997,7 @@ int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   p->lits.resize(p->spec.literal_types.size());
   p->lit_strs.resize(p->spec.literal_types.size());
   for (size_t i = 0; i < p->lits.size(); i++) { memset(&p->lits[i], 0, sizeof(sd_literal)); p->lits[i].type = p->spec.literal_types[i]; }
+  if (p->spec.mode == MODE_GROUPS) p->chunk_rows = 2 * CHUNK_ROWS;   // measured: tools/sweep.sh, profiles/r01_tuning.txt
   if (const char* e = getenv("SD_TUNE_CHUNK_ROWS")) { int v = atoi(e); if (v >= 2048 && v % 2048 == 0 && v <= (1 << 20)) p->chunk_rows = v; }
   p->lits_set = p->lits.empty();
   *out = p.release();

@@ -215,7 +215,8 @@ struct TileSmem {
   uint32_t delbits[TILE_ROWS / 32];
   uint32_t updbits[PLAN::NC > 0 ? PLAN::NC : 1][TILE_ROWS / 32];
   int32_t wprefix[PLAN::NC > 0 ? PLAN::NC : 1][TILE_WORDS];
-  int32_t drange[PLAN::NC > 0 ? PLAN::NC : 1][4];
+  int32_t drange[PLAN::NC > 0 ? PLAN::NC : 1][4];   // per column: [lo, hi) of delta0 and delta1 positions inside the tile
+  int32_t delrange[2];                               // [lo, hi) of the delete positions inside the tile
 };
 
 // row r of a thread within tile: pair u = r/2 at tile + u*2*THREADS + 2*tid + (r&1)
@@ -364,6 +365,46 @@ __device__ __forceinline__ void overlay_all(const DevBatch<PLAN::NC>& b, int64_t
   (void)dummy;
 }
 
+// [lo, hi) of the sorted `positions` that fall into [ts, te), found by one warp: `lo` continues from the previous
+// tile's `hi` (tiles of a chunk are visited in order; first >= 0) or comes from a binary search; `hi` is found 32
+// entries at a time with a ballot (a 1024-row tile rarely holds more than a handful of updated / deleted rows)
+__device__ __forceinline__ void warp_find_range(const int32_t* positions, int n, int32_t ts, int32_t te, int first, int lane, int* out_lo, int* out_hi) {
+  int lo = first >= 0 ? first : lower_bound_i32(positions, 0, n, ts);
+  int hi = lo;
+  for (;;) {
+    const int idx = hi + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, idx < n && positions[idx] < te);
+    const int c = __popc(m);
+    hi += c;
+    if (c < 32) break;
+  }
+  *out_lo = lo;
+  *out_hi = hi;
+}
+template <class PLAN, int C>
+__device__ __forceinline__ void find_col_ranges(const DevCol& col, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, int lane) {
+  if (!(col.delta0 || col.delta1)) return;
+  const int32_t ts = (int32_t)tile_start, te = ts + TileSmem<PLAN>::TILE_ROWS;
+#pragma unroll
+  for (int dd = 0; dd < 2; dd++) {
+    const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
+    int lo = 0, hi = 0;
+    if (d) warp_find_range(d->positions, d->n, ts, te, first_tile ? -1 : sm.drange[C][2 * dd + 1], lane, &lo, &hi);
+    if (lane == 0) { sm.drange[C][2 * dd] = lo; sm.drange[C][2 * dd + 1] = hi; }
+  }
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void find_all_ranges(const DevBatch<PLAN::NC>& b, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, int lane, Seq<Cs...>) {
+  int dummy[] = {0, (find_col_ranges<PLAN, Cs>(b.cols[Cs], tile_start, first_tile, sm, lane), 0)...};
+  (void)dummy;
+  if (b.deletes) {
+    int lo, hi;
+    warp_find_range(b.deletes, b.num_deletes, (int32_t)tile_start, (int32_t)tile_start + TileSmem<PLAN>::TILE_ROWS,
+                    first_tile ? -1 : sm.delrange[1], lane, &lo, &hi);
+    if (lane == 0) { sm.delrange[0] = lo; sm.delrange[1] = hi; }
+  }
+}
+
 // tile preparation for the general path: null-word prefix sums, delete / update bitmaps
 template <class PLAN, int C>
 __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
@@ -380,21 +421,18 @@ __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile
     }
     sm.wprefix[C][tid] = inc - pc;
   }
-  if (col.delta0 || col.delta1) {
-    const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
+  if (col.delta0 || col.delta1) {   // scatter the tile's updated positions (ranges found by find_all_ranges) into the bitmap
+    const int32_t ts = (int32_t)tile_start;
 #pragma unroll
     for (int dd = 0; dd < 2; dd++) {
       const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
-      int lo = 0, hi = 0;
       if (d) {
-        lo = lower_bound_i32(d->positions, 0, d->n, ts);
-        hi = lower_bound_i32(d->positions, lo, d->n, te);
+        const int lo = sm.drange[C][2 * dd], hi = sm.drange[C][2 * dd + 1];
         for (int j = lo + tid; j < hi; j += THREADS) {
           const int li = d->positions[j] - ts;
           atomicOr(&sm.updbits[C][li >> 5], 1u << (li & 31));
         }
       }
-      if (tid == 0) { sm.drange[C][2 * dd] = lo; sm.drange[C][2 * dd + 1] = hi; }
     }
   }
 }
@@ -720,12 +758,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
         if (overlay) {   // patch the tile's few updated rows, drop its deleted rows
           consumer_sync();
           clear_upd_bits<PLAN>(b, sm, ColSeq());
+          if (tid < 32) find_all_ranges<PLAN>(b, tile_start, tile == tile0, sm, tid, ColSeq());
           consumer_sync();
           prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
           if (b.deletes) {
-            const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
-            const int dlo = lower_bound_i32(b.deletes, 0, b.num_deletes, ts);
-            for (int j = dlo + tid; j < b.num_deletes && b.deletes[j] < te; j += THREADS) {
+            const int32_t ts = (int32_t)tile_start;
+            for (int j = sm.delrange[0] + tid; j < sm.delrange[1]; j += THREADS) {
               const int li = b.deletes[j] - ts;
               atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
             }
@@ -743,12 +781,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
       } else {
         consumer_sync();                       // previous tile's readers are done with sm
         clear_upd_bits<PLAN>(b, sm, ColSeq());
+        if (tid < 32) find_all_ranges<PLAN>(b, tile_start, tile == tile0, sm, tid, ColSeq());
         consumer_sync();
         prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
         if (b.deletes) {                       // delete mask -> tile bitmap (enc/ColumnDeleteDecoder.scala:49-55)
-          const int32_t ts = (int32_t)tile_start, te = ts + TILE_ROWS;
-          const int dlo = lower_bound_i32(b.deletes, 0, b.num_deletes, ts);
-          for (int j = dlo + tid; j < b.num_deletes && b.deletes[j] < te; j += THREADS) {
+          const int32_t ts = (int32_t)tile_start;
+          for (int j = sm.delrange[0] + tid; j < sm.delrange[1]; j += THREADS) {
             const int li = b.deletes[j] - ts;
             atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
           }

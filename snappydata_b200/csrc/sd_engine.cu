@@ -737,6 +737,10 @@ int flush_pending(sd_plan* p) {
       if (!p->priv->copies_done) SD_CUDA(cudaEventCreateWithFlags(&p->priv->copies_done, cudaEventDisableTiming));
       SD_CUDA(cudaEventRecord(p->priv->copies_done, p->priv->copy_stream));
       SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->copies_done, 0));
+      for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) {
+        SD_CUDA(cudaEventRecord(p->priv->extra_done[k], p->priv->extra_streams[k]));
+        SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->extra_done[k], 0));
+      }
     }
   }
   std::vector<const StoredBatch*> list;
@@ -1203,6 +1207,7 @@ int sd_plan_reset(sd_plan* p) {
   p->scratch.reset();
   if (p->priv) {
     cudaStreamSynchronize(p->priv->copy_stream);
+    for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) cudaStreamSynchronize(p->priv->extra_streams[k]);
     p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0;
     p->priv->pending_lz4.clear(); p->priv->lz4_stage.reset();
   }

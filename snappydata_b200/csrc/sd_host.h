@@ -116,6 +116,11 @@ struct sd_store {
   std::vector<sd_column> schema;
   sd::Arena arena;
   cudaStream_t copy_stream = nullptr;
+  // extra H2D streams (SD_TUNE_COPY_STREAMS > 1): large buffer copies rotate over them
+  cudaStream_t extra_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  int num_copy_streams = 1;
+  int next_stream = 0;
+  cudaEvent_t extra_done[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<std::unique_ptr<sd::StoredBatch>> batches;
   int64_t version = 0;
   int64_t h2d_bytes = 0;

@@ -9,6 +9,7 @@
 // an 8-byte aligned side copy plus a host-computed "nulls before" prefix (one int32 per 512 rows).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sd_host.h"
@@ -112,7 +113,12 @@ static int upload_vec(sd_store* s, const std::vector<T>& v, size_t align, const 
 static int upload_bytes(sd_store* s, const uint8_t* src, size_t n, size_t align, size_t misalign, uint8_t** out) {
   uint8_t* d = s->arena.alloc(n + 160, align, misalign);   // tail padding: vector loads may overrun a partial pair
   if (!d) return SD_ERR_CUDA;
-  if (n) SD_CUDA(cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, s->copy_stream));
+  cudaStream_t st = s->copy_stream;
+  if (s->num_copy_streams > 1 && n >= (size_t(64) << 10)) {   // big buffers rotate over several H2D streams
+    const int k = s->next_stream++ % s->num_copy_streams;
+    if (k > 0) st = s->extra_streams[k - 1];
+  }
+  if (n) SD_CUDA(cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, st));
   s->h2d_bytes += (int64_t)n;
   *out = d;
   return 0;
@@ -489,7 +495,10 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
     sb->stats_ncols = b->stats_ncols;
   }
   // ownership rule: the caller's buffers may be released when this call returns (unless it retains them)
-  if (!s->retain_buffers) SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+  if (!s->retain_buffers) {
+    SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+    for (int k = 0; k + 1 < s->num_copy_streams; k++) SD_CUDA(cudaStreamSynchronize(s->extra_streams[k]));
+  }
   s->batches.push_back(std::move(sb));
   s->version++;
   return 0;
@@ -516,6 +525,13 @@ int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store
   s->schema.assign(schema, schema + ncols);
   cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return sd::set_error(SD_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+  if (const char* env = getenv("SD_TUNE_COPY_STREAMS")) {
+    const int v = atoi(env);
+    if (v >= 2 && v <= 5) {
+      s->num_copy_streams = v;
+      for (int k = 0; k + 1 < v; k++) { cudaStreamCreateWithFlags(&s->extra_streams[k], cudaStreamNonBlocking); cudaEventCreateWithFlags(&s->extra_done[k], cudaEventDisableTiming); }
+    }
+  }
   *out = s;
   return 0;
 }

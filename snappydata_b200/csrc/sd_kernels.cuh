@@ -389,7 +389,9 @@ __device__ __forceinline__ void find_col_ranges(const DevCol& col, int64_t tile_
   for (int dd = 0; dd < 2; dd++) {
     const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
     int lo = 0, hi = 0;
-    if (d) warp_find_range(d->positions, d->n, ts, te, first_tile ? -1 : sm.drange[C][2 * dd + 1], lane, &lo, &hi);
+    const int first = first_tile ? -1 : sm.drange[C][2 * dd + 1];
+    if (d) warp_find_range(d->positions, d->n, ts, te, first, lane, &lo, &hi);
+    __syncwarp();   // every lane has read the previous tile's cursor before lane 0 replaces it
     if (lane == 0) { sm.drange[C][2 * dd] = lo; sm.drange[C][2 * dd + 1] = hi; }
   }
 }
@@ -399,8 +401,9 @@ __device__ __forceinline__ void find_all_ranges(const DevBatch<PLAN::NC>& b, int
   (void)dummy;
   if (b.deletes) {
     int lo, hi;
-    warp_find_range(b.deletes, b.num_deletes, (int32_t)tile_start, (int32_t)tile_start + TileSmem<PLAN>::TILE_ROWS,
-                    first_tile ? -1 : sm.delrange[1], lane, &lo, &hi);
+    const int first = first_tile ? -1 : sm.delrange[1];
+    warp_find_range(b.deletes, b.num_deletes, (int32_t)tile_start, (int32_t)tile_start + TileSmem<PLAN>::TILE_ROWS, first, lane, &lo, &hi);
+    __syncwarp();
     if (lane == 0) { sm.delrange[0] = lo; sm.delrange[1] = hi; }
   }
 }

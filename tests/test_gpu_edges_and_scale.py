@@ -1,0 +1,147 @@
+"""Edge cases the reference's tests exercise (empty and ragged inputs, all rows deleted, all-NULL columns, stats
+rows with NULL bounds) and size-independent properties at BASELINE.json scale (SF-10: 59,986,052 rows) where the
+oracle is too slow to be the checker: totals, linearity over shards, idempotence of re-execution."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from snappydata_b200 import capi, lineitem
+from snappydata_b200 import plan as P
+from snappydata_b200.column_format import (ColumnBatch, SqlType, build_batch, column_stats, encode_delete, encode_uncompressed,
+                                           stats_row)
+from snappydata_b200.plan import PlanBuilder
+
+from helpers import assert_rowsets_match
+
+pytestmark = pytest.mark.gpu
+T = SqlType
+
+
+def both(gpu_api, desc, lits, batches, nk):
+    gp = capi.Plan(gpu_api, desc).set_literals(lits)
+    op = oracle.plan(desc).set_literals(lits)
+    for x in batches:
+        gp.submit(x)
+        op.submit(x)
+    got, want = gp.finish(), op.finish()
+    assert_rowsets_match(got, want, nk)
+    return gp, op, got
+
+
+def test_empty_batch_all_deleted_and_all_null(gpu_api):
+    schema = [("k", T.STRING, True), ("v", T.INT, True), ("d", T.DOUBLE, False)]
+    r = np.random.default_rng(2)
+
+    def mk(n, all_null=False, bid=0):
+        data = {"k": np.array([b"g%d" % x for x in r.integers(0, 3, n)], dtype=object), "v": r.integers(0, 9, n).astype(np.int32), "d": r.random(n)}
+        nulls = {"k": np.ones(n, bool) if all_null else r.random(n) < 0.3, "v": np.ones(n, bool) if all_null else r.random(n) < 0.3}
+        return build_batch(n, schema, data, nulls, batch_id=bid)
+    empty = mk(0)
+    all_deleted = mk(700, bid=1)
+    all_deleted.delete_mask = encode_delete(700, np.arange(700))
+    all_null = mk(900, all_null=True, bid=2)
+    normal = mk(1500, bid=3)
+    for batches in ([empty], [all_deleted], [all_null], [empty, all_deleted, all_null, normal]):
+        b = PlanBuilder()
+        k, v, d = b.col(T.STRING, 0, True), b.col(T.INT, 1, True), b.col(T.DOUBLE, 2, False)
+        b.group_by(k)
+        b.count().count(v).sum(v).avg(v).min(v).max(d)
+        both(gpu_api, b.build(), [], batches, 1)
+        b = PlanBuilder()
+        k, v, d = b.col(T.STRING, 0, True), b.col(T.INT, 1, True), b.col(T.DOUBLE, 2, False)
+        b.filter(v.is_not_null() | k.is_null())
+        b.count().sum(v).min(v).avg(d)
+        both(gpu_api, b.build(), [], batches, 0)
+
+
+def test_stats_row_with_null_bounds_never_skips_wrongly(gpu_api):
+    """An all-NULL column has NULL lower/upper bounds: the stats predicate is NULL, the batch is kept
+    (ColumnTableScan.scala:948-957) -- and contributes nothing."""
+    n = 3000
+    vals = np.arange(n, dtype=np.int32)
+    nulls = np.ones(n, bool)
+    b0 = ColumnBatch(num_rows=n, columns=[encode_uncompressed(vals, T.INT, nulls)], stats=stats_row(n, [column_stats(vals, T.INT, nulls)]), batch_id=0)
+    b1 = ColumnBatch(num_rows=n, columns=[encode_uncompressed(vals, T.INT, None)], stats=stats_row(n, [column_stats(vals, T.INT, None)]), batch_id=1)
+    pb = PlanBuilder()
+    c = pb.col(T.INT, 0, True)
+    pb.filter((c >= pb.lit(T.INT)) & (c < pb.lit(T.INT)))
+    pb.count().sum(c)
+    for lits, skipped in (([100, 200], 0), ([5000, 6000], 1), ([-10, 0], 1)):
+        gp, op, got = both(gpu_api, pb.build(), lits, [b0, b1], 0)
+        assert gp.metrics()["columnBatchesSkipped"] == op.metrics()["columnBatchesSkipped"] == skipped
+    pb = PlanBuilder()
+    c = pb.col(T.INT, 0, True)
+    pb.filter(c.isin(3) | c.is_null())          # OR needs both sides to have a stats filter
+    pb.count()
+    both(gpu_api, pb.build(), [7, 9000, None], [b0, b1], 0)
+
+
+# ---- BASELINE.json scale: size-independent properties ---------------------------------------------------
+SF10 = 59_986_052
+
+
+@pytest.fixture(scope="module")
+def sf10_store(gpu_api):
+    store = capi.Store(gpu_api, lineitem.LINEITEM_SCHEMA)
+    store.gen_lineitem(0, SF10, 200_000, 128, 6, lineitem.Q1_COLUMN_MASK)
+    return store
+
+
+def _count_plan():
+    b = PlanBuilder()
+    ship = b.col(T.DATE, P.L_SHIPDATE)
+    b.filter(ship <= b.lit(T.DATE))
+    b.count()
+    return b.build()
+
+
+def test_sf10_q1_totals_linearity_idempotence(gpu_api, sf10_store):
+    q1 = capi.Plan(gpu_api, P.q1_plan())
+    q1.reset().set_literals(P.Q1_LITERALS)
+    q1.scan_store(sf10_store)
+    raw_all = q1.finish_raw()
+    whole = capi.final_merge(gpu_api, P.q1_plan(), raw_all)
+    assert q1.metrics()["rowsScanned"] == SF10
+    # (1) the group counts add up to COUNT(*) of the same filter (an independent plan, no group-by)
+    cnt = capi.Plan(gpu_api, _count_plan()).set_literals([P.Q1_LITERALS[0]])
+    cnt.scan_store(sf10_store)
+    (total,) = cnt.finish()[0]
+    assert sum(r[-1] for r in whole) == total
+    # (2) avg = sum / count inside every group; sum_disc_price <= sum_base_price <= sum_charge * 1.0 bounds
+    for r in whole:
+        assert abs(r[6] - r[2] / r[9]) <= 1e-9 * abs(r[6]) and abs(r[7] - r[3] / r[9]) <= 1e-9 * abs(r[7])
+        assert r[4] <= r[3] and r[4] <= r[5] <= r[3] * 1.08 + 1e-6
+    # (3) linearity: partial rows of disjoint bucket sets merge to the whole-table answer
+    parts = b""
+    for buckets in (list(range(0, 128, 2)), list(range(1, 128, 2))):
+        q1.reset().set_literals(P.Q1_LITERALS)
+        q1.scan_store(sf10_store, buckets)
+        parts += q1.finish_raw()
+    assert_rowsets_match(capi.final_merge(gpu_api, P.q1_plan(), parts), whole, 2, rel=1e-9)
+    # (4) idempotence: re-executing the cached plan reproduces the answer bit for bit (fixed reduction order)
+    q1.reset().set_literals(P.Q1_LITERALS)
+    q1.scan_store(sf10_store)
+    assert q1.finish_raw() == raw_all
+
+
+def test_sf10_q6_monotone_in_the_predicate(gpu_api, sf10_store):
+    """Widening the quantity bound can only add rows; the revenue sum with all-pass bounds equals
+    sum(l_extendedprice * l_discount) computed without a filter."""
+    q6 = capi.Plan(gpu_api, P.q6_plan())
+    prev = -1.0
+    for q in (10.0, 24.0, 51.0):
+        q6.reset().set_literals([8766, 9131, 0.05, 0.07, q])
+        q6.scan_store(sf10_store)
+        (s,) = q6.finish()[0]
+        assert s > prev
+        prev = s
+    q6.reset().set_literals([0, 100000, 0.0, 1.0, 1000.0])
+    q6.scan_store(sf10_store)
+    (everything,) = q6.finish()[0]
+    b = PlanBuilder()
+    price, disc = b.col(T.DOUBLE, P.L_EXTENDEDPRICE), b.col(T.DOUBLE, P.L_DISCOUNT)
+    b.sum(price * disc)
+    nofilter = capi.Plan(gpu_api, b.build()).set_literals([])
+    nofilter.scan_store(sf10_store)
+    (ref,) = nofilter.finish()[0]
+    assert abs(everything - ref) <= 1e-9 * abs(ref)

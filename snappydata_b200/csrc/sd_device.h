@@ -70,7 +70,7 @@ struct DevCol {
   const uint8_t* data;        // first encoded value (uncompressed), first index (dictionary),
                               // first word (bitset) or first run (run length); 128-byte aligned
   const uint64_t* nulls;      // null words (8-byte aligned copy), or nullptr when the batch has none
-  const int32_t* tile_nulls;  // [num_tiles] nulls before each tile start (host-computed), or nullptr
+  const int32_t* tile_nulls;  // [ceil(rows/512) + 1] nulls before row 512*k (last entry: all nulls), or nullptr
   const uint8_t* dict;        // int32/int64 dictionary values; for RLE strings: int32 code per run
   const int32_t* run_ends;    // RLE: [nruns] exclusive end (in stored-value index) of each run
   const DevDelta* delta0;     // depth-0 delta (wins on equal position) or nullptr
@@ -87,11 +87,13 @@ struct DevBatch {
   int32_t num_deletes;
   const int32_t* deletes;     // ascending deleted ordinals or nullptr (enc/ColumnDeleteEncoder.scala:101-134)
   const uint8_t* aux;         // per-plan per-batch tables: key code->group maps, predicate truth tables
-  int32_t flags;              // BATCH_ALL_FAST | BATCH_FAST_OVERLAY (0: general per-row decode)
+  int32_t flags;              // BATCH_ALL_FAST | BATCH_FAST_OVERLAY | BATCH_FAST_NULLS (0: general per-row decode)
   int32_t pad_;
   DevCol cols[NC > 0 ? NC : 1];
 };
 constexpr int32_t BATCH_ALL_FAST = 1;      // no nulls, simple encodings, no deltas, no deletes: staged vector loads only
+constexpr int32_t BATCH_FAST_NULLS = 4;    // simple encodings, some columns have NULLs: the tile's stored (non-null) values are staged and
+                                           // consumers map row -> value index through the null words
 constexpr int32_t BATCH_FAST_OVERLAY = 2;  // base columns as above, plus update deltas and/or a delete mask: staged loads,
                                            // then the few updated / deleted rows of each tile are patched in registers
 

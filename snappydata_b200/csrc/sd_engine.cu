@@ -418,6 +418,8 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
     hdr->deletes = sb.dev_deletes;
     bool all_fast = sb.dev_deletes == nullptr;
     bool base_fast = true;   // every base column can take the vector path (deltas / deletes aside)
+    bool simple_enc = true;  // every column has a directly addressable encoding (NULLs allowed)
+    bool any_delta = false;
     if (sb.dev_deletes) out->deleted_batches++;
     DevCol* dc = reinterpret_cast<DevCol*>(rec + (sizeof(DevBatch<1>) - sizeof(DevCol)));
     for (int c = 0; c < nc; c++) {
@@ -428,6 +430,12 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       if (!sc.unsupported.empty()) return set_error(SD_ERR_UNSUPPORTED, "column %d: %s", t, sc.unsupported.c_str());
       dc[c] = sc.dev;
       all_fast = all_fast && sc.fast;
+      {
+        const bool simple = (sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||
+                            (sp.kinds[c] != K_CODE && sc.dev.enc == ENC_UNCOMPRESSED);
+        simple_enc = simple_enc && simple;
+        any_delta = any_delta || sc.delta[0].present || sc.delta[1].present;
+      }
       base_fast = base_fast && !sc.has_nulls && ((sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||
                                                  (sp.kinds[c] != K_CODE && sc.dev.enc == ENC_UNCOMPRESSED));
       out->algo_bytes += sc.algo_bytes;
@@ -435,7 +443,7 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       for (int d = 0; d < 2; d++) if (sc.delta[d].present) out->algo_bytes += sc.delta[d].len;
     }
     if (sb.dev_deletes) out->algo_bytes += 12 + 4 * (int64_t)sb.num_deletes;
-    hdr->flags = all_fast ? BATCH_ALL_FAST : (base_fast ? BATCH_FAST_OVERLAY : 0);
+    hdr->flags = all_fast ? BATCH_ALL_FAST : (base_fast ? BATCH_FAST_OVERLAY : ((simple_enc && !any_delta && !sb.dev_deletes) ? BATCH_FAST_NULLS : 0));
     // per-batch tables: [int32 offset x nt][pad 8][uint64 kpack x nt][tables]; every table is indexed by the
     // unified dictionary code; key maps of <= 8 codes are also packed one byte per code into kpack
     if (nt) {

@@ -507,7 +507,8 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 template <class PLAN>
 __host__ __device__ constexpr int stage_col_off(int c) {
   int off = 0;
-  for (int i = 0; i < c; i++) off += THREADS * PLAN::RPT * kind_stage_width(PLAN::kind(i));
+  // + 16: a column with NULLs is copied from the 16-byte boundary below its first value of the tile
+  for (int i = 0; i < c; i++) off += THREADS * PLAN::RPT * kind_stage_width(PLAN::kind(i)) + 16;
   return off;
 }
 template <class PLAN>
@@ -521,20 +522,40 @@ __device__ __forceinline__ int col_width(uint32_t c16) {
   return PLAN::kind(C) == K_CODE ? (((c16 >> C) & 1u) ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
 }
 
+// source range of column C's values for the tile [tile_start, tile_start + rows): without NULLs value index == row
+// ordinal; with NULLs the tile's stored values are [tile_start - nulls_before(tile_start), ... ) and their count is
+// rows - nulls_in_tile, both from the host-computed prefix (one entry per NULL_PREFIX_ROWS rows)
 template <class PLAN, int C>
-__device__ __forceinline__ void issue_col_copy(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
+__device__ __forceinline__ void col_copy_range(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, int64_t* src_off, uint32_t* bytes) {
   const int w = col_width<PLAN, C>(c16);
-  const uint32_t bytes = ((uint32_t)(rows * w) + 15u) & ~15u;   // buffers are padded: over-reading a partial tile is safe
-  bulk_g2s(stage + stage_col_off<PLAN>(C), col.data + tile_start * w, bytes, bar);
+  int64_t first = tile_start;
+  int cnt = rows;
+  if (col.tile_nulls) {
+    const int n0 = col.tile_nulls[tile_start / NULL_PREFIX_ROWS];
+    const int n1 = col.tile_nulls[(tile_start + rows + NULL_PREFIX_ROWS - 1) / NULL_PREFIX_ROWS];
+    first = tile_start - n0;
+    cnt = rows - (n1 - n0);
+  }
+  const int64_t off = first * w;
+  *src_off = off & ~int64_t(15);
+  *bytes = cnt > 0 ? (uint32_t)(((off & 15) + (int64_t)cnt * w + 15) & ~int64_t(15)) : 0u;   // buffers are padded: over-reading is safe
 }
 template <class PLAN, int C>
-__device__ __forceinline__ uint32_t col_copy_bytes(uint32_t c16, int rows) {
-  return ((uint32_t)(rows * col_width<PLAN, C>(c16)) + 15u) & ~15u;
+__device__ __forceinline__ void issue_col_copy(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
+  int64_t off; uint32_t bytes;
+  col_copy_range<PLAN, C>(col, c16, tile_start, rows, &off, &bytes);
+  if (bytes) bulk_g2s(stage + stage_col_off<PLAN>(C), col.data + off, bytes, bar);
+}
+template <class PLAN, int C>
+__device__ __forceinline__ uint32_t col_copy_bytes(const DevCol& col, uint32_t c16, int64_t tile_start, int rows) {
+  int64_t off; uint32_t bytes;
+  col_copy_range<PLAN, C>(col, c16, tile_start, rows, &off, &bytes);
+  return bytes;
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void issue_tile_copies(const DevBatch<PLAN::NC>& b, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
   uint32_t total = 0;
-  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(c16, rows), 0)...};
+  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(b.cols[Cs], c16, tile_start, rows), 0)...};
   (void)d0;
   mbar_expect_tx(bar, total);
   int d1[] = {0, (issue_col_copy<PLAN, Cs>(b.cols[Cs], c16, tile_start, rows, stage, bar), 0)...};
@@ -579,6 +600,52 @@ __device__ __forceinline__ void load_col_staged(uint32_t c16, const uint8_t* sta
       regs.v[2 * u + 1] = K == K_BOOL ? (T)((x >> 8) == 1) : (T)(int8_t)(x >> 8);
     }
   }
+}
+// consumer, column with NULLs: row -> (is null, value index) through the null words; the value sits in the stage at
+// [shift + (k - first) * w] where `first` is the tile's first stored value
+template <class PLAN, int C>
+__device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, uint32_t c16, int64_t tile_start, int num_rows,
+                                                      const TileSmem<PLAN>& sm, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  const int w = col_width<PLAN, C>(c16);
+  const int n0 = col.tile_nulls[tile_start / NULL_PREFIX_ROWS];
+  const int64_t first = tile_start - n0;
+  const uint8_t* base = stage + stage_col_off<PLAN>(C) + ((first * w) & 15);
+  regs.nullmask = 0;
+#pragma unroll
+  for (int r = 0; r < PLAN::RPT; r++) {
+    const int li = row_in_tile(r);
+    const int64_t i = tile_start + li;
+    T v = (T)0;
+    bool isnull = false;
+    if (i < num_rows) {
+      const int wd = (int)(i >> 6);
+      const uint64_t word = wd < col.nwords ? col.nulls[wd] : 0ull;
+      isnull = (word >> (i & 63)) & 1ull;
+      const int64_t k = i - (n0 + sm.wprefix[C][li >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull)));
+      if (!isnull) {
+        const uint8_t* p = base + (k - first) * w;
+        if (K == K_CODE) v = (T)(w == 2 ? (int)*reinterpret_cast<const int16_t*>(p) : *reinterpret_cast<const int32_t*>(p));
+        else if (K == K_BOOL) v = (T)(*p == 1);
+        else v = *reinterpret_cast<const T*>(p);
+      } else if (K == K_CODE) v = (T)col.dict_n;
+    }
+    regs.v[r] = v;
+    regs.nullmask |= (isnull ? 1u : 0u) << r;
+  }
+}
+template <class PLAN, int C>
+__device__ __forceinline__ void load_col_staged_any(const DevCol& col, uint32_t c16, int64_t tile_start, int num_rows,
+                                                    const TileSmem<PLAN>& sm, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
+  if (col.nulls) load_col_staged_nulls<PLAN, C>(col, c16, tile_start, num_rows, sm, stage, regs);
+  else load_col_staged<PLAN, C>(c16, stage, regs);
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_all_staged_nulls(const DevBatch<PLAN::NC>& b, uint32_t c16, int64_t tile_start, const TileSmem<PLAN>& sm,
+                                                      const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+  int dummy[] = {0, (load_col_staged_any<PLAN, Cs>(b.cols[Cs], c16, tile_start, b.num_rows, sm, stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void load_all_staged(uint32_t c16, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
@@ -676,7 +743,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int bi = find_batch(args.chunk_prefix, args.nbatches, item, p_hint);
           p_hint = bi;
           const DevBatch<PLAN::NC>& b = batches[bi];
-          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY))) continue;
+          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY | BATCH_FAST_NULLS))) continue;
           const int chunk = item - args.chunk_prefix[bi];
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
@@ -733,7 +800,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
     const bool overlay = (b.flags & BATCH_FAST_OVERLAY) != 0;
-    const bool fast = (b.flags & BATCH_ALL_FAST) != 0 || (overlay && PLAN::STAGES > 0);
+    const bool with_nulls = (b.flags & BATCH_FAST_NULLS) != 0 && PLAN::STAGES > 0;
+    const bool fast = (b.flags & BATCH_ALL_FAST) != 0 || ((overlay || with_nulls) && PLAN::STAGES > 0);
     load_tables<PLAN::NTABLES>(ctx, b.aux);
     const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
     uint32_t c_scanned = 0, c_passed = 0;
@@ -750,8 +818,14 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 
       if (fast) {
         if (PLAN::STAGES > 0) {
+          if (with_nulls) {   // per-word null prefix of the tile (warp 0), visible to everyone before the loads
+            consumer_sync();
+            prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
+            consumer_sync();
+          }
           mbar_wait(&full_bar[c_stage], c_phase);
-          load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
+          if (with_nulls) load_all_staged_nulls<PLAN>(b, c16, tile_start, sm, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
+          else load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // this warp holds its rows in registers now
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }

@@ -221,7 +221,7 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
   int64_t total_nulls = 0;
   std::vector<int32_t> tile_nulls;
   if (nwords) {
-    tile_nulls.resize(ntiles > 0 ? ntiles : 1, 0);
+    tile_nulls.resize((ntiles > 0 ? ntiles : 1) + 1, 0);
     for (int w = 0; w < nwords; w++) {
       if ((w % NULL_PREFIX_WORDS) == 0 && w / NULL_PREFIX_WORDS < ntiles) tile_nulls[w / NULL_PREFIX_WORDS] = (int32_t)total_nulls;
       uint64_t word = rd_u64(buf + 8 + 8 * (int64_t)w);
@@ -232,6 +232,7 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
       total_nulls += __builtin_popcountll(word);
     }
     for (int t = (nwords + NULL_PREFIX_WORDS - 1) / NULL_PREFIX_WORDS; t < ntiles; t++) tile_nulls[t] = (int32_t)total_nulls;
+    tile_nulls.back() = (int32_t)total_nulls;
   }
   c.has_nulls = nwords > 0;
   const int64_t nn = num_rows - total_nulls;   // stored (non-null) values

@@ -522,17 +522,30 @@ __device__ __forceinline__ int col_width(uint32_t c16) {
   return PLAN::kind(C) == K_CODE ? (((c16 >> C) & 1u) ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
 }
 
+// per-chunk copy of the descriptor fields the producer needs (with the SM's shared memory carved out for the ring
+// the L1 is tiny: re-reading them from the batch descriptor for every tile costs an L2 round trip each)
+template <int NC>
+struct ProducerCols {
+  const uint8_t* data[NC > 0 ? NC : 1];
+  const int32_t* tile_nulls[NC > 0 ? NC : 1];
+};
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_producer_cols(const DevBatch<PLAN::NC>& b, ProducerCols<PLAN::NC>& pc, Seq<Cs...>) {
+  int dummy[] = {0, (pc.data[Cs] = b.cols[Cs].data, pc.tile_nulls[Cs] = b.cols[Cs].tile_nulls, 0)...};
+  (void)dummy;
+}
+
 // source range of column C's values for the tile [tile_start, tile_start + rows): without NULLs value index == row
 // ordinal; with NULLs the tile's stored values are [tile_start - nulls_before(tile_start), ... ) and their count is
 // rows - nulls_in_tile, both from the host-computed prefix (one entry per NULL_PREFIX_ROWS rows)
 template <class PLAN, int C>
-__device__ __forceinline__ void col_copy_range(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, int64_t* src_off, uint32_t* bytes) {
+__device__ __forceinline__ void col_copy_range(const int32_t* tile_nulls, uint32_t c16, int64_t tile_start, int rows, int64_t* src_off, uint32_t* bytes) {
   const int w = col_width<PLAN, C>(c16);
   int64_t first = tile_start;
   int cnt = rows;
-  if (col.tile_nulls) {
-    const int n0 = col.tile_nulls[tile_start / NULL_PREFIX_ROWS];
-    const int n1 = col.tile_nulls[(tile_start + rows + NULL_PREFIX_ROWS - 1) / NULL_PREFIX_ROWS];
+  if (tile_nulls) {
+    const int n0 = tile_nulls[tile_start / NULL_PREFIX_ROWS];
+    const int n1 = tile_nulls[(tile_start + rows + NULL_PREFIX_ROWS - 1) / NULL_PREFIX_ROWS];
     first = tile_start - n0;
     cnt = rows - (n1 - n0);
   }
@@ -540,25 +553,15 @@ __device__ __forceinline__ void col_copy_range(const DevCol& col, uint32_t c16, 
   *src_off = off & ~int64_t(15);
   *bytes = cnt > 0 ? (uint32_t)(((off & 15) + (int64_t)cnt * w + 15) & ~int64_t(15)) : 0u;   // buffers are padded: over-reading is safe
 }
-template <class PLAN, int C>
-__device__ __forceinline__ void issue_col_copy(const DevCol& col, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar) {
-  int64_t off; uint32_t bytes;
-  col_copy_range<PLAN, C>(col, c16, tile_start, rows, &off, &bytes);
-  if (bytes) bulk_g2s(stage + stage_col_off<PLAN>(C), col.data + off, bytes, bar);
-}
-template <class PLAN, int C>
-__device__ __forceinline__ uint32_t col_copy_bytes(const DevCol& col, uint32_t c16, int64_t tile_start, int rows) {
-  int64_t off; uint32_t bytes;
-  col_copy_range<PLAN, C>(col, c16, tile_start, rows, &off, &bytes);
-  return bytes;
-}
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void issue_tile_copies(const DevBatch<PLAN::NC>& b, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
+__device__ __forceinline__ void issue_tile_copies(const ProducerCols<PLAN::NC>& pc, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
+  int64_t off[PLAN::NC > 0 ? PLAN::NC : 1];
+  uint32_t bytes[PLAN::NC > 0 ? PLAN::NC : 1];
   uint32_t total = 0;
-  int d0[] = {0, (total += col_copy_bytes<PLAN, Cs>(b.cols[Cs], c16, tile_start, rows), 0)...};
+  int d0[] = {0, (col_copy_range<PLAN, Cs>(pc.tile_nulls[Cs], c16, tile_start, rows, &off[Cs], &bytes[Cs]), total += bytes[Cs], 0)...};
   (void)d0;
   mbar_expect_tx(bar, total);
-  int d1[] = {0, (issue_col_copy<PLAN, Cs>(b.cols[Cs], c16, tile_start, rows, stage, bar), 0)...};
+  int d1[] = {0, (bytes[Cs] ? (bulk_g2s(stage + stage_col_off<PLAN>(Cs), pc.data[Cs] + off[Cs], bytes[Cs], bar), 0) : 0)...};
   (void)d1;
 }
 
@@ -749,11 +752,13 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
           const int tile0 = chunk * CHUNK_TILES, tile_end = min(tile0 + CHUNK_TILES, ntiles);
           const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
+          ProducerCols<PLAN::NC> pc;
+          load_producer_cols<PLAN>(b, pc, ColSeq());
           for (int tile = tile0; tile < tile_end; tile++) {
             const int64_t tile_start = (int64_t)tile * TILE_ROWS;
             const int rows = min(TILE_ROWS, num_rows - (int)tile_start);
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            issue_tile_copies<PLAN>(b, c16, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
+            issue_tile_copies<PLAN>(pc, c16, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
         }

@@ -154,7 +154,7 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out) {
   out.name = spec.struct_name;
   out.staged = spec.stages > 0 ? 1 : 0;
   out.stage_bytes = 0;
-  for (int k : spec.kinds) out.stage_bytes += (size_t)THREADS * spec.rpt * kind_stage_width(k) + 16;
+  for (int k : spec.kinds) out.stage_bytes += (size_t)THREADS * spec.rpt * kind_stage_width(k) + 128;
   return 0;
 }
 

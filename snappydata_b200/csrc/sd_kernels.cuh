@@ -507,8 +507,9 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 template <class PLAN>
 __host__ __device__ constexpr int stage_col_off(int c) {
   int off = 0;
-  // + 16: a column with NULLs is copied from the 16-byte boundary below its first value of the tile
-  for (int i = 0; i < c; i++) off += THREADS * PLAN::RPT * kind_stage_width(PLAN::kind(i)) + 16;
+  // + 128: a column with NULLs is copied from the 16-byte boundary below its first value of the tile (<= 15 extra
+  // bytes); a full 128 keeps every column's region 128-byte aligned for the bulk copies
+  for (int i = 0; i < c; i++) off += THREADS * PLAN::RPT * kind_stage_width(PLAN::kind(i)) + 128;
   return off;
 }
 template <class PLAN>

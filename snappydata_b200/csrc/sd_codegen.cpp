@@ -533,6 +533,13 @@ struct Gen {
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
     o << "0; }\n";
+    {   // columns the plan declares nullable: only those carry the NULL-aware staged path
+      bool any = false;
+      o << "  __host__ __device__ static constexpr bool col_nullable(int c) { return ";
+      for (int c = 0; c < nc; c++) { if (p.cols[c].nullable) { o << "c == " << c << " || "; any = true; } }
+      o << "false; }\n";
+      o << "  static constexpr bool ANY_NULLABLE = " << (any ? "true" : "false") << ";\n";
+    }
     o << "  __host__ __device__ static constexpr int slot_op(int s) { return ";
     for (int s = 0; s < ns; s++) o << "s == " << s << " ? " << p.slots[s].op << " : ";
     o << "0; }\n";

@@ -433,7 +433,7 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       {
         const bool simple = (sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||
                             (sp.kinds[c] != K_CODE && sc.dev.enc == ENC_UNCOMPRESSED);
-        simple_enc = simple_enc && simple;
+        simple_enc = simple_enc && simple && (!sc.has_nulls || sp.cols[c].nullable);   // NULLs in a column the plan calls non-nullable: per-row path
         any_delta = any_delta || sc.delta[0].present || sc.delta[1].present;
       }
       base_fast = base_fast && !sc.has_nulls && ((sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||

@@ -532,7 +532,7 @@ struct ProducerCols {
 };
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void load_producer_cols(const DevBatch<PLAN::NC>& b, ProducerCols<PLAN::NC>& pc, Seq<Cs...>) {
-  int dummy[] = {0, (pc.data[Cs] = b.cols[Cs].data, pc.tile_nulls[Cs] = b.cols[Cs].tile_nulls, 0)...};
+  int dummy[] = {0, (pc.data[Cs] = b.cols[Cs].data, pc.tile_nulls[Cs] = PLAN::col_nullable(Cs) ? b.cols[Cs].tile_nulls : nullptr, 0)...};
   (void)dummy;
 }
 
@@ -544,7 +544,7 @@ __device__ __forceinline__ void col_copy_range(const int32_t* tile_nulls, uint32
   const int w = col_width<PLAN, C>(c16);
   int64_t first = tile_start;
   int cnt = rows;
-  if (tile_nulls) {
+  if (PLAN::col_nullable(C) && tile_nulls) {
     const int n0 = tile_nulls[tile_start / NULL_PREFIX_ROWS];
     const int n1 = tile_nulls[(tile_start + rows + NULL_PREFIX_ROWS - 1) / NULL_PREFIX_ROWS];
     first = tile_start - n0;
@@ -562,7 +562,7 @@ __device__ __forceinline__ void issue_tile_copies(const ProducerCols<PLAN::NC>& 
   int d0[] = {0, (col_copy_range<PLAN, Cs>(pc.tile_nulls[Cs], c16, tile_start, rows, &off[Cs], &bytes[Cs]), total += bytes[Cs], 0)...};
   (void)d0;
   mbar_expect_tx(bar, total);
-  int d1[] = {0, (bytes[Cs] ? (bulk_g2s(stage + stage_col_off<PLAN>(Cs), pc.data[Cs] + off[Cs], bytes[Cs], bar), 0) : 0)...};
+  int d1[] = {0, ((!PLAN::col_nullable(Cs) || bytes[Cs]) ? (bulk_g2s(stage + stage_col_off<PLAN>(Cs), pc.data[Cs] + off[Cs], bytes[Cs], bar), 0) : 0)...};
   (void)d1;
 }
 
@@ -642,7 +642,7 @@ __device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, uint32_
 template <class PLAN, int C>
 __device__ __forceinline__ void load_col_staged_any(const DevCol& col, uint32_t c16, int64_t tile_start, int num_rows,
                                                     const TileSmem<PLAN>& sm, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
-  if (col.nulls) load_col_staged_nulls<PLAN, C>(col, c16, tile_start, num_rows, sm, stage, regs);
+  if (PLAN::col_nullable(C) && col.nulls) load_col_staged_nulls<PLAN, C>(col, c16, tile_start, num_rows, sm, stage, regs);
   else load_col_staged<PLAN, C>(c16, stage, regs);
 }
 template <class PLAN, int... Cs>
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int bi = find_batch(args.chunk_prefix, args.nbatches, item, p_hint);
           p_hint = bi;
           const DevBatch<PLAN::NC>& b = batches[bi];
-          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY | BATCH_FAST_NULLS))) continue;
+          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY | (PLAN::ANY_NULLABLE ? BATCH_FAST_NULLS : 0)))) continue;
           const int chunk = item - args.chunk_prefix[bi];
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
     const bool overlay = (b.flags & BATCH_FAST_OVERLAY) != 0;
-    const bool with_nulls = (b.flags & BATCH_FAST_NULLS) != 0 && PLAN::STAGES > 0;
+    const bool with_nulls = PLAN::ANY_NULLABLE && (b.flags & BATCH_FAST_NULLS) != 0 && PLAN::STAGES > 0;
     const bool fast = (b.flags & BATCH_ALL_FAST) != 0 || ((overlay || with_nulls) && PLAN::STAGES > 0);
     load_tables<PLAN::NTABLES>(ctx, b.aux);
     const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());

@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <cstdlib>
 
 #include <cstdio>
 #include <cstring>
@@ -122,8 +123,10 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out) {
   nvrtcResult nr = d.CreateProgram(&prog, src.c_str(), (spec.struct_name + ".cu").c_str(), 2, headers, names);
   if (nr != NVRTC_SUCCESS) return set_error(SD_ERR_CUDA, "nvrtcCreateProgram: %s", d.GetErrorString(nr));
   d.AddNameExpression(prog, name_expr.c_str());
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
-  nr = d.CompileProgram(prog, 5, opts);
+  // -lineinfo adds ~50 % to the compile: only when a profile of a JIT kernel is wanted (SD_JIT_LINEINFO=1)
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-default-device", "-lineinfo"};
+  const char* li = getenv("SD_JIT_LINEINFO");
+  nr = d.CompileProgram(prog, (li && atoi(li) > 0) ? 5 : 4, opts);
   if (nr != NVRTC_SUCCESS) {
     size_t ls = 0;
     d.GetProgramLogSize(prog, &ls);

@@ -198,6 +198,59 @@ __device__ __forceinline__ typename KindT<KIND>::T decode_delta_value(const DevD
   return decode_value<KIND>(d.data, d.dict, nullptr, d.enc, 0, k);
 }
 
+// Out-of-line helpers for the per-row paths.  They are instantiated once per value kind instead of once per
+// (column, row-of-thread), which keeps the NVRTC compile of a plan short (the inlined form made up two thirds of
+// Q1's 10 s compile) and costs nothing on the staged paths that never call them.
+//
+// base value #k of a column in any encoding but the directly addressable uncompressed one
+template <int KIND>
+__device__ __noinline__ typename KindT<KIND>::T decode_value_slow(const uint8_t* data, const uint8_t* dict, const int32_t* run_ends,
+                                                                  int enc, int nruns, int64_t k) {
+  return decode_value<KIND>(data, dict, run_ends, enc, nruns, k);
+}
+template <int KIND>
+__device__ __forceinline__ typename KindT<KIND>::T decode_value_any(const uint8_t* data, const uint8_t* dict, const int32_t* run_ends,
+                                                                    int enc, int nruns, int64_t k) {
+  typedef typename KindT<KIND>::T T;
+  if (enc == ENC_UNCOMPRESSED) {
+    if (KIND == K_BOOL) return (T)(data[k] == 1);
+    return ld_at<T>(data, k);
+  }
+  return decode_value_slow<KIND>(data, dict, run_ends, enc, nruns, k);
+}
+// value of row `i` from the column's update deltas (the row's bit is set in the tile's update bitmap, so one of the
+// two deltas holds it); the depth-0 delta wins on equal position (enc/UpdatedColumnDecoder.scala:95-104); null
+// bits index the relative entry (enc/ColumnDeltaDecoder.scala:77-83).  r0..r3 = [lo, hi) of delta0 / delta1
+// positions inside the tile.
+template <int KIND>
+__device__ __noinline__ typename KindT<KIND>::T delta_lookup(const DevDelta* d0, const DevDelta* d1, int r0, int r1, int r2, int r3,
+                                                             int32_t i, int null_code, bool* out_null) {
+  typedef typename KindT<KIND>::T T;
+  const DevDelta* d = d0;
+  int j = -1;
+  if (d) {
+    int q = lower_bound_i32(d->positions, r0, r1, i);
+    if (q < r1 && d->positions[q] == i) j = q;
+  }
+  if (j < 0) {
+    d = d1;
+    j = lower_bound_i32(d->positions, r2, r3, i);
+  }
+  int64_t k = j;
+  bool isnull = false;
+  if (d->nulls) {
+    const int w = j >> 6;
+    const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
+    isnull = (word >> (j & 63)) & 1ull;
+    int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
+    for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
+    k = j - before;
+  }
+  *out_null = isnull;
+  if (!isnull) return decode_delta_value<KIND>(*d, k);
+  return KIND == K_CODE ? (T)null_code : (T)0;   // NULL code (ColumnTableScan.scala:706-716)
+}
+
 // ---- per-thread registers of one tile -----------------------------------------------------------
 template <class PLAN, int C>
 struct ColRegs {
@@ -288,28 +341,10 @@ __device__ __forceinline__ void load_col_general(const DevCol& col, int tile, in
           isnull = (word >> (i & 63)) & 1ull;
           k = i - (tile_nulls + sm.wprefix[C][li >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull)));
         }
-        if (!isnull) v = decode_value<K>(col.data, col.dict, col.run_ends, col.enc, col.nruns, k);
-      } else {      // depth-0 delta wins on equal position (enc/UpdatedColumnDecoder.scala:95-104)
-        const DevDelta* d = col.delta0;
-        int j = -1;
-        if (d) {
-          int q = lower_bound_i32(d->positions, sm.drange[C][0], sm.drange[C][1], (int32_t)i);
-          if (q < sm.drange[C][1] && d->positions[q] == (int32_t)i) j = q;
-        }
-        if (j < 0) {
-          d = col.delta1;
-          j = lower_bound_i32(d->positions, sm.drange[C][2], sm.drange[C][3], (int32_t)i);
-        }
-        int64_t k = j;
-        if (d->nulls) {   // null bits index the relative entry (enc/ColumnDeltaDecoder.scala:77-83)
-          const int w = j >> 6;
-          const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
-          isnull = (word >> (j & 63)) & 1ull;
-          int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
-          for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
-          k = j - before;
-        }
-        if (!isnull) v = decode_delta_value<K>(*d, k);
+        if (!isnull) v = decode_value_any<K>(col.data, col.dict, col.run_ends, col.enc, col.nruns, k);
+      } else {
+        v = delta_lookup<K>(col.delta0, col.delta1, sm.drange[C][0], sm.drange[C][1], sm.drange[C][2], sm.drange[C][3],
+                            (int32_t)i, col.dict_n, &isnull);
       }
       if (isnull && K == K_CODE) v = (T)col.dict_n;   // NULL code (ColumnTableScan.scala:706-716)
     }
@@ -331,29 +366,9 @@ __device__ __forceinline__ void overlay_col(const DevCol& col, int64_t tile_star
     const int li = row_in_tile(r);
     const int64_t i = tile_start + li;
     if (i >= num_rows || !((sm.updbits[C][li >> 5] >> (li & 31)) & 1u)) continue;
-    const DevDelta* d = col.delta0;
-    int j = -1;
-    if (d) {
-      int q = lower_bound_i32(d->positions, sm.drange[C][0], sm.drange[C][1], (int32_t)i);
-      if (q < sm.drange[C][1] && d->positions[q] == (int32_t)i) j = q;
-    }
-    if (j < 0) {
-      d = col.delta1;
-      j = lower_bound_i32(d->positions, sm.drange[C][2], sm.drange[C][3], (int32_t)i);
-    }
-    int64_t k = j;
     bool isnull = false;
-    if (d->nulls) {
-      const int w = j >> 6;
-      const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
-      isnull = (word >> (j & 63)) & 1ull;
-      int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
-      for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
-      k = j - before;
-    }
-    T v = (T)0;
-    if (!isnull) v = decode_delta_value<K>(*d, k);
-    else if (K == K_CODE) v = (T)col.dict_n;
+    const T v = delta_lookup<K>(col.delta0, col.delta1, sm.drange[C][0], sm.drange[C][1], sm.drange[C][2], sm.drange[C][3],
+                                (int32_t)i, col.dict_n, &isnull);
     regs.v[r] = v;
     regs.nullmask = (regs.nullmask & ~(1u << r)) | ((isnull ? 1u : 0u) << r);
   }
@@ -381,38 +396,44 @@ __device__ __forceinline__ void warp_find_range(const int32_t* positions, int n,
   *out_lo = lo;
   *out_hi = hi;
 }
+// one copy for all columns and plans (out of line: see decode_value_slow)
+__device__ __noinline__ void find_delta_ranges(const DevDelta* d0, const DevDelta* d1, int32_t ts, int32_t te, bool first_tile, int32_t* drange, int lane) {
+#pragma unroll
+  for (int dd = 0; dd < 2; dd++) {
+    const DevDelta* d = dd == 0 ? d0 : d1;
+    int lo = 0, hi = 0;
+    const int first = first_tile ? -1 : drange[2 * dd + 1];
+    if (d) warp_find_range(d->positions, d->n, ts, te, first, lane, &lo, &hi);
+    __syncwarp();   // every lane has read the previous tile's cursor before lane 0 replaces it
+    if (lane == 0) { drange[2 * dd] = lo; drange[2 * dd + 1] = hi; }
+  }
+}
+__device__ __noinline__ void find_delete_range(const int32_t* deletes, int n, int32_t ts, int32_t te, bool first_tile, int32_t* delrange, int lane) {
+  int lo, hi;
+  const int first = first_tile ? -1 : delrange[1];
+  warp_find_range(deletes, n, ts, te, first, lane, &lo, &hi);
+  __syncwarp();
+  if (lane == 0) { delrange[0] = lo; delrange[1] = hi; }
+}
 template <class PLAN, int C>
 __device__ __forceinline__ void find_col_ranges(const DevCol& col, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, int lane) {
   if (!(col.delta0 || col.delta1)) return;
-  const int32_t ts = (int32_t)tile_start, te = ts + TileSmem<PLAN>::TILE_ROWS;
-#pragma unroll
-  for (int dd = 0; dd < 2; dd++) {
-    const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
-    int lo = 0, hi = 0;
-    const int first = first_tile ? -1 : sm.drange[C][2 * dd + 1];
-    if (d) warp_find_range(d->positions, d->n, ts, te, first, lane, &lo, &hi);
-    __syncwarp();   // every lane has read the previous tile's cursor before lane 0 replaces it
-    if (lane == 0) { sm.drange[C][2 * dd] = lo; sm.drange[C][2 * dd + 1] = hi; }
-  }
+  const int32_t ts = (int32_t)tile_start;
+  find_delta_ranges(col.delta0, col.delta1, ts, ts + TileSmem<PLAN>::TILE_ROWS, first_tile, sm.drange[C], lane);
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void find_all_ranges(const DevBatch<PLAN::NC>& b, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, int lane, Seq<Cs...>) {
   int dummy[] = {0, (find_col_ranges<PLAN, Cs>(b.cols[Cs], tile_start, first_tile, sm, lane), 0)...};
   (void)dummy;
-  if (b.deletes) {
-    int lo, hi;
-    const int first = first_tile ? -1 : sm.delrange[1];
-    warp_find_range(b.deletes, b.num_deletes, (int32_t)tile_start, (int32_t)tile_start + TileSmem<PLAN>::TILE_ROWS, first, lane, &lo, &hi);
-    __syncwarp();
-    if (lane == 0) { sm.delrange[0] = lo; sm.delrange[1] = hi; }
-  }
+  if (b.deletes)
+    find_delete_range(b.deletes, b.num_deletes, (int32_t)tile_start, (int32_t)tile_start + TileSmem<PLAN>::TILE_ROWS, first_tile, sm.delrange, lane);
 }
 
 // tile preparation for the general path: null-word prefix sums, delete / update bitmaps
-template <class PLAN, int C>
-__device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
+template <int TILE_WORDS>
+__device__ __noinline__ void prep_col_words(const DevCol* colp, int64_t tile_start, int32_t* wprefix, uint32_t* updbits, const int32_t* drange) {
+  const DevCol& col = *colp;
   const int tid = threadIdx.x;
-  constexpr int TILE_ROWS = TileSmem<PLAN>::TILE_ROWS, TILE_WORDS = TileSmem<PLAN>::TILE_WORDS;
   if (col.nulls && tid < TILE_WORDS) {   // warp 0, lanes 0..TILE_WORDS-1: exclusive scan of per-word popcounts
     const int w = (int)(tile_start >> 6) + tid;
     const int pc = w < col.nwords ? __popcll(col.nulls[w]) : 0;
@@ -422,7 +443,7 @@ __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile
       int t = __shfl_up_sync((TILE_WORDS >= 32 ? 0xffffffffu : ((1u << TILE_WORDS) - 1u)), inc, d, TILE_WORDS);
       if (tid >= d) inc += t;
     }
-    sm.wprefix[C][tid] = inc - pc;
+    wprefix[tid] = inc - pc;
   }
   if (col.delta0 || col.delta1) {   // scatter the tile's updated positions (ranges found by find_all_ranges) into the bitmap
     const int32_t ts = (int32_t)tile_start;
@@ -430,14 +451,18 @@ __device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile
     for (int dd = 0; dd < 2; dd++) {
       const DevDelta* d = dd == 0 ? col.delta0 : col.delta1;
       if (d) {
-        const int lo = sm.drange[C][2 * dd], hi = sm.drange[C][2 * dd + 1];
+        const int lo = drange[2 * dd], hi = drange[2 * dd + 1];
         for (int j = lo + tid; j < hi; j += THREADS) {
           const int li = d->positions[j] - ts;
-          atomicOr(&sm.updbits[C][li >> 5], 1u << (li & 31));
+          atomicOr(&updbits[li >> 5], 1u << (li & 31));
         }
       }
     }
   }
+}
+template <class PLAN, int C>
+__device__ __forceinline__ void prep_col_general(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm) {
+  if (col.nulls || col.delta0 || col.delta1) prep_col_words<TileSmem<PLAN>::TILE_WORDS>(&col, tile_start, sm.wprefix[C], sm.updbits[C], sm.drange[C]);
 }
 
 template <class PLAN, int... Cs>
@@ -838,30 +863,10 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
         } else {
           load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
         }
-        if (overlay) {   // patch the tile's few updated rows, drop its deleted rows
-          consumer_sync();
-          clear_upd_bits<PLAN>(b, sm, ColSeq());
-          if (tid < 32) find_all_ranges<PLAN>(b, tile_start, tile == tile0, sm, tid, ColSeq());
-          consumer_sync();
-          prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
-          if (b.deletes) {
-            const int32_t ts = (int32_t)tile_start;
-            for (int j = sm.delrange[0] + tid; j < sm.delrange[1]; j += THREADS) {
-              const int li = b.deletes[j] - ts;
-              atomicOr(&sm.delbits[li >> 5], 1u << (li & 31));
-            }
-          }
-          consumer_sync();
-          overlay_all<PLAN>(b, tile_start, sm, regs, ColSeq());
-          if (b.deletes) {
-#pragma unroll
-            for (int r = 0; r < RPT; r++) {
-              const int li = row_in_tile(r);
-              if ((sm.delbits[li >> 5] >> (li & 31)) & 1u) live &= ~(1u << r);
-            }
-          }
-        }
-      } else {
+      }
+      if (!fast || overlay) {
+        // per-row decode of the whole tile (!fast), or patch the staged tile's few updated rows (overlay); both
+        // drop the deleted rows
         consumer_sync();                       // previous tile's readers are done with sm
         clear_upd_bits<PLAN>(b, sm, ColSeq());
         if (tid < 32) find_all_ranges<PLAN>(b, tile_start, tile == tile0, sm, tid, ColSeq());
@@ -875,7 +880,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           }
         }
         consumer_sync();
-        load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
+        if (fast) overlay_all<PLAN>(b, tile_start, sm, regs, ColSeq());
+        else load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
         if (b.deletes) {
 #pragma unroll
           for (int r = 0; r < RPT; r++) {

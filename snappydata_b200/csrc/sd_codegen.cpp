@@ -507,7 +507,7 @@ struct Gen {
       }
     }
     if ((int)p.tables.size() > MAX_TABLES) return fail(SD_ERR_UNSUPPORTED, "more than 16 dictionary lookup tables in one plan");
-    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups << ";litnull=" << p.lit_nullable;
+    sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups << ";litnull=" << p.lit_nullable << ";slow=" << p.slow_paths;
     p.signature = sig.str();
     char hbuf[32];
     snprintf(hbuf, sizeof(hbuf), "%016llx", (unsigned long long)std::hash<std::string>()(p.signature));
@@ -529,6 +529,7 @@ struct Gen {
     o << "  static constexpr int MIN_CTAS = " << p.min_ctas << ";\n  static constexpr int RPT = " << p.rpt << ";\n";
     o << "  static constexpr int STAGES = " << (p.stages > 0 ? 1 : 0) << ";\n";
     o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
+    o << "  static constexpr bool SLOW_PATHS = " << (p.slow_paths ? "true" : "false") << ";\n";
     o << "  static constexpr int NTABLES = " << p.tables.size() << ";\n";
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
@@ -609,6 +610,7 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
     if (opt) o = *opt;
     out.reg_groups = out.mode == MODE_GROUPS ? std::max(0, o.reg_groups) : 0;
     out.lit_nullable = o.lit_nullable ? 1 : 0;
+    out.slow_paths = o.slow_paths ? 1 : 0;
     out.rpt = 4;
     out.min_ctas = out.mode == MODE_GROUPS ? 1 : (row_bytes <= 28 ? 3 : 2);   // group tables want the SM's shared memory
     out.stages = 1;
@@ -629,12 +631,13 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
 // ---- C entry point: generated source + signature of a plan (build step, debugging, profiling) ------
 extern "C" int sd_plan_codegen(const sd_plan_desc* desc, char* source, int64_t source_cap, int64_t* source_len,
                                char* signature, int64_t sig_cap, char* struct_name, int64_t name_cap, int32_t reg_groups,
-                               int32_t lit_nullable) {
+                               int32_t lit_nullable, int32_t slow_paths) {
   sd::PlanSpec spec;
   std::string err;
   sd::CodegenOptions opt;
   opt.reg_groups = reg_groups;
   opt.lit_nullable = lit_nullable;
+  opt.slow_paths = slow_paths;
   int rc = sd::analyze_plan(desc, spec, err, &opt);
   if (rc) {
     if (source && source_cap > 0) snprintf(source, (size_t)source_cap, "%s", err.c_str());

@@ -59,6 +59,7 @@ struct PlanSpec {
   int min_ctas = 2;                  // __launch_bounds__ min CTAs per SM (= target CTAs per SM)
   int stages = 1;                    // > 0: staged fast path (producer warp + cp.async.bulk ring); 0: direct loads
   int lit_nullable = 0;              // 1: literal slots may be NULL at run time (separate kernel variant)
+  int slow_paths = 0;                // 1: kernel variant that also carries the per-row decode / delta / delete paths
   int reg_groups = 0;                // > 0: MODE_GROUPS table held in registers for up to this many groups
   std::string signature;             // canonical text of everything the generated code depends on
   std::string struct_name;           // Plan_<hash of signature>
@@ -73,6 +74,7 @@ struct CodegenOptions {
   int stages = -1;
   int reg_groups = 0;
   int lit_nullable = 0;
+  int slow_paths = 0;
   int force_hash = 0;   // keyed plans: use the hash table even when all keys are dictionary strings
 };
 

@@ -233,8 +233,11 @@ struct sd_plan {
   KernelEntry kernel;             // generic kernel of the plan
   KernelEntry kernel_reg;         // register-group-table variant (MODE_GROUPS, <= REG_GROUPS_MAX groups), lazily resolved
   int kernel_reg_state = 0;       // 0 unknown, 1 available, -1 unavailable
-  KernelEntry kernel_litnull;     // variant for executions with a NULL literal, lazily resolved
-  int kernel_litnull_state = 0;
+  // lazily resolved variants of the generic kernel, indexed by (NULL literal in this execution) | (scan has batches
+  // that need the per-row decode / delta / delete paths) << 1; index 0 is `kernel` itself (staged paths only)
+  KernelEntry variant[4];
+  int variant_state[4] = {0, 0, 0, 0};
+  bool force_hash = false;        // the dense group table was abandoned for the hash table during an execution
   const KernelEntry* active = nullptr;
   std::string kernel_name;
   int max_ctas_per_sm = 0;
@@ -279,7 +282,7 @@ struct sd_plan {
     const sd_store* store = nullptr; int64_t version = -1; std::vector<int32_t> buckets; std::string lit_key;
     const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
     int64_t rows = 0, algo_bytes = 0, seen = 0, skipped = 0, updated_cols = 0, deleted_batches = 0;
-    int32_t radix[MAX_KEYS] = {1, 1, 1, 1}; int ngroups = 1; bool valid = false;
+    int32_t radix[MAX_KEYS] = {1, 1, 1, 1}; int ngroups = 1; bool valid = false; int needs_slow = 0;
     std::vector<const StoredBatch*> batches;
   } cache;
   Arena cache_arena;
@@ -288,7 +291,7 @@ struct sd_plan {
   uint32_t hash_capacity = 0;
   uint64_t* d_hash_ident = nullptr;
   bool hash_init = false;
-  struct Launch { const void* d_batches; const int32_t* d_prefix; int nbatches; int total_chunks; int batch_base; };
+  struct Launch { const void* d_batches; const int32_t* d_prefix; int nbatches; int total_chunks; int batch_base; int needs_slow; };
   // MODE_PROJECT output records + the batches of this execution (records carry a batch ordinal)
   uint8_t* d_out = nullptr;
   int64_t out_cap = 0;
@@ -397,6 +400,7 @@ int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int devi
 struct BuiltScan {
   const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
   int64_t rows = 0, algo_bytes = 0, updated_cols = 0, deleted_batches = 0;
+  int needs_slow = 0;   // some batch needs the kernel variant with the per-row paths
 };
 
 // Build the device descriptors + per-batch tables for a list of resident batches.
@@ -444,6 +448,7 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
     }
     if (sb.dev_deletes) out->algo_bytes += 12 + 4 * (int64_t)sb.num_deletes;
     hdr->flags = all_fast ? BATCH_ALL_FAST : (base_fast ? BATCH_FAST_OVERLAY : ((simple_enc && !any_delta && !sb.dev_deletes) ? BATCH_FAST_NULLS : 0));
+    if (!(hdr->flags == BATCH_ALL_FAST || (hdr->flags == BATCH_FAST_NULLS && p->kernel.staged))) out->needs_slow = 1;
     // per-batch tables: [int32 offset x nt][pad 8][uint64 kpack x nt][tables]; every table is indexed by the
     // unified dictionary code; key maps of <= 8 codes are also packed one byte per code into kpack
     if (nt) {
@@ -563,12 +568,30 @@ int ensure_out(sd_plan* p, int64_t cap_records) {
   return 0;
 }
 
-int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks,
+// the kernel variant of the plan for this execution / launch
+int plan_variant(sd_plan* p, int litnull, int slow, const KernelEntry** out) {
+  const int idx = (litnull ? 1 : 0) | (slow ? 2 : 0);
+  if (idx == 0) { *out = &p->kernel; return 0; }
+  if (!p->variant_state[idx]) {
+    CodegenOptions opt;
+    opt.lit_nullable = litnull ? 1 : 0;
+    opt.slow_paths = slow ? 1 : 0;
+    opt.force_hash = p->force_hash ? 1 : 0;
+    sd_plan_desc dv = p->spec.desc_view();
+    int rc = resolve_kernel(dv, opt, p->device, &p->variant[idx], nullptr);
+    if (rc) return rc;
+    p->variant_state[idx] = 1;
+  }
+  *out = &p->variant[idx];
+  return 0;
+}
+
+int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks, int needs_slow,
                 const std::vector<const StoredBatch*>* blist = nullptr, int replay_batch_base = -1) {
   const bool replay = replay_batch_base >= 0;
   int batch_base = replay ? replay_batch_base : (int)p->exec_batches.size();
   if (!replay && p->spec.mode != MODE_NOKEY) {
-    p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks, batch_base});
+    p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks, batch_base, needs_slow});
     if (blist) p->exec_batches.insert(p->exec_batches.end(), blist->begin(), blist->end());
   }
   p->finished_nrows = -1;
@@ -597,15 +620,16 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     std::vector<sd_plan::Launch> earlier(p->launch_log.begin(), p->launch_log.end() - (replay ? 0 : 1));
     p->spec = hspec;
     p->kernel = hk;
-    p->kernel_litnull_state = 0;
+    p->force_hash = true;
+    for (int v = 0; v < 4; v++) p->variant_state[v] = 0;
     p->active = nullptr;
     p->last_kernel = nullptr;
     p->last_smem = (size_t)-1;
     p->result_init = false;
     p->hash_init = false;
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
-    for (auto& l : earlier) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
-    return launch_scan(p, d_batches, d_prefix, nbatches, total_chunks, nullptr, batch_base);
+    for (auto& l : earlier) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
+    return launch_scan(p, d_batches, d_prefix, nbatches, total_chunks, needs_slow, nullptr, batch_base);
   }
   const size_t ne = (size_t)ngroups * ns;
   // Where the dense group table lives (decided per launch from its size):
@@ -613,20 +637,13 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   //   per CTA with atomics > global atomics on the running result.
   // What is left of the SM's shared memory (per target CTA) becomes the ring of the staged fast path.
   const KernelEntry* k = &p->kernel;
-  {   // a NULL literal needs the variant whose generated code carries literal null flags
+  {   // a NULL literal needs the variant whose generated code carries literal null flags; batches with deltas, deletes
+      // or encodings that are not directly addressable need the variant that carries the per-row paths
     bool any_null = false;
     for (auto& l : p->lits) any_null = any_null || l.is_null;
-    if (any_null) {
-      if (p->kernel_litnull_state == 0) {
-        CodegenOptions opt;
-        opt.lit_nullable = 1;
-        sd_plan_desc dv = sp.desc_view();
-        int rc = resolve_kernel(dv, opt, p->device, &p->kernel_litnull, nullptr);
-        if (rc) return rc;
-        p->kernel_litnull_state = 1;
-      }
-      k = &p->kernel_litnull;
-    }
+    static const bool force_full = getenv("SD_TUNE_FULL_KERNEL") != nullptr;   // measurement aid
+    int rc = plan_variant(p, any_null, needs_slow || force_full, &k);
+    if (rc) return rc;
   }
   int table_mode = TABLE_PRIVATE;
   int target_ctas = std::max(1, sp.min_ctas);
@@ -759,7 +776,7 @@ int flush_pending(sd_plan* p) {
   p->metrics[3] += bs.updated_cols;
   p->metrics[4] += bs.deleted_batches;
   p->metrics[9] += bs.algo_bytes;
-  rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks, &list);
+  rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks, bs.needs_slow, &list);
   p->pending.clear();
   p->pending_bytes = 0;
   return rc;
@@ -833,7 +850,7 @@ int finish_hash(sd_plan* p) {
     int rc = hash_ensure(p, ncap);
     if (rc) return rc;
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
-    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
+    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
   }
   const uint32_t count = flags[8];
   // compact -> host
@@ -900,7 +917,7 @@ int finish_project(sd_plan* p) {
     if (rc) return rc;
     SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
-    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, nullptr, l.batch_base); if (rc) return rc; }
+    for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
   }
   std::vector<uint64_t> recs((size_t)count * (size_t)(rec / 8));
   unsigned long long counters[2] = {0, 0};
@@ -1120,7 +1137,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
     c.store = s; c.version = s->version; c.buckets = buckets; c.lit_key = lk;
     c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
     c.rows = bs.rows; c.algo_bytes = bs.algo_bytes; c.seen = seen; c.skipped = skipped;
-    c.updated_cols = bs.updated_cols; c.deleted_batches = bs.deleted_batches;
+    c.updated_cols = bs.updated_cols; c.deleted_batches = bs.deleted_batches; c.needs_slow = bs.needs_slow;
     c.batches = list;
     c.valid = true;
   }
@@ -1129,7 +1146,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   p->metrics[3] += c.updated_cols;
   p->metrics[4] += c.deleted_batches;
   p->metrics[9] += c.algo_bytes;
-  return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks, &c.batches);
+  return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks, c.needs_slow, &c.batches);
 }
 
 int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {

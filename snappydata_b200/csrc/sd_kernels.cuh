@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int bi = find_batch(args.chunk_prefix, args.nbatches, item, p_hint);
           p_hint = bi;
           const DevBatch<PLAN::NC>& b = batches[bi];
-          if (!(b.flags & (BATCH_ALL_FAST | BATCH_FAST_OVERLAY | (PLAN::ANY_NULLABLE ? BATCH_FAST_NULLS : 0)))) continue;
+          if (!(b.flags & (BATCH_ALL_FAST | (PLAN::SLOW_PATHS ? BATCH_FAST_OVERLAY : 0) | (PLAN::ANY_NULLABLE ? BATCH_FAST_NULLS : 0)))) continue;
           const int chunk = item - args.chunk_prefix[bi];
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
@@ -830,9 +830,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     const DevBatch<PLAN::NC>& b = batches[lo];
     const int chunk = item - args.chunk_prefix[lo];
     const int num_rows = b.num_rows;
-    const bool overlay = (b.flags & BATCH_FAST_OVERLAY) != 0;
+    const bool overlay = PLAN::SLOW_PATHS && (b.flags & BATCH_FAST_OVERLAY) != 0;
     const bool with_nulls = PLAN::ANY_NULLABLE && (b.flags & BATCH_FAST_NULLS) != 0 && PLAN::STAGES > 0;
     const bool fast = (b.flags & BATCH_ALL_FAST) != 0 || ((overlay || with_nulls) && PLAN::STAGES > 0);
+    // the staged-only variant of a plan (SLOW_PATHS == false) is launched on batches of the staged kinds only; anything
+    // else reaching it is a host-side bug: stop loudly instead of aggregating garbage
+    if (!PLAN::SLOW_PATHS && !fast) __trap();
     load_tables<PLAN::NTABLES>(ctx, b.aux);
     const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
     uint32_t c_scanned = 0, c_passed = 0;
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
         }
       }
-      if (!fast || overlay) {
+      if (PLAN::SLOW_PATHS && (!fast || overlay)) {
         // per-row decode of the whole tile (!fast), or patch the staged tile's few updated rows (overlay); both
         // drop the deleted rows
         consumer_sync();                       // previous tile's readers are done with sm

@@ -612,7 +612,9 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
     out.lit_nullable = o.lit_nullable ? 1 : 0;
     out.slow_paths = o.slow_paths ? 1 : 0;
     out.rpt = 4;
-    out.min_ctas = out.mode == MODE_GROUPS ? 1 : (row_bytes <= 28 ? 3 : 2);   // group tables want the SM's shared memory
+    // group tables want the SM's shared memory; otherwise 2 CTAs per SM (sweep in profiles/r01_tuning.txt: Q6 6.9 TB/s
+    // at 2 vs 6.8 at 3, 6.5 at 1), 3 only for very narrow rows whose tiles are too small to keep enough bytes in flight
+    out.min_ctas = out.mode == MODE_GROUPS ? 1 : (row_bytes <= 8 ? 3 : 2);
     out.stages = 1;
     if (const char* e = getenv("SD_TUNE_RPT")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) out.rpt = v; }
     if (const char* e = getenv("SD_TUNE_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) out.min_ctas = v; }

@@ -286,6 +286,7 @@ struct sd_plan {
     std::vector<const StoredBatch*> batches;
   } cache;
   Arena cache_arena;
+  PinnedArena pinned;             // staging of descriptor uploads (valid until the next reset)
   // MODE_HASH group table + the launches of this execution (replayed after a grow)
   HashTable hash = {};
   uint32_t hash_capacity = 0;
@@ -404,7 +405,9 @@ struct BuiltScan {
 };
 
 // Build the device descriptors + per-batch tables for a list of resident batches.
-int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& arena, BuiltScan* out) {
+// `up` is the stream the descriptors are uploaded on (from page-locked staging: the caller is never blocked); the
+// scan must be ordered after it.
+int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& arena, cudaStream_t up, BuiltScan* out) {
   const PlanSpec& sp = p->spec;
   const int nc = (int)sp.cols.size();
   const size_t bstride = sizeof(DevBatch<1>) - sizeof(DevCol) + (size_t)std::max(nc, 1) * sizeof(DevCol);
@@ -496,16 +499,21 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
   uint8_t* d_aux = nullptr;
   if (!aux.empty()) {
     d_aux = arena.alloc(aux.size() + 16, 16);
-    if (!d_aux) return SD_ERR_CUDA;
-    SD_CUDA(cudaMemcpyAsync(d_aux, aux.data(), aux.size(), cudaMemcpyHostToDevice, p->stream));
+    uint8_t* h_aux = p->pinned.alloc(aux.size());
+    if (!d_aux || !h_aux) return SD_ERR_CUDA;
+    memcpy(h_aux, aux.data(), aux.size());
+    SD_CUDA(cudaMemcpyAsync(d_aux, h_aux, aux.size(), cudaMemcpyHostToDevice, up));
     for (size_t bi = 0; bi < list.size(); bi++) reinterpret_cast<DevBatch<1>*>(hb.data() + bi * bstride)->aux = d_aux + aux_off[bi];
   }
   uint8_t* d_b = arena.alloc(hb.size() + 16, 16);
   uint8_t* d_p = arena.alloc(prefix.size() * 4 + 16, 16);
-  if (!d_b || !d_p) return SD_ERR_CUDA;
-  SD_CUDA(cudaMemcpyAsync(d_b, hb.data(), hb.size(), cudaMemcpyHostToDevice, p->stream));
-  SD_CUDA(cudaMemcpyAsync(d_p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, p->stream));
-  SD_CUDA(cudaStreamSynchronize(p->stream));   // host vectors go out of scope
+  uint8_t* h_b = p->pinned.alloc(hb.size());
+  uint8_t* h_p = p->pinned.alloc(prefix.size() * 4);
+  if (!d_b || !d_p || !h_b || !h_p) return SD_ERR_CUDA;
+  memcpy(h_b, hb.data(), hb.size());
+  memcpy(h_p, prefix.data(), prefix.size() * 4);
+  SD_CUDA(cudaMemcpyAsync(d_b, h_b, hb.size(), cudaMemcpyHostToDevice, up));
+  SD_CUDA(cudaMemcpyAsync(d_p, h_p, prefix.size() * 4, cudaMemcpyHostToDevice, up));
   out->d_batches = d_b;
   out->d_prefix = reinterpret_cast<const int32_t*>(d_p);
   out->nbatches = (int)list.size();
@@ -755,24 +763,28 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
 
 int flush_pending(sd_plan* p) {
   if (p->pending.empty()) return 0;
-  if (p->priv) {
+  if (p->priv) {   // queue the expansion of compressed buffers first: it runs while the descriptors are being built
     int rc0 = store_flush_lz4(p->priv);
     if (rc0) return rc0;
-    if (p->priv->retain_buffers) {   // copies were queued without synchronisation: order the scan after them
-      if (!p->priv->copies_done) SD_CUDA(cudaEventCreateWithFlags(&p->priv->copies_done, cudaEventDisableTiming));
-      SD_CUDA(cudaEventRecord(p->priv->copies_done, p->priv->copy_stream));
-      SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->copies_done, 0));
-      for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) {
-        SD_CUDA(cudaEventRecord(p->priv->extra_done[k], p->priv->extra_streams[k]));
-        SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->extra_done[k], 0));
-      }
-    }
   }
   std::vector<const StoredBatch*> list;
   for (auto& x : p->pending) list.push_back(x.sb);
   BuiltScan bs;
-  int rc = build_scan(p, list, p->scratch, &bs);
+  // nothing below blocks the submitting thread: descriptors go out on the copy stream from page-locked staging, and
+  // the scan is ordered after the copies and the expansions with events
+  int rc = build_scan(p, list, p->scratch, p->priv ? p->priv->copy_stream : p->stream, &bs);
   if (rc) return rc;
+  if (p->priv) {
+    if (!p->priv->copies_done) SD_CUDA(cudaEventCreateWithFlags(&p->priv->copies_done, cudaEventDisableTiming));
+    SD_CUDA(cudaEventRecord(p->priv->copies_done, p->priv->copy_stream));
+    SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->copies_done, 0));
+    for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) {
+      SD_CUDA(cudaEventRecord(p->priv->extra_done[k], p->priv->extra_streams[k]));
+      SD_CUDA(cudaStreamWaitEvent(p->stream, p->priv->extra_done[k], 0));
+    }
+    rc = store_lz4_order(p->priv, p->stream);   // the scan reads what the expansions write
+    if (rc) return rc;
+  }
   p->metrics[3] += bs.updated_cols;
   p->metrics[4] += bs.deleted_batches;
   p->metrics[9] += bs.algo_bytes;
@@ -1093,9 +1105,9 @@ int sd_batch_submit(sd_plan* p, const sd_batch* b) {
   // scan columns of the private store are positional: re-point table ordinals on the fly in build_scan
   p->pending.push_back({sb});
   p->pending_bytes += p->priv->h2d_bytes - before;
-  // compressed inputs are expanded by one launch per flush whose duration is that of the longest buffer:
-  // use fewer, larger flushes for them
-  const int64_t threshold = p->priv->pending_lz4.empty() ? (int64_t(256) << 20) : (int64_t(1) << 30);
+  // (compressed inputs: one expansion launch per flush, as long as its longest buffer; the launches of successive
+  // flushes overlap on their own streams, so the same flush size serves both)
+  const int64_t threshold = int64_t(256) << 20;
   if (p->pending_bytes >= threshold) return flush_pending(p);
   return 0;
 }
@@ -1108,6 +1120,8 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   int rc = flush_pending(p);
   if (rc) return rc;
   rc = store_flush_lz4(s);
+  if (rc) return rc;
+  rc = store_lz4_check(s);   // resident stores: expansions happen once, before the first scan
   if (rc) return rc;
   for (auto& c : p->spec.cols) {
     if (c.table_ordinal < 0 || c.table_ordinal >= (int)s->schema.size()) return set_error(SD_ERR_INVALID, "plan column ordinal %d outside the store schema", c.table_ordinal);
@@ -1132,7 +1146,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
       list.push_back(&sb);
     }
     BuiltScan bs;
-    rc = build_scan(p, list, p->cache_arena, &bs);
+    rc = build_scan(p, list, p->cache_arena, p->stream, &bs);
     if (rc) return rc;
     c.store = s; c.version = s->version; c.buckets = buckets; c.lit_key = lk;
     c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
@@ -1154,6 +1168,7 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   SD_CUDA(cudaSetDevice(p->device));
   int rc = flush_pending(p);
   if (rc) return rc;
+  if (p->priv) { rc = store_lz4_check(p->priv); if (rc) return rc; }   // a corrupt compressed buffer fails the execution
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
   if (sp.mode == MODE_HASH || sp.mode == MODE_PROJECT) {
@@ -1230,11 +1245,14 @@ int sd_plan_reset(sd_plan* p) {
   SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
   memset(p->metrics, 0, sizeof(p->metrics));
   p->scratch.reset();
+  p->pinned.reset();
   if (p->priv) {
     cudaStreamSynchronize(p->priv->copy_stream);
     for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) cudaStreamSynchronize(p->priv->extra_streams[k]);
     p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0;
-    p->priv->pending_lz4.clear(); p->priv->lz4_stage.reset();
+    p->priv->pending_lz4.clear();
+    store_lz4_check(p->priv);   // waits for queued expansions (their result is being discarded) and releases the staging
+    p->priv->lz4_stage.reset();
   }
   // key dictionaries persist across executions of a cached plan only if the scan cache refers to them
   if (!p->cache.valid) {

@@ -73,6 +73,17 @@ struct Arena {
   ~Arena() { release(); }
 };
 
+// page-locked host staging for small uploads (descriptors, tables) that must not block the submitting thread:
+// copies from it are truly asynchronous, and the memory stays valid until reset()
+struct PinnedArena {
+  size_t slab_bytes = size_t(4) << 20;
+  std::vector<std::pair<uint8_t*, size_t>> slabs;
+  size_t cur_slab = 0, cur_off = 0;
+  uint8_t* alloc(size_t n);   // 16-byte aligned, nullptr on failure (error set)
+  void reset() { cur_slab = 0; cur_off = 0; }
+  ~PinnedArena();
+};
+
 // ---- resident batches ------------------------------------------------------------------------------
 struct StoredDelta {
   bool present = false;
@@ -131,13 +142,25 @@ struct sd_store {
   sd::Arena lz4_stage;
   unsigned int* d_lz4_error = nullptr;
   int64_t lz4_buffers = 0, lz4_in_bytes = 0, lz4_out_bytes = 0;
+  // expansions are queued on a few streams of their own so that the launches of successive flushes (each one as
+  // long as its longest buffer) overlap each other and the copies that follow
+  static constexpr int LZ4_STREAMS = 4;
+  cudaStream_t lz4_streams[LZ4_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lz4_done[LZ4_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  bool lz4_used[LZ4_STREAMS] = {false, false, false, false};
+  cudaEvent_t lz4_copied = nullptr;
+  int lz4_next = 0;
 };
 
 namespace sd {
 // upload one batch (columns by table ordinal of `schema`) into the store's arena
 int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals /* nullptr: identity */);
-// expand every pending compressed buffer (blocks until done); no-op when nothing is pending
+// queue the expansion of every pending compressed buffer (asynchronous; no-op when nothing is pending)
 int store_flush_lz4(sd_store* s);
+// make `stream` wait for every expansion queued so far
+int store_lz4_order(sd_store* s, cudaStream_t stream);
+// block until the queued expansions are done, release their staging memory, report a corrupt payload
+int store_lz4_check(sd_store* s);
 }
 
 #endif

@@ -4,7 +4,7 @@
 // >= 2048 bytes and shrinks to <= 75 % (encoders/.../store/CompressionUtils.scala:53-61,102-110) and
 // decompresses it on the CPU whenever a scan needs it (ColumnFormatEntry.scala:498-570,
 // ColumnBatchIterator.scala:102-113).  Here only the COMPRESSED bytes cross PCIe; the block is expanded in
-// HBM by one warp per buffer, many buffers per launch.  The host decodes just the first bytes it needs to
+// HBM by one warp per buffer, many buffers per launch, launches of successive flushes overlapping each other.  The host decodes just the first bytes it needs to
 // lay the buffer out (8-byte header, null words, dictionary) with the small prefix decoder below.
 //
 // LZ4 block format: sequences of [token][literal length ext*][literals][offset:2][match length ext*];
@@ -39,55 +39,251 @@ int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int
   return o;
 }
 
-// ---- device: one warp per buffer ---------------------------------------------------------------------
-// Measured (round 1, profiles/r01_lz4.txt): the decode of one 1.6 MB column buffer is a serial chain of ~350
-// cycles per LZ4 sequence (token load, offset load, match source read from L2), i.e. ~70-130 ms per launch
-// however many buffers it covers, so for Q1 the compressed path (46 % of the bytes over PCIe) is currently
-// SLOWER end to end than sending the buffers uncompressed (0.43 vs 1.09 G rows/s).  A variant that staged the
-// input and a 16 KB output window in shared memory was not faster (more instructions per sequence) and was
-// dropped.  Making this path pay needs intra-buffer parallelism (speculative sequence boundaries or a
-// two-pass parse/copy split): next round.
-// Every lane parses the (uniform) token stream redundantly -- the loads are warp-uniform broadcasts -- and
-// the copies are split across lanes.  A match may overlap its own output (offset < length): byte i of the
-// match is out[o - off + (i % off)], which always lies in the already written region.
-__global__ void lz4_decode_kernel(const Lz4Job* jobs, int njobs, unsigned int* error_flag) {
-  const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= njobs) return;
-  const Lz4Job j = jobs[warp];
-  const uint8_t* __restrict__ src = j.src;
-  uint8_t* dst = j.dst;
-  int64_t s = 0, o = 0;
-  bool bad = false;
-  while (s < j.src_len) {
-    const uint32_t token = src[s++];
-    int64_t lit = token >> 4;
-    if (lit == 15) { uint32_t b; do { if (s >= j.src_len) { bad = true; break; } b = src[s++]; lit += b; } while (b == 255); }
-    if (bad || s + lit > j.src_len || o + lit > j.dst_len) { bad = true; break; }
-    for (int64_t i = lane; i < lit; i += 32) dst[o + i] = src[s + i];
-    o += lit; s += lit;
-    if (s >= j.src_len) break;   // last sequence: literals only
-    if (s + 2 > j.src_len) { bad = true; break; }
-    const int64_t off = (int64_t)src[s] | ((int64_t)src[s + 1] << 8);
-    s += 2;
-    int64_t ml = token & 15;
-    if (ml == 15) { uint32_t b; do { if (s >= j.src_len) { bad = true; break; } b = src[s++]; ml += b; } while (b == 255); }
-    ml += 4;
-    if (bad || off == 0 || off > o || o + ml > j.dst_len) { bad = true; break; }
-    __syncwarp();   // the match source was written by other lanes (this or earlier sequences)
-    const uint8_t* m = dst + o - off;
-    if (off >= ml) { for (int64_t i = lane; i < ml; i += 32) dst[o + i] = m[i]; }
-    else { for (int64_t i = lane; i < ml; i += 32) dst[o + i] = m[i % off]; }
-    o += ml;
+// ---- device: one warp per buffer, 32 sequences at a time -------------------------------------------------
+// A column buffer is ONE LZ4 block (the reference compresses the whole value, CompressionUtils.scala:102-110), so
+// the unit of independent work is the buffer and the time of a launch is the serial chain of its longest buffer.
+// The first decoder here walked that chain one sequence at a time with every match source read coming back from
+// L2: ~1200 cycles per sequence, 130 ms for a 1.6 MB column of doubles (profiles/r01_lz4.txt).  This one shortens
+// the chain instead of adding warps:
+//   * phase A: all lanes parse the token stream redundantly (warp-uniform loads) and lane i keeps sequence i of a
+//     group of up to 32 -- the chain per sequence is one cached byte load, the copies are no longer part of it;
+//   * phase B: lane i copies its own sequence.  Literals have no hazards.  A match may read bytes produced by an
+//     earlier sequence of the same group, so matches run in rounds: a lane goes when its source range lies below
+//     the output position of the first sequence that is still pending (that lane always qualifies);
+//   * the most recent LZ_WIN bytes of output live in a shared-memory ring, so a round costs shared-memory
+//     latency, not L2 latency; the ring is written out with coalesced 16-byte stores after every group.  Sources
+//     farther back than the ring are read from HBM/L2 (they were flushed long before);
+//   * sequences with long literal runs or long matches end the group and are copied by the whole warp;
+//   * the parse is the serial part, so it is kept lean: while a whole group's worth of input and output remains,
+//     the input is staged in a small shared-memory ring (coalesced 16-byte loads) and a short sequence -- at most
+//     one length-extension byte each -- is parsed without per-field bounds checks (only the offset is validated);
+//     anything else takes the fully checked path that reads HBM.  (The first version of this kernel spent ~110
+//     instructions per sequence in the parse, 9/10 of its time: profiles/r01_lz4.txt.)
+// Positions below are "shifted": P = output offset + (dst & 15), so that dst_al = dst - (dst & 15) is 16-byte
+// aligned, byte P lives at dst_al[P] and in ring slot P & (LZ_WIN - 1), and ring vectors line up with HBM vectors.
+constexpr int LZ_WARPS = 4;            // warps (buffers) per CTA
+constexpr int LZ_WIN = 16384;          // ring bytes per warp (power of two)
+constexpr int LZ_MAX_LIT = 32;         // longer literal runs / matches are copied by the whole warp
+constexpr int LZ_MAX_ML = 64;
+constexpr int LZ_PIECE = 4096;         // whole-warp copies proceed in pieces of this size (ring >= 2 pieces + a group)
+constexpr uint32_t LZ_M = LZ_WIN - 1;
+constexpr int LZ_IN = 4096;            // ring of staged input bytes per warp (power of two)
+constexpr uint32_t LZ_IM = LZ_IN - 1;
+constexpr int LZ_SEQ_IN_MAX = 1 + 1 + LZ_MAX_LIT + 2 + 1;   // input bytes of a short sequence: token, <= 1 length byte each
+constexpr uint32_t LZ_GROUP_IN = 32 * LZ_SEQ_IN_MAX + 16;   // input a group of short sequences can consume (+ slack)
+constexpr uint32_t LZ_GROUP_OUT = 32 * (LZ_MAX_LIT + LZ_MAX_ML);
+
+// write ring bytes [flushed, floor16(upto)) to HBM; only the very first flush can start unaligned (the head)
+__device__ __forceinline__ void lz_flush(const uint8_t* win, uint8_t* dst_al, uint32_t& flushed, uint32_t upto, int lane) {
+  const uint32_t lim = upto & ~15u;
+  if (lim <= flushed) return;
+  if (flushed & 15u) {
+    const uint32_t head_end = (flushed + 15u) & ~15u;
+    for (uint32_t P = flushed + lane; P < head_end; P += 32) dst_al[P] = win[P & LZ_M];
+    flushed = head_end;
   }
-  if ((bad || o != j.dst_len) && lane == 0) atomicExch(error_flag, 1u);
+  const uint4* w = reinterpret_cast<const uint4*>(win);
+  uint4* d = reinterpret_cast<uint4*>(dst_al);
+  for (uint32_t v = (flushed >> 4) + lane; v < (lim >> 4); v += 32) d[v] = w[v & (LZ_WIN / 16 - 1)];
+  flushed = lim;
+}
+
+// one lane copies its own match of <= LZ_MAX_ML bytes into the ring
+__device__ __forceinline__ void lz_lane_match(uint8_t* win, const uint8_t* dst_al, uint32_t mdst, uint32_t msrc, uint32_t ml, uint32_t off, bool near) {
+  uint32_t q = 0;
+  if (off >= 8) {   // 8 source bytes never overlap the 8 bytes they produce: fetch them all, then store
+    for (; q + 8 <= ml; q += 8) {
+      uint8_t t[8];
+      if (near) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = win[(msrc + q + u) & LZ_M];
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(dst_al + msrc + q + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) win[(mdst + q + u) & LZ_M] = t[u];
+    }
+  }
+  for (; q < ml; q++) {   // tail, or a match that overlaps its own output (offset < 8): byte by byte, in order
+    const uint8_t v = near ? win[(msrc + q) & LZ_M] : __ldcg(dst_al + msrc + q);
+    win[(mdst + q) & LZ_M] = v;
+  }
+}
+
+__global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job* jobs, int njobs, unsigned int* error_flag) {
+  extern __shared__ __align__(16) uint8_t lz_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * LZ_WARPS + wib;
+  if (job >= njobs) return;
+  uint8_t* win = lz_smem + (size_t)wib * (LZ_WIN + LZ_IN);
+  uint8_t* in = win + LZ_WIN;
+  const Lz4Job j = jobs[job];
+  const unsigned FULL = 0xffffffffu;
+  if (j.src_len < 0 || j.dst_len < 0 || j.src_len > 0x7fffffff || j.dst_len > 0x7fffff00) {   // column buffers are < 2 GB
+    if (lane == 0) atomicExch(error_flag, 1u);
+    return;
+  }
+  const uint8_t* __restrict__ src = j.src;
+  const uint32_t wofs = (uint32_t)(reinterpret_cast<uintptr_t>(j.dst) & 15);
+  uint8_t* dst_al = j.dst - wofs;
+  const uint32_t n_src = (uint32_t)j.src_len, end = (uint32_t)j.dst_len + wofs;
+  uint32_t s = 0, o = wofs, flushed = wofs;
+  uint32_t in_hi = 0;   // the input ring holds src[.., in_hi) (multiple of 16), byte p in slot p & LZ_IM
+  const bool src_aligned = (reinterpret_cast<uintptr_t>(j.src) & 15) == 0;
+  bool bad = false, finished = false;
+
+  while (!finished && !bad) {
+    // ---- phase A: parse up to 32 short sequences; lane i keeps sequence i ----------------------------------
+    uint32_t my_lit_src = 0, my_lit = 0, my_mdst = 0, my_off = 0, my_ml = 0;
+    bool my_staged = false;   // this lane's literals are in the input ring
+    uint32_t b_lit_src = 0, b_lit = 0, b_off = 0, b_ml = 0;
+    bool big = false, b_last = false;
+    int n = 0;
+    // a whole group of short sequences fits in what is left of the input and the output: stage the input and
+    // parse without bounds checks
+    const bool safe = src_aligned && n_src - s >= LZ_GROUP_IN && end - o >= LZ_GROUP_OUT;
+    if (safe) {
+      if (in_hi < (s & ~15u)) in_hi = s & ~15u;
+      while (in_hi < s + LZ_GROUP_IN) {   // (the payload allocation is padded: a 16-byte load may run past n_src)
+        const uint32_t pos = in_hi + 16u * lane;
+        if (pos < n_src) *reinterpret_cast<uint4*>(in + (pos & LZ_IM)) = __ldg(reinterpret_cast<const uint4*>(src + pos));
+        in_hi += 512;
+      }
+      __syncwarp();
+    }
+    while (n < 32) {
+      if (safe) {
+        const uint32_t token = in[s & LZ_IM];
+        uint32_t q = s + 1, lit = token >> 4, ml = token & 15;
+        bool ok = true;
+        if (lit == 15) { const uint32_t e = in[q & LZ_IM]; q++; lit += e; ok = e != 255 && lit <= (uint32_t)LZ_MAX_LIT; }
+        const uint32_t lit_src = q;
+        q += lit;
+        if (ok) {
+          const uint32_t off = (uint32_t)in[q & LZ_IM] | ((uint32_t)in[(q + 1) & LZ_IM] << 8);
+          q += 2;
+          if (ml == 15) { const uint32_t e = in[q & LZ_IM]; q++; ml += e; ok = e != 255; }
+          ml += 4;
+          ok = ok && ml <= (uint32_t)LZ_MAX_ML;
+          if (ok) {
+            if (off == 0 || off > o - wofs + lit) { bad = true; break; }
+            if (lane == n) { my_lit_src = lit_src; my_lit = lit; my_mdst = o + lit; my_off = off; my_ml = ml; my_staged = true; }
+            s = q;
+            o += lit + ml;
+            n++;
+            continue;
+          }
+        }
+      }
+      if (s >= n_src) { finished = true; break; }
+      const uint32_t token = __ldg(src + s); s++;
+      uint32_t lit = token >> 4;
+      if (lit == 15) { uint32_t b; do { if (s >= n_src) { bad = true; break; } b = __ldg(src + s); s++; lit += b; } while (b == 255); }
+      if (bad || lit > n_src - s || lit > end - o) { bad = true; break; }
+      const uint32_t lit_src = s;
+      s += lit;
+      const bool last = s >= n_src;   // the block ends with a literals-only sequence
+      uint32_t off = 0, ml = 0;
+      if (!last) {
+        if (n_src - s < 2) { bad = true; break; }
+        off = (uint32_t)__ldg(src + s) | ((uint32_t)__ldg(src + s + 1) << 8);
+        s += 2;
+        ml = token & 15;
+        if (ml == 15) { uint32_t b; do { if (s >= n_src) { bad = true; break; } b = __ldg(src + s); s++; ml += b; } while (b == 255); }
+        ml += 4;
+        if (bad || off == 0 || off > o - wofs + lit || ml > end - o - lit) { bad = true; break; }
+      }
+      if (lit > LZ_MAX_LIT || ml > LZ_MAX_ML) {   // ends the group; copied by the whole warp below
+        big = true; b_lit_src = lit_src; b_lit = lit; b_off = off; b_ml = ml; b_last = last;
+        break;
+      }
+      if (lane == n) { my_lit_src = lit_src; my_lit = lit; my_mdst = o + lit; my_off = off; my_ml = ml; my_staged = false; }
+      o += lit + ml;
+      n++;
+      if (last) { finished = true; break; }
+    }
+    if (bad) break;
+
+    // ---- phase B: the group's copies -----------------------------------------------------------------------
+    if (n > 0) {
+      const uint32_t group_end = o;
+      if (lane < n) {
+        const uint32_t p0 = my_mdst - my_lit;
+        if (my_staged) { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & LZ_M] = in[(my_lit_src + k) & LZ_IM]; }
+        else { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & LZ_M] = __ldg(src + my_lit_src + k); }
+      }
+      __syncwarp();
+      bool pending = lane < n && my_ml > 0;
+      const uint32_t msrc = my_mdst - my_off;
+      const uint32_t dep_end = msrc + (my_ml < my_off ? my_ml : my_off);   // exclusive end of the bytes the match needs from others
+      const bool near = group_end - msrc <= (uint32_t)LZ_WIN;              // its source is still in the ring after this group's writes
+      for (;;) {
+        const unsigned mask = __ballot_sync(FULL, pending);
+        if (!mask) break;
+        const int k = __ffs(mask) - 1;
+        const uint32_t ready_below = __shfl_sync(FULL, my_mdst, k);   // every byte below it is final
+        if (pending && (lane == k || dep_end <= ready_below)) {
+          lz_lane_match(win, dst_al, my_mdst, msrc, my_ml, my_off, near);
+          pending = false;
+        }
+        __syncwarp();
+      }
+      lz_flush(win, dst_al, flushed, o, lane);
+    }
+    if (big) {
+      // literals, piece by piece: input -> ring -> HBM
+      for (uint32_t done = 0; done < b_lit;) {
+        const uint32_t piece = b_lit - done < (uint32_t)LZ_PIECE ? b_lit - done : (uint32_t)LZ_PIECE;
+        for (uint32_t i = lane; i < piece; i += 32) win[(o + i) & LZ_M] = __ldg(src + b_lit_src + done + i);
+        o += piece; done += piece;
+        __syncwarp();
+        lz_flush(win, dst_al, flushed, o, lane);
+      }
+      // match: byte i comes from [m0 - off, m0): i-th byte of the source for a plain match, the repeating pattern
+      // for one that overlaps its own output; bytes that left the ring were flushed and are read back from HBM
+      const uint32_t m0 = o;
+      for (uint32_t done = 0; done < b_ml;) {
+        const uint32_t piece = b_ml - done < (uint32_t)LZ_PIECE ? b_ml - done : (uint32_t)LZ_PIECE;
+        const uint32_t piece_end = o + piece;
+        if (b_off >= b_ml) {
+          for (uint32_t i = lane; i < piece; i += 32) {
+            const uint32_t p = m0 - b_off + done + i;
+            win[(o + i) & LZ_M] = piece_end - p <= (uint32_t)LZ_WIN ? win[p & LZ_M] : __ldcg(dst_al + p);
+          }
+        } else {
+          for (uint32_t i = lane; i < piece; i += 32) {
+            const uint32_t p = m0 - b_off + (done + i) % b_off;
+            win[(o + i) & LZ_M] = piece_end - p <= (uint32_t)LZ_WIN ? win[p & LZ_M] : __ldcg(dst_al + p);
+          }
+        }
+        o += piece; done += piece;
+        __syncwarp();
+        lz_flush(win, dst_al, flushed, o, lane);
+      }
+      if (b_last) finished = true;
+    }
+  }
+  // tail: the last (< 16) bytes of the ring, or everything for a tiny buffer
+  __syncwarp();
+  if (!bad && o == end) {
+    lz_flush(win, dst_al, flushed, o, lane);
+    for (uint32_t P = flushed + lane; P < end; P += 32) dst_al[P] = win[P & LZ_M];
+  } else if (lane == 0) atomicExch(error_flag, 1u);
 }
 
 int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
   if (njobs <= 0) return 0;
-  const int warps_per_block = 4;
-  const int blocks = (njobs + warps_per_block - 1) / warps_per_block;
-  lz4_decode_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(d_jobs, njobs, d_error);
+  const int blocks = (njobs + LZ_WARPS - 1) / LZ_WARPS;
+  const size_t smem = (size_t)(LZ_WIN + LZ_IN) * LZ_WARPS;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  SD_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev] = true;
+  }
+  lz4_decode_kernel<<<blocks, LZ_WARPS * 32, smem, stream>>>(d_jobs, njobs, d_error);
   SD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,6 +87,25 @@ void Arena::release() {
   reset();
 }
 
+uint8_t* PinnedArena::alloc(size_t n) {
+  n = (n + 15) & ~size_t(15);
+  if (n == 0) n = 16;
+  for (;;) {
+    if (cur_slab < slabs.size()) {
+      if (cur_off + n <= slabs[cur_slab].second) { uint8_t* p = slabs[cur_slab].first + cur_off; cur_off += n; return p; }
+      cur_slab++;
+      cur_off = 0;
+      continue;
+    }
+    const size_t sz = n > slab_bytes ? n : slab_bytes;
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, sz, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error(SD_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", sz, cudaGetErrorString(e)); return nullptr; }
+    slabs.emplace_back(reinterpret_cast<uint8_t*>(p), sz);
+  }
+}
+PinnedArena::~PinnedArena() { for (auto& s : slabs) cudaFreeHost(s.first); }
+
 // ---- little-endian host reads ----------------------------------------------------------------------
 static inline int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
 static inline uint64_t rd_u64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -397,20 +416,51 @@ static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, 
 int store_flush_lz4(sd_store* s) {
   if (s->pending_lz4.empty()) return 0;
   SD_CUDA(cudaSetDevice(s->device));
-  if (!s->d_lz4_error) { SD_CUDA(cudaMalloc(&s->d_lz4_error, 64)); }
-  SD_CUDA(cudaMemsetAsync(s->d_lz4_error, 0, 4, s->copy_stream));
+  if (!s->d_lz4_error) {
+    SD_CUDA(cudaMalloc(&s->d_lz4_error, 64));
+    SD_CUDA(cudaMemset(s->d_lz4_error, 0, 64));
+    SD_CUDA(cudaEventCreateWithFlags(&s->lz4_copied, cudaEventDisableTiming));
+    for (int k = 0; k < sd_store::LZ4_STREAMS; k++) {
+      SD_CUDA(cudaStreamCreateWithFlags(&s->lz4_streams[k], cudaStreamNonBlocking));
+      SD_CUDA(cudaEventCreateWithFlags(&s->lz4_done[k], cudaEventDisableTiming));
+    }
+  }
   const size_t nbytes = s->pending_lz4.size() * sizeof(Lz4Job);
   uint8_t* d_jobs = s->lz4_stage.alloc(nbytes + 16, 16);
   if (!d_jobs) return SD_ERR_CUDA;
+  // (pageable source: the runtime stages it before returning, so the vector may be cleared right away)
   SD_CUDA(cudaMemcpyAsync(d_jobs, s->pending_lz4.data(), nbytes, cudaMemcpyHostToDevice, s->copy_stream));
-  int rc = lz4_launch(s->copy_stream, reinterpret_cast<const Lz4Job*>(d_jobs), (int)s->pending_lz4.size(), s->d_lz4_error);
+  SD_CUDA(cudaEventRecord(s->lz4_copied, s->copy_stream));   // the compressed payloads went over this stream too
+  const int k = s->lz4_next++ % sd_store::LZ4_STREAMS;
+  SD_CUDA(cudaStreamWaitEvent(s->lz4_streams[k], s->lz4_copied, 0));
+  int rc = lz4_launch(s->lz4_streams[k], reinterpret_cast<const Lz4Job*>(d_jobs), (int)s->pending_lz4.size(), s->d_lz4_error);
   if (rc) return rc;
-  unsigned int err = 0;
-  SD_CUDA(cudaMemcpyAsync(&err, s->d_lz4_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
-  SD_CUDA(cudaStreamSynchronize(s->copy_stream));
+  SD_CUDA(cudaEventRecord(s->lz4_done[k], s->lz4_streams[k]));
+  s->lz4_used[k] = true;
   s->pending_lz4.clear();
-  s->lz4_stage.reset();
-  if (err) return set_error(SD_ERR_INVALID, "corrupt LZ4 payload in a column buffer (device decode failed)");
+  return 0;
+}
+
+int store_lz4_order(sd_store* s, cudaStream_t stream) {
+  for (int k = 0; k < sd_store::LZ4_STREAMS; k++)
+    if (s->lz4_used[k]) SD_CUDA(cudaStreamWaitEvent(stream, s->lz4_done[k], 0));
+  return 0;
+}
+
+int store_lz4_check(sd_store* s) {
+  bool any = false;
+  for (int k = 0; k < sd_store::LZ4_STREAMS; k++) any = any || s->lz4_used[k];
+  if (!any) return 0;
+  SD_CUDA(cudaSetDevice(s->device));
+  for (int k = 0; k < sd_store::LZ4_STREAMS; k++)
+    if (s->lz4_used[k]) { SD_CUDA(cudaStreamSynchronize(s->lz4_streams[k])); s->lz4_used[k] = false; }
+  unsigned int err = 0;
+  SD_CUDA(cudaMemcpy(&err, s->d_lz4_error, 4, cudaMemcpyDeviceToHost));
+  if (s->pending_lz4.empty()) s->lz4_stage.reset();   // nothing refers to the staged payloads any more
+  if (err) {
+    SD_CUDA(cudaMemset(s->d_lz4_error, 0, 4));
+    return set_error(SD_ERR_INVALID, "corrupt LZ4 payload in a column buffer (device decode failed)");
+  }
   return 0;
 }
 
@@ -551,6 +601,11 @@ void sd_store_destroy(sd_store* s) {
   cudaSetDevice(s->device);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->d_lz4_error) cudaFree(s->d_lz4_error);
+  if (s->lz4_copied) cudaEventDestroy(s->lz4_copied);
+  for (int k = 0; k < sd_store::LZ4_STREAMS; k++) {
+    if (s->lz4_streams[k]) { cudaStreamSynchronize(s->lz4_streams[k]); cudaStreamDestroy(s->lz4_streams[k]); }
+    if (s->lz4_done[k]) cudaEventDestroy(s->lz4_done[k]);
+  }
   if (s->copies_done) cudaEventDestroy(s->copies_done);
   delete s;
 }
@@ -570,7 +625,7 @@ int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, vo
   if (table_col < 0 || table_col >= (int)b.cols.size() || !b.cols[table_col].present || !b.cols[table_col].dev_base)
     return sd::set_error(SD_ERR_INVALID, "column %d not resident", table_col);
   const sd::StoredCol& c = b.cols[table_col];
-  { int rc = sd::store_flush_lz4(s); if (rc) return rc; }
+  { int rc = sd::store_flush_lz4(s); if (rc) return rc; rc = sd::store_lz4_check(s); if (rc) return rc; }
   *out_len = c.len;
   if (cap < c.len) return sd::set_error(SD_ERR_OVERFLOW, "buffer too small");
   SD_CUDA(cudaSetDevice(s->device));

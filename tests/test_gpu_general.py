@@ -278,6 +278,43 @@ def test_lz4_compressed_buffers_are_expanded_on_the_device(gpu_api, batches):
     assert gp.metrics()["h2dBytes"] < gplain.metrics()["h2dBytes"]
 
 
+def test_lz4_device_decoder_is_byte_exact_on_hard_blocks(gpu_api):
+    """The device LZ4 decoder against liblz4's own output on blocks that stress every copy path: runs (matches that
+    overlap their output at offsets 1..9), long literal runs, long matches, matches farther back than the decoder's
+    shared-memory ring, dense short sequences, a tiny buffer, several buffers per launch."""
+    import numpy as np
+    import struct
+    from snappydata_b200.column_format import compress_lz4, decompress
+    rng = np.random.default_rng(5)
+    a30 = rng.bytes(30_000)
+    bodies = [
+        bytes(40_000),                                                             # one huge overlapping match (offset 1)
+        b"".join(bytes([i + 1]) * (i + 1) * 700 for i in range(9)),                # runs of every small period
+        b"".join((b"abcdefghi"[:k] * 3000)[:9000] for k in range(1, 10)),          # periods 1..9
+        rng.bytes(50_000),                                                         # incompressible: one long literal run
+        a30 + rng.bytes(25_000) + a30 + rng.bytes(100) + a30[5_000:9_000],         # long matches ~55 KB back (beyond the ring)
+        rng.integers(1, 51, 60_000).astype(np.float64).tobytes(),                  # dense 8-byte sequences, near sources
+        rng.integers(0, 3, 100_000).astype(np.int16).tobytes(),                    # short sequences, deep dependency chains
+        rng.integers(8000, 10_500, 50_000).astype(np.int32).tobytes(),
+        b"".join(rng.bytes(int(n)) + bytes(int(m)) for n, m in zip(rng.integers(0, 80, 400), rng.integers(4, 300, 400))),
+        rng.bytes(13) + bytes(27),                                                  # tiny
+    ]
+    cols = []
+    for body in bodies:
+        body = body + bytes(-len(body) % 8)
+        plain = struct.pack("<ii", 0, 0) + body                                     # Uncompressed LONG column, no nulls
+        env = compress_lz4(plain, force=True)
+        assert decompress(env) == plain
+        cols.append((plain, env, len(body) // 8))
+    schema = [(T.LONG, False)]
+    store = capi.Store(gpu_api, schema)
+    for i, (plain, env, n) in enumerate(cols):
+        store.put(ColumnBatch(num_rows=n, columns=[env], batch_id=i))
+    for i, (plain, env, n) in enumerate(cols):
+        got = store.get_buffer(i, 0)
+        assert got == plain, f"block {i}: first difference at byte {next((k for k in range(len(plain)) if got[k] != plain[k]), -1)}"
+
+
 def test_lz4_lineitem_q1_q6(gpu_api):
     from snappydata_b200 import lineitem, plan as P
     plain = lineitem.gen_table(260_001, 65_000, seed=21)

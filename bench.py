@@ -370,11 +370,16 @@ class QueryRun:
         p = self.e2e_plan
         p.reset().set_literals(self.lits)
         sub, h = self.api.batch_submit, p.h
+        t0 = time.perf_counter()
         for mb in self.marshalled:
             rc = sub(h, C.byref(mb.c))
             if rc:
                 self.api.check(rc)
+        t1 = time.perf_counter()
         raw = p.finish_raw()
+        if os.environ.get("BENCH_DEBUG"):   # where a step's wall time goes: queueing on the host vs waiting for the device
+            print(f"[e2e step] submit loop {1e3 * (t1 - t0):.1f} ms, finish {1e3 * (time.perf_counter() - t1):.1f} ms, "
+                  f"{len(self.marshalled)} batches", file=sys.stderr)
         self.e2e_launches = p.metrics()["kernelLaunches"]
         return self.exchange_and_merge(raw)
 

@@ -1107,7 +1107,8 @@ int sd_batch_submit(sd_plan* p, const sd_batch* b) {
   p->pending_bytes += p->priv->h2d_bytes - before;
   // (compressed inputs: one expansion launch per flush, as long as its longest buffer; the launches of successive
   // flushes overlap on their own streams, so the same flush size serves both)
-  const int64_t threshold = int64_t(256) << 20;
+  int64_t threshold = int64_t(256) << 20;
+  if (const char* e = getenv("SD_TUNE_FLUSH_MB")) { const long v = atol(e); if (v >= 1 && v <= 65536) threshold = int64_t(v) << 20; }
   if (p->pending_bytes >= threshold) return flush_pending(p);
   return 0;
 }

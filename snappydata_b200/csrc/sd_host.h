@@ -150,6 +150,7 @@ struct sd_store {
   bool lz4_used[LZ4_STREAMS] = {false, false, false, false};
   cudaEvent_t lz4_copied = nullptr;
   int lz4_next = 0;
+  sd::PinnedArena lz4_jobs_host;   // page-locked copies of the job lists (a pageable source would stall the caller per flush)
 };
 
 namespace sd {

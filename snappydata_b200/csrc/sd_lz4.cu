@@ -61,17 +61,24 @@ int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int
 //     instructions per sequence in the parse, 9/10 of its time: profiles/r01_lz4.txt.)
 // Positions below are "shifted": P = output offset + (dst & 15), so that dst_al = dst - (dst & 15) is 16-byte
 // aligned, byte P lives at dst_al[P] and in ring slot P & (LZ_WIN - 1), and ring vectors line up with HBM vectors.
-constexpr int LZ_WARPS = 4;            // warps (buffers) per CTA
-constexpr int LZ_WIN = 16384;          // ring bytes per warp (power of two)
+// One warp per CTA and ~10 KB of shared memory per buffer: the launch is a latency chain per buffer, so what counts
+// is how many buffers are resident at once (22 per SM here) -- with 4 warps and 80 KB per CTA only 148..296 CTAs
+// were resident and the expansions of one SF-100 pass could not keep up with PCIe (profiles/r01_lz4.txt).
+constexpr int LZ_WARPS = 1;            // warps (buffers) per CTA
+constexpr int LZ_WIN = 8192;           // ring bytes per warp (power of two)
 constexpr int LZ_MAX_LIT = 32;         // longer literal runs / matches are copied by the whole warp
 constexpr int LZ_MAX_ML = 64;
-constexpr int LZ_PIECE = 4096;         // whole-warp copies proceed in pieces of this size (ring >= 2 pieces + a group)
+constexpr int LZ_PIECE = 2048;         // whole-warp copies proceed in pieces of this size (ring >= 2 pieces + a group)
 constexpr uint32_t LZ_M = LZ_WIN - 1;
-constexpr int LZ_IN = 4096;            // ring of staged input bytes per warp (power of two)
+constexpr int LZ_IN = 2048;            // ring of staged input bytes per warp (power of two)
 constexpr uint32_t LZ_IM = LZ_IN - 1;
 constexpr int LZ_SEQ_IN_MAX = 1 + 1 + LZ_MAX_LIT + 2 + 1;   // input bytes of a short sequence: token, <= 1 length byte each
 constexpr uint32_t LZ_GROUP_IN = 32 * LZ_SEQ_IN_MAX + 16;   // input a group of short sequences can consume (+ slack)
 constexpr uint32_t LZ_GROUP_OUT = 32 * (LZ_MAX_LIT + LZ_MAX_ML);
+// the output ring must hold a piece being flushed, the piece (or group) being written and the flush's 16-byte slack;
+// the input ring a group's input plus the 512-byte staging step
+static_assert(2 * LZ_PIECE + LZ_GROUP_OUT + 16 <= LZ_WIN && 2 * LZ_GROUP_OUT + 16 <= LZ_WIN, "output ring too small");
+static_assert(LZ_GROUP_IN + 512 <= LZ_IN, "input ring too small");
 
 // write ring bytes [flushed, floor16(upto)) to HBM; only the very first flush can start unaligned (the head)
 __device__ __forceinline__ void lz_flush(const uint8_t* win, uint8_t* dst_al, uint32_t& flushed, uint32_t upto, int lane) {
@@ -281,6 +288,8 @@ int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned in
   SD_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
     SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // as many resident buffers per SM as the shared memory allows
+    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
   lz4_decode_kernel<<<blocks, LZ_WARPS * 32, smem, stream>>>(d_jobs, njobs, d_error);

@@ -428,10 +428,14 @@ int store_flush_lz4(sd_store* s) {
   const size_t nbytes = s->pending_lz4.size() * sizeof(Lz4Job);
   uint8_t* d_jobs = s->lz4_stage.alloc(nbytes + 16, 16);
   if (!d_jobs) return SD_ERR_CUDA;
-  // (pageable source: the runtime stages it before returning, so the vector may be cleared right away)
-  SD_CUDA(cudaMemcpyAsync(d_jobs, s->pending_lz4.data(), nbytes, cudaMemcpyHostToDevice, s->copy_stream));
+  uint8_t* h_jobs = s->lz4_jobs_host.alloc(nbytes);
+  if (!h_jobs) return SD_ERR_CUDA;
+  memcpy(h_jobs, s->pending_lz4.data(), nbytes);
+  SD_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, nbytes, cudaMemcpyHostToDevice, s->copy_stream));
   SD_CUDA(cudaEventRecord(s->lz4_copied, s->copy_stream));   // the compressed payloads went over this stream too
-  const int k = s->lz4_next++ % sd_store::LZ4_STREAMS;
+  int nstreams = sd_store::LZ4_STREAMS;
+  if (const char* e = getenv("SD_TUNE_LZ4_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= sd_store::LZ4_STREAMS) nstreams = v; }
+  const int k = s->lz4_next++ % nstreams;
   SD_CUDA(cudaStreamWaitEvent(s->lz4_streams[k], s->lz4_copied, 0));
   int rc = lz4_launch(s->lz4_streams[k], reinterpret_cast<const Lz4Job*>(d_jobs), (int)s->pending_lz4.size(), s->d_lz4_error);
   if (rc) return rc;
@@ -456,7 +460,7 @@ int store_lz4_check(sd_store* s) {
     if (s->lz4_used[k]) { SD_CUDA(cudaStreamSynchronize(s->lz4_streams[k])); s->lz4_used[k] = false; }
   unsigned int err = 0;
   SD_CUDA(cudaMemcpy(&err, s->d_lz4_error, 4, cudaMemcpyDeviceToHost));
-  if (s->pending_lz4.empty()) s->lz4_stage.reset();   // nothing refers to the staged payloads any more
+  if (s->pending_lz4.empty()) { s->lz4_stage.reset(); s->lz4_jobs_host.reset(); }   // nothing refers to the staged payloads any more
   if (err) {
     SD_CUDA(cudaMemset(s->d_lz4_error, 0, 4));
     return set_error(SD_ERR_INVALID, "corrupt LZ4 payload in a column buffer (device decode failed)");

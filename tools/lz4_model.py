@@ -1,0 +1,161 @@
+"""Executable model of the device LZ4 decoder (snappydata_b200/csrc/sd_lz4.cu), used to check its ring / flush /
+dependency-round logic on the host: the same group parse, per-lane copies in rounds, shared-memory output ring with
+"shifted" positions, 16-byte flushes and near (ring) / far (HBM) source reads -- with assertions where the kernel
+relies on an invariant (a ring slot still holds the byte it is read for; a far byte has been flushed; a match
+never reads a byte that a pending sequence has yet to produce).  The constants are read from the .cu file, so
+changing LZ_WIN / LZ_PIECE / LZ_MAX_* there and running this (or tests/test_lz4_model.py) re-checks the invariants.
+
+    python tools/lz4_model.py          # decodes a set of adversarial blocks at several output alignments
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from snappydata_b200.column_format import compress_lz4  # noqa: E402
+
+
+def kernel_constants():
+    text = open(os.path.join(ROOT, "snappydata_b200", "csrc", "sd_lz4.cu")).read()
+    out = {}
+    for name in ("LZ_WIN", "LZ_MAX_LIT", "LZ_MAX_ML", "LZ_PIECE"):
+        out[name] = int(re.search(r"constexpr int %s = (\d+);" % name, text).group(1))
+    return out
+
+
+K = kernel_constants()
+WIN, MAX_LIT, MAX_ML, PIECE = K["LZ_WIN"], K["LZ_MAX_LIT"], K["LZ_MAX_ML"], K["LZ_PIECE"]
+M = WIN - 1
+
+def decode(src, n_out, wofs):
+    n_src=len(src); end=n_out+wofs
+    dst_al=bytearray(end+64); written=bytearray(end+64)   # HBM
+    win=bytearray(WIN); ring_pos=[-1]*WIN                  # which P each slot holds
+    st=dict(s=0,o=wofs,flushed=wofs)
+    def wr(P,v): win[P&M]=v; ring_pos[P&M]=P
+    def rr(P):
+        assert ring_pos[P&M]==P, f"ring slot for {P} holds {ring_pos[P&M]}"
+        return win[P&M]
+    def far(P):
+        assert written[P], f"far read of unflushed byte {P} (flushed {st['flushed']})"
+        return dst_al[P]
+    def flush(upto):
+        lim=upto&~15
+        if lim<=st['flushed']: return
+        if st['flushed']&15:
+            he=(st['flushed']+15)&~15
+            for P in range(st['flushed'],he): dst_al[P]=rr(P); written[P]=1
+            st['flushed']=he
+        for v in range(st['flushed']>>4, lim>>4):
+            for u in range(16): P=v*16+u; dst_al[P]=rr(P); written[P]=1
+        st['flushed']=lim
+    finished=False
+    while not finished:
+        recs=[]; big=None
+        s=st['s']; o=st['o']
+        while len(recs)<32:
+            if s>=n_src: finished=True; break
+            tok=src[s]; s+=1; lit=tok>>4
+            if lit==15:
+                while True:
+                    b=src[s]; s+=1; lit+=b
+                    if b!=255: break
+            assert lit<=n_src-s and lit<=end-o
+            lit_src=s; s+=lit; last=s>=n_src; off=ml=0
+            if not last:
+                off=src[s]|(src[s+1]<<8); s+=2; ml=tok&15
+                if ml==15:
+                    while True:
+                        b=src[s]; s+=1; ml+=b
+                        if b!=255: break
+                ml+=4
+                assert off!=0 and off<=o-wofs+lit and ml<=end-o-lit
+            if lit>MAX_LIT or ml>MAX_ML: big=(lit_src,lit,off,ml,last); break
+            recs.append((lit_src,lit,o+lit,off,ml)); o+=lit+ml
+            if last: finished=True; break
+        st['s']=s; st['o']=o
+        n=len(recs)
+        if n:
+            group_end=o
+            for (lit_src,lit,mdst,off,ml) in recs:
+                for k in range(lit): wr(mdst-lit+k, src[lit_src+k])
+            pending=[r[4]>0 for r in recs]
+            while any(pending):
+                k=pending.index(True); W=recs[k][2]
+                writes=[]
+                for i,(lit_src,lit,mdst,off,ml) in enumerate(recs):
+                    if not pending[i]: continue
+                    msrc=mdst-off; dep_end=msrc+min(ml,off); near=group_end-msrc<=WIN
+                    if i==k or dep_end<=W:
+                        own={}
+                        for q in range(ml):
+                            P=msrc+q
+                            if P in own: v=own[P]
+                            else:
+                                if near:
+                                    v=rr(P); assert P<W, f"near read of byte {P} that a pending sequence produces (ready_below {W})"
+                                else: v=far(P)
+                            own[mdst+q]=v
+                        writes.append(own); pending[i]=False
+                for own in writes:
+                    for P,v in own.items(): wr(P,v)
+            flush(o)
+        if big:
+            lit_src,lit,off,ml,last=big
+            done=0
+            while done<lit:
+                piece=min(PIECE,lit-done)
+                for i in range(piece): wr(o+i, src[lit_src+done+i])
+                o+=piece; done+=piece; flush(o)
+            m0=o; done=0
+            while done<ml:
+                piece=min(PIECE,ml-done); piece_end=o+piece
+                vals=[]
+                for i in range(piece):
+                    P=m0-off+done+i if off>=ml else m0-off+(done+i)%off
+                    assert P<o
+                    vals.append(rr(P) if piece_end-P<=WIN else far(P))
+                for i,v in enumerate(vals): wr(o+i,v)
+                o+=piece; done+=piece; flush(o)
+            st['o']=o
+            if last: finished=True
+    assert st['o']==end
+    flush(st['o'])
+    for P in range(st['flushed'],end): dst_al[P]=rr(P); written[P]=1
+    assert all(written[wofs:end])
+    return bytes(dst_al[wofs:end])
+
+
+def blocks(rng, scale=1):
+    a30 = rng.bytes(30_000)
+    return [
+        bytes(40_000 // scale),
+        b"".join(bytes([i + 1]) * (i + 1) * (700 // scale) for i in range(9)),
+        b"".join((b"abcdefghi"[:k] * 3000)[:9000 // scale] for k in range(1, 10)),
+        rng.bytes(50_000 // scale),
+        a30 + rng.bytes(25_000) + a30 + rng.bytes(100) + a30[5_000:9_000],
+        rng.integers(1, 51, 20_000 // scale).astype(np.float64).tobytes(),
+        rng.integers(0, 3, 30_000 // scale).astype(np.int16).tobytes(),
+        rng.integers(8000, 10_500, 20_000 // scale).astype(np.int32).tobytes(),
+        b"".join(rng.bytes(int(n)) + bytes(int(m)) for n, m in zip(rng.integers(0, 80, 400 // scale), rng.integers(4, 300, 400 // scale))),
+        rng.bytes(13) + bytes(27),
+        b"xy",
+    ]
+
+
+def check(scale=1, alignments=(0, 8, 5, 15)):
+    rng = np.random.default_rng(5)
+    for bi, b in enumerate(blocks(rng, scale)):
+        env = compress_lz4(b, force=True)
+        for wofs in alignments:
+            assert decode(env[8:], len(b), wofs) == b, (bi, wofs)
+        yield bi, len(b), len(env)
+
+
+if __name__ == "__main__":
+    print("kernel constants", K)
+    for bi, n, c in check():
+        print("ok block", bi, n, "->", c, "bytes")

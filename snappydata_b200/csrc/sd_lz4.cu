@@ -9,6 +9,7 @@
 //
 // LZ4 block format: sequences of [token][literal length ext*][literals][offset:2][match length ext*];
 // token = (literal length << 4) | (match length - 4); the last sequence ends after its literals.
+#include <cstdlib>
 #include <cstring>
 
 #include "sd_host.h"
@@ -50,7 +51,7 @@ int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int
 //   * phase B: lane i copies its own sequence.  Literals have no hazards.  A match may read bytes produced by an
 //     earlier sequence of the same group, so matches run in rounds: a lane goes when its source range lies below
 //     the output position of the first sequence that is still pending (that lane always qualifies);
-//   * the most recent LZ_WIN bytes of output live in a shared-memory ring, so a round costs shared-memory
+//   * the most recent CFG::WIN bytes of output live in a shared-memory ring, so a round costs shared-memory
 //     latency, not L2 latency; the ring is written out with coalesced 16-byte stores after every group.  Sources
 //     farther back than the ring are read from HBM/L2 (they were flushed long before);
 //   * sequences with long literal runs or long matches end the group and are copied by the whole warp;
@@ -60,42 +61,54 @@ int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int
 //     anything else takes the fully checked path that reads HBM.  (The first version of this kernel spent ~110
 //     instructions per sequence in the parse, 9/10 of its time: profiles/r01_lz4.txt.)
 // Positions below are "shifted": P = output offset + (dst & 15), so that dst_al = dst - (dst & 15) is 16-byte
-// aligned, byte P lives at dst_al[P] and in ring slot P & (LZ_WIN - 1), and ring vectors line up with HBM vectors.
-// One warp per CTA and ~10 KB of shared memory per buffer: the launch is a latency chain per buffer, so what counts
-// is how many buffers are resident at once (22 per SM here) -- with 4 warps and 80 KB per CTA only 148..296 CTAs
-// were resident and the expansions of one SF-100 pass could not keep up with PCIe (profiles/r01_lz4.txt).
-constexpr int LZ_WARPS = 1;            // warps (buffers) per CTA
-constexpr int LZ_WIN = 8192;           // ring bytes per warp (power of two)
+// aligned, byte P lives at dst_al[P] and in ring slot P & (CFG::WIN - 1), and ring vectors line up with HBM vectors.
 constexpr int LZ_MAX_LIT = 32;         // longer literal runs / matches are copied by the whole warp
 constexpr int LZ_MAX_ML = 64;
-constexpr int LZ_PIECE = 2048;         // whole-warp copies proceed in pieces of this size (ring >= 2 pieces + a group)
-constexpr uint32_t LZ_M = LZ_WIN - 1;
-constexpr int LZ_IN = 2048;            // ring of staged input bytes per warp (power of two)
-constexpr uint32_t LZ_IM = LZ_IN - 1;
 constexpr int LZ_SEQ_IN_MAX = 1 + 1 + LZ_MAX_LIT + 2 + 1;   // input bytes of a short sequence: token, <= 1 length byte each
 constexpr uint32_t LZ_GROUP_IN = 32 * LZ_SEQ_IN_MAX + 16;   // input a group of short sequences can consume (+ slack)
 constexpr uint32_t LZ_GROUP_OUT = 32 * (LZ_MAX_LIT + LZ_MAX_ML);
-// the output ring must hold a piece being flushed, the piece (or group) being written and the flush's 16-byte slack;
-// the input ring a group's input plus the 512-byte staging step
-static_assert(2 * LZ_PIECE + LZ_GROUP_OUT + 16 <= LZ_WIN && 2 * LZ_GROUP_OUT + 16 <= LZ_WIN, "output ring too small");
-static_assert(LZ_GROUP_IN + 512 <= LZ_IN, "input ring too small");
+
+// Shape of the kernel: warps (= buffers) per CTA, output ring, input ring, piece size of whole-warp copies.
+template <int WARPS_, int WIN_, int IN_, int PIECE_>
+struct LzCfg {
+  static constexpr int WARPS = WARPS_;
+  static constexpr int WIN = WIN_;         // output ring bytes per warp (power of two)
+  static constexpr int IN = IN_;           // ring of staged input bytes per warp (power of two)
+  static constexpr int PIECE = PIECE_;     // whole-warp copies proceed in pieces of this size
+  static constexpr uint32_t M = WIN_ - 1, IM = IN_ - 1;
+  static constexpr size_t SMEM = (size_t)(WIN_ + IN_) * WARPS_;
+  // the output ring must hold a piece being flushed, the piece (or group) being written and the flush's 16-byte slack;
+  // the input ring a group's input plus the 512-byte staging step
+  static_assert((WIN_ & (WIN_ - 1)) == 0 && (IN_ & (IN_ - 1)) == 0, "rings are powers of two");
+  static_assert(2 * PIECE_ + LZ_GROUP_OUT + 16 <= WIN_ && 2 * LZ_GROUP_OUT + 16 <= WIN_, "output ring too small");
+  static_assert(LZ_GROUP_IN + 512 <= IN_, "input ring too small");
+};
+// The default is the shape every measurement and sanitizer run of round 1 was taken with (profiles/r01_lz4.txt).
+// LzDense trades ring size for residency: the launch is a latency chain per buffer, so the aggregate expansion rate is
+// (resident buffers) x (bytes per chain-time); with 1 warp and 10 KB per CTA 20 buffers fit an SM instead of 8.  It is
+// selected with SD_TUNE_LZ4_DENSE=1 and has NOT been run on hardware yet (the round's GPU budget ended first); its
+// ring invariants are checked by tools/lz4_model.py.
+typedef LzCfg<4, 16384, 4096, 4096> LzDefault;
+typedef LzCfg<1, 8192, 2048, 2048> LzDense;
 
 // write ring bytes [flushed, floor16(upto)) to HBM; only the very first flush can start unaligned (the head)
+template <class CFG>
 __device__ __forceinline__ void lz_flush(const uint8_t* win, uint8_t* dst_al, uint32_t& flushed, uint32_t upto, int lane) {
   const uint32_t lim = upto & ~15u;
   if (lim <= flushed) return;
   if (flushed & 15u) {
     const uint32_t head_end = (flushed + 15u) & ~15u;
-    for (uint32_t P = flushed + lane; P < head_end; P += 32) dst_al[P] = win[P & LZ_M];
+    for (uint32_t P = flushed + lane; P < head_end; P += 32) dst_al[P] = win[P & CFG::M];
     flushed = head_end;
   }
   const uint4* w = reinterpret_cast<const uint4*>(win);
   uint4* d = reinterpret_cast<uint4*>(dst_al);
-  for (uint32_t v = (flushed >> 4) + lane; v < (lim >> 4); v += 32) d[v] = w[v & (LZ_WIN / 16 - 1)];
+  for (uint32_t v = (flushed >> 4) + lane; v < (lim >> 4); v += 32) d[v] = w[v & (CFG::WIN / 16 - 1)];
   flushed = lim;
 }
 
 // one lane copies its own match of <= LZ_MAX_ML bytes into the ring
+template <class CFG>
 __device__ __forceinline__ void lz_lane_match(uint8_t* win, const uint8_t* dst_al, uint32_t mdst, uint32_t msrc, uint32_t ml, uint32_t off, bool near) {
   uint32_t q = 0;
   if (off >= 8) {   // 8 source bytes never overlap the 8 bytes they produce: fetch them all, then store
@@ -103,28 +116,29 @@ __device__ __forceinline__ void lz_lane_match(uint8_t* win, const uint8_t* dst_a
       uint8_t t[8];
       if (near) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = win[(msrc + q + u) & LZ_M];
+        for (int u = 0; u < 8; u++) t[u] = win[(msrc + q + u) & CFG::M];
       } else {
 #pragma unroll
         for (int u = 0; u < 8; u++) t[u] = __ldcg(dst_al + msrc + q + u);
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) win[(mdst + q + u) & LZ_M] = t[u];
+      for (int u = 0; u < 8; u++) win[(mdst + q + u) & CFG::M] = t[u];
     }
   }
   for (; q < ml; q++) {   // tail, or a match that overlaps its own output (offset < 8): byte by byte, in order
-    const uint8_t v = near ? win[(msrc + q) & LZ_M] : __ldcg(dst_al + msrc + q);
-    win[(mdst + q) & LZ_M] = v;
+    const uint8_t v = near ? win[(msrc + q) & CFG::M] : __ldcg(dst_al + msrc + q);
+    win[(mdst + q) & CFG::M] = v;
   }
 }
 
-__global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job* jobs, int njobs, unsigned int* error_flag) {
+template <class CFG>
+__global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Job* jobs, int njobs, unsigned int* error_flag) {
   extern __shared__ __align__(16) uint8_t lz_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.x * LZ_WARPS + wib;
+  const int job = blockIdx.x * CFG::WARPS + wib;
   if (job >= njobs) return;
-  uint8_t* win = lz_smem + (size_t)wib * (LZ_WIN + LZ_IN);
-  uint8_t* in = win + LZ_WIN;
+  uint8_t* win = lz_smem + (size_t)wib * (CFG::WIN + CFG::IN);
+  uint8_t* in = win + CFG::WIN;
   const Lz4Job j = jobs[job];
   const unsigned FULL = 0xffffffffu;
   if (j.src_len < 0 || j.dst_len < 0 || j.src_len > 0x7fffffff || j.dst_len > 0x7fffff00) {   // column buffers are < 2 GB
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job*
   uint8_t* dst_al = j.dst - wofs;
   const uint32_t n_src = (uint32_t)j.src_len, end = (uint32_t)j.dst_len + wofs;
   uint32_t s = 0, o = wofs, flushed = wofs;
-  uint32_t in_hi = 0;   // the input ring holds src[.., in_hi) (multiple of 16), byte p in slot p & LZ_IM
+  uint32_t in_hi = 0;   // the input ring holds src[.., in_hi) (multiple of 16), byte p in slot p & CFG::IM
   const bool src_aligned = (reinterpret_cast<uintptr_t>(j.src) & 15) == 0;
   bool bad = false, finished = false;
 
@@ -154,23 +168,23 @@ __global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job*
       if (in_hi < (s & ~15u)) in_hi = s & ~15u;
       while (in_hi < s + LZ_GROUP_IN) {   // (the payload allocation is padded: a 16-byte load may run past n_src)
         const uint32_t pos = in_hi + 16u * lane;
-        if (pos < n_src) *reinterpret_cast<uint4*>(in + (pos & LZ_IM)) = __ldg(reinterpret_cast<const uint4*>(src + pos));
+        if (pos < n_src) *reinterpret_cast<uint4*>(in + (pos & CFG::IM)) = __ldg(reinterpret_cast<const uint4*>(src + pos));
         in_hi += 512;
       }
       __syncwarp();
     }
     while (n < 32) {
       if (safe) {
-        const uint32_t token = in[s & LZ_IM];
+        const uint32_t token = in[s & CFG::IM];
         uint32_t q = s + 1, lit = token >> 4, ml = token & 15;
         bool ok = true;
-        if (lit == 15) { const uint32_t e = in[q & LZ_IM]; q++; lit += e; ok = e != 255 && lit <= (uint32_t)LZ_MAX_LIT; }
+        if (lit == 15) { const uint32_t e = in[q & CFG::IM]; q++; lit += e; ok = e != 255 && lit <= (uint32_t)LZ_MAX_LIT; }
         const uint32_t lit_src = q;
         q += lit;
         if (ok) {
-          const uint32_t off = (uint32_t)in[q & LZ_IM] | ((uint32_t)in[(q + 1) & LZ_IM] << 8);
+          const uint32_t off = (uint32_t)in[q & CFG::IM] | ((uint32_t)in[(q + 1) & CFG::IM] << 8);
           q += 2;
-          if (ml == 15) { const uint32_t e = in[q & LZ_IM]; q++; ml += e; ok = e != 255; }
+          if (ml == 15) { const uint32_t e = in[q & CFG::IM]; q++; ml += e; ok = e != 255; }
           ml += 4;
           ok = ok && ml <= (uint32_t)LZ_MAX_ML;
           if (ok) {
@@ -217,56 +231,56 @@ __global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job*
       const uint32_t group_end = o;
       if (lane < n) {
         const uint32_t p0 = my_mdst - my_lit;
-        if (my_staged) { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & LZ_M] = in[(my_lit_src + k) & LZ_IM]; }
-        else { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & LZ_M] = __ldg(src + my_lit_src + k); }
+        if (my_staged) { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & CFG::M] = in[(my_lit_src + k) & CFG::IM]; }
+        else { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & CFG::M] = __ldg(src + my_lit_src + k); }
       }
       __syncwarp();
       bool pending = lane < n && my_ml > 0;
       const uint32_t msrc = my_mdst - my_off;
       const uint32_t dep_end = msrc + (my_ml < my_off ? my_ml : my_off);   // exclusive end of the bytes the match needs from others
-      const bool near = group_end - msrc <= (uint32_t)LZ_WIN;              // its source is still in the ring after this group's writes
+      const bool near = group_end - msrc <= (uint32_t)CFG::WIN;              // its source is still in the ring after this group's writes
       for (;;) {
         const unsigned mask = __ballot_sync(FULL, pending);
         if (!mask) break;
         const int k = __ffs(mask) - 1;
         const uint32_t ready_below = __shfl_sync(FULL, my_mdst, k);   // every byte below it is final
         if (pending && (lane == k || dep_end <= ready_below)) {
-          lz_lane_match(win, dst_al, my_mdst, msrc, my_ml, my_off, near);
+          lz_lane_match<CFG>(win, dst_al, my_mdst, msrc, my_ml, my_off, near);
           pending = false;
         }
         __syncwarp();
       }
-      lz_flush(win, dst_al, flushed, o, lane);
+      lz_flush<CFG>(win, dst_al, flushed, o, lane);
     }
     if (big) {
       // literals, piece by piece: input -> ring -> HBM
       for (uint32_t done = 0; done < b_lit;) {
-        const uint32_t piece = b_lit - done < (uint32_t)LZ_PIECE ? b_lit - done : (uint32_t)LZ_PIECE;
-        for (uint32_t i = lane; i < piece; i += 32) win[(o + i) & LZ_M] = __ldg(src + b_lit_src + done + i);
+        const uint32_t piece = b_lit - done < (uint32_t)CFG::PIECE ? b_lit - done : (uint32_t)CFG::PIECE;
+        for (uint32_t i = lane; i < piece; i += 32) win[(o + i) & CFG::M] = __ldg(src + b_lit_src + done + i);
         o += piece; done += piece;
         __syncwarp();
-        lz_flush(win, dst_al, flushed, o, lane);
+        lz_flush<CFG>(win, dst_al, flushed, o, lane);
       }
       // match: byte i comes from [m0 - off, m0): i-th byte of the source for a plain match, the repeating pattern
       // for one that overlaps its own output; bytes that left the ring were flushed and are read back from HBM
       const uint32_t m0 = o;
       for (uint32_t done = 0; done < b_ml;) {
-        const uint32_t piece = b_ml - done < (uint32_t)LZ_PIECE ? b_ml - done : (uint32_t)LZ_PIECE;
+        const uint32_t piece = b_ml - done < (uint32_t)CFG::PIECE ? b_ml - done : (uint32_t)CFG::PIECE;
         const uint32_t piece_end = o + piece;
         if (b_off >= b_ml) {
           for (uint32_t i = lane; i < piece; i += 32) {
             const uint32_t p = m0 - b_off + done + i;
-            win[(o + i) & LZ_M] = piece_end - p <= (uint32_t)LZ_WIN ? win[p & LZ_M] : __ldcg(dst_al + p);
+            win[(o + i) & CFG::M] = piece_end - p <= (uint32_t)CFG::WIN ? win[p & CFG::M] : __ldcg(dst_al + p);
           }
         } else {
           for (uint32_t i = lane; i < piece; i += 32) {
             const uint32_t p = m0 - b_off + (done + i) % b_off;
-            win[(o + i) & LZ_M] = piece_end - p <= (uint32_t)LZ_WIN ? win[p & LZ_M] : __ldcg(dst_al + p);
+            win[(o + i) & CFG::M] = piece_end - p <= (uint32_t)CFG::WIN ? win[p & CFG::M] : __ldcg(dst_al + p);
           }
         }
         o += piece; done += piece;
         __syncwarp();
-        lz_flush(win, dst_al, flushed, o, lane);
+        lz_flush<CFG>(win, dst_al, flushed, o, lane);
       }
       if (b_last) finished = true;
     }
@@ -274,27 +288,32 @@ __global__ void __launch_bounds__(LZ_WARPS * 32) lz4_decode_kernel(const Lz4Job*
   // tail: the last (< 16) bytes of the ring, or everything for a tiny buffer
   __syncwarp();
   if (!bad && o == end) {
-    lz_flush(win, dst_al, flushed, o, lane);
-    for (uint32_t P = flushed + lane; P < end; P += 32) dst_al[P] = win[P & LZ_M];
+    lz_flush<CFG>(win, dst_al, flushed, o, lane);
+    for (uint32_t P = flushed + lane; P < end; P += 32) dst_al[P] = win[P & CFG::M];
   } else if (lane == 0) atomicExch(error_flag, 1u);
 }
 
-int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
-  if (njobs <= 0) return 0;
-  const int blocks = (njobs + LZ_WARPS - 1) / LZ_WARPS;
-  const size_t smem = (size_t)(LZ_WIN + LZ_IN) * LZ_WARPS;
+template <class CFG>
+static int lz4_launch_cfg(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
+  const int blocks = (njobs + CFG::WARPS - 1) / CFG::WARPS;
   static bool attr_set[64] = {false};
   int dev = 0;
   SD_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
     // as many resident buffers per SM as the shared memory allows
-    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel<CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
-  lz4_decode_kernel<<<blocks, LZ_WARPS * 32, smem, stream>>>(d_jobs, njobs, d_error);
+  lz4_decode_kernel<CFG><<<blocks, CFG::WARPS * 32, CFG::SMEM, stream>>>(d_jobs, njobs, d_error);
   SD_CUDA(cudaGetLastError());
   return 0;
+}
+
+int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
+  if (njobs <= 0) return 0;
+  static const bool dense = getenv("SD_TUNE_LZ4_DENSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
+  return dense ? lz4_launch_cfg<LzDense>(stream, d_jobs, njobs, d_error) : lz4_launch_cfg<LzDefault>(stream, d_jobs, njobs, d_error);
 }
 
 }  // namespace sd

@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 
 def test_model_with_the_kernels_constants_decodes_adversarial_blocks():
     import lz4_model
-    k = lz4_model.K
-    assert k["LZ_WIN"] & (k["LZ_WIN"] - 1) == 0
-    done = list(lz4_model.check(scale=4, alignments=(0, 5)))
-    assert len(done) == 11
+    for which in ("LzDefault", "LzDense"):   # the measured shape and the denser, not yet measured one
+        lz4_model.use(which)
+        k = lz4_model.K
+        assert k["LZ_WIN"] & (k["LZ_WIN"] - 1) == 0
+        done = list(lz4_model.check(scale=4, alignments=(0, 5)))
+        assert len(done) == 11

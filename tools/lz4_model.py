@@ -3,7 +3,7 @@ dependency-round logic on the host: the same group parse, per-lane copies in rou
 "shifted" positions, 16-byte flushes and near (ring) / far (HBM) source reads -- with assertions where the kernel
 relies on an invariant (a ring slot still holds the byte it is read for; a far byte has been flushed; a match
 never reads a byte that a pending sequence has yet to produce).  The constants are read from the .cu file, so
-changing LZ_WIN / LZ_PIECE / LZ_MAX_* there and running this (or tests/test_lz4_model.py) re-checks the invariants.
+changing a shape (LzDefault / LzDense) or LZ_MAX_* there and running this (or tests/test_lz4_model.py) re-checks the invariants.
 
     python tools/lz4_model.py          # decodes a set of adversarial blocks at several output alignments
 """
@@ -18,12 +18,23 @@ sys.path.insert(0, ROOT)
 from snappydata_b200.column_format import compress_lz4  # noqa: E402
 
 
-def kernel_constants():
+def kernel_constants(which=None):
+    """Constants of one kernel shape: `typedef LzCfg<WARPS, WIN, IN, PIECE> <which>;` + the shared LZ_MAX_*."""
+    which = which or os.environ.get("LZ4_MODEL_CFG", "LzDefault")
     text = open(os.path.join(ROOT, "snappydata_b200", "csrc", "sd_lz4.cu")).read()
-    out = {}
-    for name in ("LZ_WIN", "LZ_MAX_LIT", "LZ_MAX_ML", "LZ_PIECE"):
+    m = re.search(r"typedef LzCfg<(\d+), (\d+), (\d+), (\d+)> %s;" % which, text)
+    out = {"LZ_WIN": int(m.group(2)), "LZ_IN": int(m.group(3)), "LZ_PIECE": int(m.group(4))}
+    for name in ("LZ_MAX_LIT", "LZ_MAX_ML"):
         out[name] = int(re.search(r"constexpr int %s = (\d+);" % name, text).group(1))
     return out
+
+
+def use(which):
+    """Switch the model to another kernel shape (LzDefault | LzDense)."""
+    global K, WIN, MAX_LIT, MAX_ML, PIECE, M
+    K = kernel_constants(which)
+    WIN, MAX_LIT, MAX_ML, PIECE = K["LZ_WIN"], K["LZ_MAX_LIT"], K["LZ_MAX_ML"], K["LZ_PIECE"]
+    M = WIN - 1
 
 
 K = kernel_constants()
@@ -156,6 +167,8 @@ def check(scale=1, alignments=(0, 8, 5, 15)):
 
 
 if __name__ == "__main__":
-    print("kernel constants", K)
-    for bi, n, c in check():
-        print("ok block", bi, n, "->", c, "bytes")
+    for which in ("LzDefault", "LzDense"):
+        use(which)
+        print(which, K)
+        for bi, n, c in check():
+            print("  ok block", bi, n, "->", c, "bytes")

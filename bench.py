@@ -19,8 +19,11 @@ N > 1) prints ONE JSON line on rank 0.  A "step" is one execution of the query o
 Spark fork whose sources are absent and there is no JVM here: DESIGN.md).
 
 Workload: Q1 over an SF-100 lineitem column table (600,037,902 rows, 200,000-row batches, 24.0 GB of
-scanned column bytes), sharded by contiguous batch ranges over the ranks (strong scaling); Q6 over SF-10
-is measured in the same run and reported under "also".
+scanned column bytes) per GPU.  The path partitions by bucket, so N > 1 is one process per GPU, each holding and
+scanning its own table-sized partition set with no data-path collective (`"scaling": "weak"`, the default; the job is
+N x 600,037,902 rows per step) and ONE all-gather of the partial rows followed by the final merge on every rank.
+`--scaling strong` splits a single table into N contiguous batch ranges instead.  Q6 over SF-10 is measured in the
+same run and reported under "also".
 """
 import argparse
 import ctypes as C
@@ -56,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-lz4", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank scans its own table-sized partition set (per-GPU work fixed, the job is "
+                         "N tables' worth of rows); strong = one table split into N contiguous batch ranges")
     return ap.parse_args()
 
 
@@ -200,9 +206,9 @@ def run_reference_arm(args):
     sample = f"first {nsample} batches ({rows} rows) of the {total}-row table per step"
     print(json.dumps({
         "impl": "reference", "metric": metric_name(q1), "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(q1, total, args.gpus),
+        "config": workload_config(q1, total, args.gpus, args.scaling),
         "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample, "cpus": cpu_info},
         "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference-algorithm CPU restatement (oracle/scan_oracle.c, generated-loop layer); the reference itself "
@@ -214,10 +220,17 @@ def metric_name(q1):
             else "rows/sec, TPC-H Q6 lineitem scan+filter+aggregate over a column table")
 
 
-def workload_config(q1, total, gpus):
+def workload_config(q1, total, gpus, scaling="weak"):
+    if scaling == "weak":
+        sharding = (f"{gpus} rank(s), one process per GPU; every rank holds and scans its own {total}-row partition set "
+                    f"(weak scaling: {gpus * total} rows per step in total); no data-path collective, one all-gather of partial rows")
+    else:
+        sharding = f"one {total}-row table split into contiguous batch ranges over {gpus} rank(s), one partition per GPU"
     return {"workload": ("TPC-H Q1 on SF-100 lineitem column table" if q1 else "TPC-H Q6 on SF-10 lineitem column table"),
-            "rows": total, "rows_per_batch": ROWS_PER_BATCH, "bytes_per_row": 40 if q1 else 28,
-            "sharding": f"contiguous batch ranges over {gpus} rank(s), one partition per GPU",
+            "rows": total, "rows_per_gpu": total if scaling == "weak" else (total + gpus - 1) // gpus,
+            "total_rows": total * gpus if scaling == "weak" else total,
+            "rows_per_batch": ROWS_PER_BATCH, "bytes_per_row": 40 if q1 else 28,
+            "sharding": sharding,
             "l2": "inputs per step (>= 3 GB per GPU) are larger than the 126 MB L2; no flush needed",
             "literals": "Q1 cutoff 1997-10-02; Q6 1994-01-01, 0.05..0.07, 24"}
 
@@ -226,14 +239,23 @@ def workload_config(q1, total, gpus):
 class QueryRun:
     """One query over this rank's shard: resident store, plan, timing helpers."""
 
-    def __init__(self, api, torch, dist, q1, total_rows, rank, world, device):
+    def __init__(self, api, torch, dist, q1, total_rows, rank, world, device, scaling="weak"):
         from snappydata_b200 import capi, lineitem, plan as P
         self.api, self.torch, self.dist, self.q1, self.rank, self.world = api, torch, dist, q1, rank, world
         self.capi = capi
         self.desc = P.q1_plan() if q1 else P.q6_plan()
         self.lits = P.Q1_LITERALS if q1 else P.Q6_LITERALS
         self.total_rows = total_rows
-        first_row, nrows, _ = shard_batches(total_rows, rank, world)
+        if scaling == "weak" or world == 1:
+            # rank r's partition set: `total_rows` rows of its own, starting at a batch-aligned row of the generator's stream
+            stride = (total_rows + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH * ROWS_PER_BATCH
+            first_row, nrows = rank * stride, total_rows
+            self.job_rows = total_rows * world
+            self.e2e_rows_target = total_rows if world == 1 else (total_rows + world - 1) // world   # bounds pinned host memory
+        else:
+            first_row, nrows, _ = shard_batches(total_rows, rank, world)
+            self.job_rows = total_rows
+            self.e2e_rows_target = nrows
         self.local_rows = nrows
         self.store = capi.Store(api, lineitem.LINEITEM_SCHEMA, device)
         self.store.gen_lineitem(first_row, nrows, ROWS_PER_BATCH, NBUCKETS, SEED_Q1 if q1 else SEED_Q6,
@@ -275,7 +297,8 @@ class QueryRun:
         from snappydata_b200.column_format import ColumnBatch
         cols = self.desc.table_cols
         self.host_keep, self.marshalled, self.h2d_bytes = [], [], 0
-        nb = self.store.num_batches()
+        nb = min(self.store.num_batches(), max(1, (self.e2e_rows_target + ROWS_PER_BATCH - 1) // ROWS_PER_BATCH))
+        self.e2e_rows = sum(self.store.batch_info(i)[0] for i in range(nb))
         sizes = []
         for i in range(nb):
             for c in cols:
@@ -454,7 +477,15 @@ def main():
 
     q1 = args.workload == "q1"
     total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
-    main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank)
+    main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank, args.scaling)
+    job_rows = main_run.job_rows   # rows all ranks scan per step
+
+    def job_sum(x):   # sum of a per-rank count over the job
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS") else None
     ms = timed_steps(torch, dist, world, main_run.step_resident, args.warmup, args.steps)
@@ -467,10 +498,10 @@ def main():
     d2h_step = 0
     final_rows = capi.parse_row_stream(main_run.final_raw, main_run.desc.final_schema())
 
-    out = {"metric": metric_name(q1), "value": total * args.steps / (ms / 1e3), "unit": "rows/s", "n_gpus": world,
+    out = {"metric": metric_name(q1), "value": job_rows * args.steps / (ms / 1e3), "unit": "rows/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(q1, total, world), "gpu_launches": launches_timed, "clocks": clocks}
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(q1, total, world, args.scaling), "gpu_launches": launches_timed, "clocks": clocks}
     peak, peak_src = measured_peak_gbs()
     achieved = algo_per_launch / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
     tpr = ncu_traffic_per_row(q1)
@@ -479,20 +510,26 @@ def main():
                        "traffic_source": "profiles/r01_traffic.json (ncu --set full, 200M-row launch) scaled by rows", "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
                        "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": algo_per_launch,
                        "note": "per rank (rank 0); one launch scans the rank's whole shard"}
-    out["hbm_gbs_whole_job"] = total * (40 if q1 else 28) / (ms / args.steps / 1e3) / 1e9
+    out["hbm_gbs_whole_job"] = job_rows * (40 if q1 else 28) / (ms / args.steps / 1e3) / 1e9
 
     if not args.no_e2e:
         main_run.prepare_host_copy()
         e_steps = max(1, args.e2e_steps)
+        e2e_job_rows = job_sum(main_run.e2e_rows)
         ems = timed_steps(torch, dist, world, main_run.step_e2e, 1, e_steps)
-        out["e2e"] = {"value": total * e_steps / (ems / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.h2d_bytes,
+        out["e2e"] = {"value": e2e_job_rows * e_steps / (ems / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.h2d_bytes,
+                      "rows_per_step": e2e_job_rows,
                       "d2h_bytes_per_step": 4096 if world > 1 else 1024, "ms_per_step": ems / e_steps, "steps": e_steps,
                       "gpu_launches_per_step": main_run.e2e_launches,
-                      "note": "per-rank bytes; every ColumnBatch submitted from pinned host memory through sd_batch_submit each step (SD_OPT_RETAIN_BUFFERS: buffers stay valid until finish)"}
+                      "note": "per-rank bytes; every ColumnBatch of the e2e rows submitted from pinned host memory through sd_batch_submit "
+                              "each step (SD_OPT_RETAIN_BUFFERS: buffers stay valid until finish)"
+                              + ("" if main_run.e2e_rows == main_run.local_rows else
+                                 f"; the e2e legs stream the first {main_run.e2e_rows} rows of each rank's partition set "
+                                 "(bounds pinned host memory to one table across the job; the rate is link-bound and linear in rows)")}
         if not args.no_lz4:
             main_run.prepare_compressed_copy()
             lms = timed_steps(torch, dist, world, main_run.step_e2e_lz4, 1, e_steps)
-            out["e2e_lz4"] = {"value": total * e_steps / (lms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.lz4_h2d_bytes,
+            out["e2e_lz4"] = {"value": e2e_job_rows * e_steps / (lms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.lz4_h2d_bytes,
                               "ms_per_step": lms / e_steps, "steps": e_steps, "compressed_buffers": main_run.lz4_compressed_buffers,
                               "note": "same as e2e but the host holds the buffers in their stored LZ4 form ([-1][len][block], only when "
                                       "they shrink to <= 75 %); blocks are expanded on the device (sd_lz4.cu); not the headline e2e"}
@@ -508,11 +545,11 @@ def main():
         torch.cuda.empty_cache()
         oq1 = not q1
         ototal = SF100_ROWS if oq1 else SF10_ROWS
-        other = QueryRun(api, torch, dist, oq1, ototal, rank, world, local_rank)
+        other = QueryRun(api, torch, dist, oq1, ototal, rank, world, local_rank, args.scaling)
         oms = timed_steps(torch, dist, world, other.step_resident, args.warmup, args.steps)
         okms = other.kernel_ns / 1e6 / max(1, other.launches)
         oalgo = other.algo_bytes / max(1, other.launches)
-        out["also"] = {"workload": workload_config(oq1, ototal, world)["workload"], "value": ototal * args.steps / (oms / 1e3),
+        out["also"] = {"workload": workload_config(oq1, ototal, world, args.scaling)["workload"], "value": other.job_rows * args.steps / (oms / 1e3),
                        "unit": "rows/s", "ms_per_step": oms / args.steps,
                        "roofline": {"bound": "hbm", "achieved": oalgo / (okms / 1e3) / 1e9 if okms > 0 else 0.0, "peak": peak,
                                     "unit": "GB/s", "frac": (oalgo / (okms / 1e3) / 1e9 / peak) if okms > 0 else 0.0,

@@ -11,6 +11,7 @@
 // token = (literal length << 4) | (match length - 4); the last sequence ends after its literals.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "sd_host.h"
 
@@ -310,13 +311,81 @@ static int lz4_launch_cfg(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, 
   return 0;
 }
 
-int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
+int lz4_launch_shape(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error, bool dense) {
   if (njobs <= 0) return 0;
-  static const bool dense = getenv("SD_TUNE_LZ4_DENSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
   return dense ? lz4_launch_cfg<LzDense>(stream, d_jobs, njobs, d_error) : lz4_launch_cfg<LzDefault>(stream, d_jobs, njobs, d_error);
 }
 
+int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
+  static const bool dense = getenv("SD_TUNE_LZ4_DENSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
+  return lz4_launch_shape(stream, d_jobs, njobs, d_error, dense);
+}
+
 }  // namespace sd
+
+// bench/test hook: the device kernel on raw blocks (include/snappy_gpu.h)
+extern "C" int sdx_lz4_expand(int32_t device, const void* const* blocks, const int64_t* block_lens, const int64_t* out_lens,
+                              int32_t n, int32_t dst_misalign, int32_t dense, int32_t reps, void* const* outs, double* ms_per_launch) {
+  using namespace sd;
+  if (n <= 0 || !blocks || !block_lens || !out_lens || dst_misalign < 0 || dst_misalign > 15) return set_error(SD_ERR_INVALID, "sdx_lz4_expand: bad arguments");
+  SD_CUDA(cudaSetDevice(device));
+  size_t in_total = 0, out_total = 0;
+  for (int i = 0; i < n; i++) {
+    if (block_lens[i] < 0 || out_lens[i] < 0) return set_error(SD_ERR_INVALID, "sdx_lz4_expand: negative length");
+    in_total += ((size_t)block_lens[i] + 16 + 15) & ~size_t(15);
+    out_total += ((size_t)out_lens[i] + 32 + 15) & ~size_t(15);
+  }
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  Lz4Job* d_jobs = nullptr;
+  unsigned int* d_err = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = 0;
+  std::vector<Lz4Job> jobs((size_t)n);
+  auto cleanup = [&]() {
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (d_jobs) cudaFree(d_jobs);
+    if (d_err) cudaFree(d_err);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define LZX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = set_error(SD_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+  LZX(cudaMalloc(&d_in, in_total + 256));
+  LZX(cudaMalloc(&d_out, out_total + 256));
+  LZX(cudaMalloc(&d_jobs, sizeof(Lz4Job) * (size_t)n));
+  LZX(cudaMalloc(&d_err, 64));
+  LZX(cudaMemset(d_err, 0, 64));
+  LZX(cudaMemset(d_out, 0xEE, out_total + 256));
+  size_t io = 0, oo = 0;
+  for (int i = 0; i < n; i++) {
+    LZX(cudaMemcpy(d_in + io, blocks[i], (size_t)block_lens[i], cudaMemcpyHostToDevice));
+    jobs[i] = Lz4Job{d_in + io, d_out + oo + dst_misalign, block_lens[i], out_lens[i]};
+    io += ((size_t)block_lens[i] + 16 + 15) & ~size_t(15);
+    oo += ((size_t)out_lens[i] + 32 + 15) & ~size_t(15);
+  }
+  LZX(cudaMemcpy(d_jobs, jobs.data(), sizeof(Lz4Job) * (size_t)n, cudaMemcpyHostToDevice));
+  LZX(cudaEventCreate(&e0));
+  LZX(cudaEventCreate(&e1));
+  rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, dense != 0);   // warm-up (and the functional run)
+  if (rc) { cleanup(); return rc; }
+  LZX(cudaDeviceSynchronize());
+  if (reps > 0) {
+    LZX(cudaEventRecord(e0, nullptr));
+    for (int r = 0; r < reps; r++) { rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, dense != 0); if (rc) { cleanup(); return rc; } }
+    LZX(cudaEventRecord(e1, nullptr));
+    LZX(cudaEventSynchronize(e1));
+    float ms = 0;
+    LZX(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+  }
+  unsigned int err = 0;
+  LZX(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+  if (outs) for (int i = 0; i < n; i++) if (outs[i]) LZX(cudaMemcpy(outs[i], jobs[i].dst, (size_t)out_lens[i], cudaMemcpyDeviceToHost));
+#undef LZX
+  cleanup();
+  if (err) return set_error(SD_ERR_INVALID, "sdx_lz4_expand: the device decoder rejected a block");
+  return 0;
+}
 
 // test hook: the host prefix decoder (tests/test_lz4_prefix.py compares it with liblz4)
 extern "C" int64_t sdx_lz4_decode_prefix(const void* src, int64_t src_len, void* dst, int64_t want) {

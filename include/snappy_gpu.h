@@ -233,8 +233,9 @@ int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, in
                          int64_t* batch_id);
 /* expand n raw LZ4 blocks with the engine's device kernel (bench/test hook used by tools/lz4_bench.py): uploads the
  * blocks, places output i at a 16-byte boundary + dst_misalign, runs `reps` launches timed with CUDA events
- * (ms_per_launch = their mean) and copies output i to outs[i] when outs != NULL.  dense != 0 selects the denser
- * kernel shape (SD_TUNE_LZ4_DENSE).  A corrupt block -> SD_ERR_INVALID. */
+ * (ms_per_launch = their mean) and copies output i to outs[i] when outs != NULL.  `dense` selects the kernel variant:
+ * bit 0 = the denser shape (SD_TUNE_LZ4_DENSE), bit 1 = the window parse (SD_TUNE_LZ4_PARSE).  A corrupt block ->
+ * SD_ERR_INVALID. */
 int sdx_lz4_expand(int32_t device, const void* const* blocks, const int64_t* block_lens, const int64_t* out_lens,
                    int32_t n, int32_t dst_misalign, int32_t dense, int32_t reps, void* const* outs,
                    double* ms_per_launch);

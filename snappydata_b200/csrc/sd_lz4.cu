@@ -92,6 +92,40 @@ struct LzCfg {
 typedef LzCfg<4, 16384, 4096, 4096> LzDefault;
 typedef LzCfg<1, 8192, 2048, 2048> LzDense;
 
+// ---- window parse (kernel template parameter PARSE == 1; opt-in with SD_TUNE_LZ4_PARSE=1) ------------------------
+// The serial parse costs one dependent shared-memory round trip plus ~35 instructions per sequence.  The window parse
+// examines LZ_WP input bytes per step without a chain: every position is parsed speculatively as if a token started
+// there (`next token` per position, STOP where the checked path is needed), two doubling passes turn that into a 4-step
+// jump, the chain from the window's first byte is walked four sequences at a time (8 dependent steps for 32 sequences)
+// and each lane fills in its own member and extracts its fields; output positions come from a warp prefix sum.
+// tools/lz4_model.py (window_parse) is the executable model of exactly this and cross-checks it against the serial
+// parse; the kernel code below compiles but was written after the round's GPU budget ended: NOT yet run on hardware.
+constexpr int LZ_WP = 256;
+constexpr uint32_t LZ_STOP = 0xFFFFu;
+static_assert(LZ_WP + LZ_SEQ_IN_MAX + 2 <= (int)LZ_GROUP_IN, "the window's speculative reads stay inside the staged input");
+
+// parse the short sequence that would start at window position p (input byte s0 + p); returns the position of the
+// next token (may lie beyond the window) or LZ_STOP when the sequence needs the checked path
+template <class CFG>
+__device__ __forceinline__ uint32_t lz_spec(const uint8_t* in, uint32_t s0, uint32_t p, uint32_t& lit_src, uint32_t& lit, uint32_t& q_off, uint32_t& ml) {
+  const uint32_t token = in[(s0 + p) & CFG::IM];
+  uint32_t q = p + 1;
+  lit = token >> 4;
+  ml = token & 15;
+  bool ok = true;
+  if (lit == 15) { const uint32_t e = in[(s0 + q) & CFG::IM]; q++; lit += e; ok = e != 255; }
+  ok = ok && lit <= (uint32_t)LZ_MAX_LIT;
+  if (!ok) lit = 0;   // keeps the speculative reads below inside the staged range
+  lit_src = q;
+  q += lit;
+  q_off = q;
+  q += 2;
+  if (ml == 15) { const uint32_t e = in[(s0 + q) & CFG::IM]; q++; ml += e; ok = ok && e != 255; }
+  ml += 4;
+  ok = ok && ml <= (uint32_t)LZ_MAX_ML;
+  return ok ? q : LZ_STOP;
+}
+
 // write ring bytes [flushed, floor16(upto)) to HBM; only the very first flush can start unaligned (the head)
 template <class CFG>
 __device__ __forceinline__ void lz_flush(const uint8_t* win, uint8_t* dst_al, uint32_t& flushed, uint32_t upto, int lane) {
@@ -132,14 +166,18 @@ __device__ __forceinline__ void lz_lane_match(uint8_t* win, const uint8_t* dst_a
   }
 }
 
-template <class CFG>
+template <class CFG, int PARSE>
 __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Job* jobs, int njobs, unsigned int* error_flag) {
   extern __shared__ __align__(16) uint8_t lz_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * CFG::WARPS + wib;
   if (job >= njobs) return;
-  uint8_t* win = lz_smem + (size_t)wib * (CFG::WIN + CFG::IN);
+  constexpr int TABLES = PARSE == 1 ? 3 * LZ_WP * 2 : 0;   // next / 2-step / 4-step jump tables of the window parse
+  uint8_t* win = lz_smem + (size_t)wib * (CFG::WIN + CFG::IN + TABLES);
   uint8_t* in = win + CFG::WIN;
+  uint16_t* nx = reinterpret_cast<uint16_t*>(in + CFG::IN);
+  uint16_t* j1 = nx + LZ_WP;
+  uint16_t* j2 = j1 + LZ_WP;
   const Lz4Job j = jobs[job];
   const unsigned FULL = 0xffffffffu;
   if (j.src_len < 0 || j.dst_len < 0 || j.src_len > 0x7fffffff || j.dst_len > 0x7fffff00) {   // column buffers are < 2 GB
@@ -174,7 +212,69 @@ __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Jo
       }
       __syncwarp();
     }
-    while (n < 32) {
+    if (PARSE == 1 && safe) {
+      // speculative parse of every window position (lane-interleaved: conflict-free byte loads and table stores)
+#pragma unroll
+      for (int t = 0; t < LZ_WP / 32; t++) {
+        const uint32_t p = lane + 32u * t;
+        uint32_t a0, a1, a2, a3;
+        nx[p] = (uint16_t)lz_spec<CFG>(in, s, p, a0, a1, a2, a3);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < LZ_WP / 32; t++) {   // member after the next one (in-window members only)
+        const uint32_t p = lane + 32u * t;
+        const uint32_t v = nx[p];
+        const uint32_t w = v < (uint32_t)LZ_WP ? nx[v] : LZ_STOP;
+        j1[p] = (uint16_t)(w < (uint32_t)LZ_WP ? w : LZ_STOP);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < LZ_WP / 32; t++) {   // four members ahead
+        const uint32_t p = lane + 32u * t;
+        const uint32_t v = j1[p];
+        const uint32_t w = v < (uint32_t)LZ_WP ? j1[v] : LZ_STOP;
+        j2[p] = (uint16_t)(w < (uint32_t)LZ_WP ? w : LZ_STOP);
+      }
+      __syncwarp();
+      // anchors: members 0, 4, 8, ... (uniform walk, 8 dependent steps); lanes 4i..4i+3 hang off anchor i
+      uint32_t a = 0, my_a = LZ_STOP;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if ((lane >> 2) == i) my_a = a;
+        a = a < (uint32_t)LZ_WP ? j2[a] : LZ_STOP;
+      }
+      uint32_t pos = LZ_STOP;
+      if (my_a < (uint32_t)LZ_WP) {
+        const int r = lane & 3;
+        if (r == 0) pos = my_a;
+        else if (r == 1) pos = nx[my_a];
+        else {
+          const uint32_t v = j1[my_a];
+          pos = r == 2 ? v : (v < (uint32_t)LZ_WP ? nx[v] : LZ_STOP);
+        }
+        if (pos >= (uint32_t)LZ_WP) pos = LZ_STOP;
+      }
+      uint32_t f_lit_src = 0, f_lit = 0, f_qoff = 0, f_ml = 0, f_next = LZ_STOP;
+      if (pos != LZ_STOP) f_next = lz_spec<CFG>(in, s, pos, f_lit_src, f_lit, f_qoff, f_ml);
+      const unsigned vm = __ballot_sync(FULL, pos != LZ_STOP && f_next != LZ_STOP);
+      const int nw = vm == FULL ? 32 : __ffs(~vm) - 1;   // the valid lanes are a prefix; anything after the first gap is ignored
+      if (nw > 0) {
+        const bool mine = lane < nw;
+        const uint32_t len = mine ? f_lit + f_ml : 0u;
+        uint32_t scan = len;   // inclusive prefix sum of the sequences' output lengths
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t2 = __shfl_up_sync(FULL, scan, d); if (lane >= d) scan += t2; }
+        const uint32_t my_o = o + scan - len;
+        const uint32_t off = mine ? ((uint32_t)in[(s + f_qoff) & CFG::IM] | ((uint32_t)in[(s + f_qoff + 1) & CFG::IM] << 8)) : 1u;
+        if (__any_sync(FULL, mine && (off == 0 || off > my_o - wofs + f_lit))) { bad = true; break; }
+        if (mine) { my_lit_src = s + f_lit_src; my_lit = f_lit; my_mdst = my_o + f_lit; my_off = off; my_ml = f_ml; my_staged = true; }
+        o += __shfl_sync(FULL, scan, nw - 1);
+        s += __shfl_sync(FULL, f_next, nw - 1);
+        n = nw;
+      }
+    }
+    while (n < 32 && !(PARSE == 1 && n > 0)) {   // serial parse (with the window parse: only when it found nothing to take)
       if (safe) {
         const uint32_t token = in[s & CFG::IM];
         uint32_t q = s + 1, lit = token >> 4, ml = token & 15;
@@ -294,31 +394,35 @@ __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Jo
   } else if (lane == 0) atomicExch(error_flag, 1u);
 }
 
-template <class CFG>
+template <class CFG, int PARSE>
 static int lz4_launch_cfg(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
   const int blocks = (njobs + CFG::WARPS - 1) / CFG::WARPS;
+  constexpr size_t SMEM = CFG::SMEM + (PARSE == 1 ? (size_t)3 * LZ_WP * 2 * CFG::WARPS : 0);
   static bool attr_set[64] = {false};
   int dev = 0;
   SD_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
+    SD_CUDA(cudaFuncSetAttribute((lz4_decode_kernel<CFG, PARSE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     // as many resident buffers per SM as the shared memory allows
-    SD_CUDA(cudaFuncSetAttribute(lz4_decode_kernel<CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    SD_CUDA(cudaFuncSetAttribute((lz4_decode_kernel<CFG, PARSE>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
-  lz4_decode_kernel<CFG><<<blocks, CFG::WARPS * 32, CFG::SMEM, stream>>>(d_jobs, njobs, d_error);
+  lz4_decode_kernel<CFG, PARSE><<<blocks, CFG::WARPS * 32, SMEM, stream>>>(d_jobs, njobs, d_error);
   SD_CUDA(cudaGetLastError());
   return 0;
 }
 
-int lz4_launch_shape(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error, bool dense) {
+int lz4_launch_shape(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error, bool dense, bool window_parse) {
   if (njobs <= 0) return 0;
-  return dense ? lz4_launch_cfg<LzDense>(stream, d_jobs, njobs, d_error) : lz4_launch_cfg<LzDefault>(stream, d_jobs, njobs, d_error);
+  if (window_parse)
+    return dense ? lz4_launch_cfg<LzDense, 1>(stream, d_jobs, njobs, d_error) : lz4_launch_cfg<LzDefault, 1>(stream, d_jobs, njobs, d_error);
+  return dense ? lz4_launch_cfg<LzDense, 0>(stream, d_jobs, njobs, d_error) : lz4_launch_cfg<LzDefault, 0>(stream, d_jobs, njobs, d_error);
 }
 
 int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
   static const bool dense = getenv("SD_TUNE_LZ4_DENSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
-  return lz4_launch_shape(stream, d_jobs, njobs, d_error, dense);
+  static const bool wparse = getenv("SD_TUNE_LZ4_PARSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_PARSE")) > 0;
+  return lz4_launch_shape(stream, d_jobs, njobs, d_error, dense, wparse);
 }
 
 }  // namespace sd
@@ -366,12 +470,12 @@ extern "C" int sdx_lz4_expand(int32_t device, const void* const* blocks, const i
   LZX(cudaMemcpy(d_jobs, jobs.data(), sizeof(Lz4Job) * (size_t)n, cudaMemcpyHostToDevice));
   LZX(cudaEventCreate(&e0));
   LZX(cudaEventCreate(&e1));
-  rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, dense != 0);   // warm-up (and the functional run)
+  rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, (dense & 1) != 0, (dense & 2) != 0);   // warm-up (and the functional run)
   if (rc) { cleanup(); return rc; }
   LZX(cudaDeviceSynchronize());
   if (reps > 0) {
     LZX(cudaEventRecord(e0, nullptr));
-    for (int r = 0; r < reps; r++) { rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, dense != 0); if (rc) { cleanup(); return rc; } }
+    for (int r = 0; r < reps; r++) { rc = lz4_launch_shape(nullptr, d_jobs, n, d_err, (dense & 1) != 0, (dense & 2) != 0); if (rc) { cleanup(); return rc; } }
     LZX(cudaEventRecord(e1, nullptr));
     LZX(cudaEventSynchronize(e1));
     float ms = 0;

@@ -15,3 +15,7 @@ def test_model_with_the_kernels_constants_decodes_adversarial_blocks():
         assert k["LZ_WIN"] & (k["LZ_WIN"] - 1) == 0
         done = list(lz4_model.check(scale=4, alignments=(0, 5)))
         assert len(done) == 11
+    # the window parse (kernel template parameter PARSE == 1): at every step it must return a prefix of what the serial
+    # parse finds from the same position -- checked inside the model -- and the decode must stay byte-exact
+    lz4_model.use("LzDense")
+    assert len(list(lz4_model.check(scale=4, alignments=(8,), parse=1))) == 11

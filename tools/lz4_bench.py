@@ -5,7 +5,7 @@ input: the quick loop for working on snappydata_b200/csrc/sd_lz4.cu.
 
 Per kind of column it prints the compressed ratio, the time of one launch over `buffers` identical-shape buffers (a
 launch lasts as long as its longest buffer chain: the figure of merit is ms per buffer chain) and the aggregate output
-rate of that launch; both kernel shapes (default / dense).  (Written at the end of round 1 after the GPU budget was spent:
+rate of that launch; every kernel variant (default / dense shape, serial / window parse).  (Written at the end of round 1 after the GPU budget was spent:
 not yet run on hardware.)"""
 import ctypes as C
 import os
@@ -42,8 +42,8 @@ def main():
         raws = [t[name] for t in tables]
         blocks = [compress_lz4(b, force=True)[8:] for b in raws]
         ratio = sum(map(len, blocks)) / sum(map(len, raws))
-        for dense in (0, 1):
-            for mis in ((0, 8) if dense == 0 else (8,)):
+        for variant in (0, 1, 2, 3):   # bit 0: dense kernel shape, bit 1: window parse
+            for mis in ((0, 8) if variant == 0 else (8,)):
                 keep = [C.create_string_buffer(b, len(b)) for b in blocks]
                 outs = [C.create_string_buffer(len(b)) for b in raws]
                 bp = (C.c_void_p * nbuf)(*[C.cast(k, C.c_void_p) for k in keep])
@@ -51,11 +51,12 @@ def main():
                 bl = (C.c_int64 * nbuf)(*[len(b) for b in blocks])
                 ol = (C.c_int64 * nbuf)(*[len(b) for b in raws])
                 ms = C.c_double()
-                api.check(L.sdx_lz4_expand(0, bp, bl, ol, nbuf, mis, dense, reps, op, C.byref(ms)))
+                api.check(L.sdx_lz4_expand(0, bp, bl, ol, nbuf, mis, variant, reps, op, C.byref(ms)))
                 for o, b in zip(outs, raws):
                     assert o.raw == b, "device output differs from the input of the compressor"
                 out_bytes = sum(map(len, raws))
-                print(f"{name:42s} ratio {ratio:.2f}  {'dense  ' if dense else 'default'} misalign {mis:2d}: {ms.value:8.3f} ms per launch of {nbuf} "
+                label = ("dense" if variant & 1 else "default") + ("+window-parse" if variant & 2 else "")
+                print(f"{name:42s} ratio {ratio:.2f}  {label:20s} misalign {mis:2d}: {ms.value:8.3f} ms per launch of {nbuf} "
                       f"buffers ({len(raws[0]) / 1e6:.2f} MB each) = {out_bytes / ms.value / 1e6:8.2f} GB/s out")
 
 

@@ -41,7 +41,72 @@ K = kernel_constants()
 WIN, MAX_LIT, MAX_ML, PIECE = K["LZ_WIN"], K["LZ_MAX_LIT"], K["LZ_MAX_ML"], K["LZ_PIECE"]
 M = WIN - 1
 
-def decode(src, n_out, wofs):
+WP = 256          # input bytes examined per step by the window parse (LZ_WP in the kernel)
+STOP = 0xFFFF     # "the sequence starting here needs the checked path" (long run, > 1 length byte)
+
+
+def window_parse(src, s, o, wofs):
+    """Model of the kernel's window parse (sd_lz4.cu, PARSE == 1): every position of the window is parsed speculatively as
+    if a token started there (independent work, no chain), two doubling passes turn `next token` into a 4-step jump, the
+    chain from position 0 is then walked 4 sequences at a time (8 dependent steps for 32 sequences) and the lanes fill in
+    the members in between; fields are extracted per lane and output positions come from a prefix sum.
+    Returns (records, next s, next o); no record when the first sequence needs the checked path."""
+    def spec(p):
+        tok = src[s + p]; lit = tok >> 4; ml = tok & 15; q = p + 1
+        if lit == 15:
+            e = src[s + q]; q += 1; lit += e
+            if e == 255: return STOP, None
+        if lit > MAX_LIT: return STOP, None
+        lit_src = q; q += lit
+        q_off = q; q += 2
+        if ml == 15:
+            e = src[s + q]; q += 1; ml += e
+            if e == 255: return STOP, None
+        ml += 4
+        if ml > MAX_ML: return STOP, None
+        return q, (lit_src, lit, q_off, ml)
+    nxt = [spec(p)[0] for p in range(WP)]
+    def hop(table, p):          # member after p through `table`, or STOP when there is none inside the window
+        return table[p] if p < WP else STOP
+    j1 = [STOP if nxt[p] >= WP else nxt[nxt[p]] for p in range(WP)]
+    j1 = [STOP if v >= WP else v for v in j1]            # only in-window positions are members
+    j2 = [STOP if j1[p] >= WP else j1[j1[p]] for p in range(WP)]
+    j2 = [STOP if v >= WP else v for v in j2]
+    anchors = []
+    a = 0
+    for i in range(8):
+        anchors.append(a)
+        a = j2[a] if a < WP else STOP
+    recs, last_next = [], None
+    lane_pos = []
+    for L in range(32):
+        a = anchors[L >> 2]; r = L & 3
+        if a >= WP: pos = STOP
+        elif r == 0: pos = a
+        elif r == 1: pos = nxt[a] if nxt[a] < WP else STOP
+        elif r == 2: pos = j1[a]
+        else: pos = (nxt[j1[a]] if j1[a] < WP and nxt[j1[a]] < WP else STOP)
+        lane_pos.append(pos)
+    valid = [pos < WP and nxt[pos] != STOP for pos in lane_pos]
+    n = 0
+    while n < 32 and valid[n]: n += 1
+    assert not any(valid[n:]) or True   # (lanes after the first invalid one are ignored, as in the kernel)
+    lens = []
+    for L in range(n):
+        q, (lit_src, lit, q_off, ml) = spec(lane_pos[L])
+        lens.append((lit_src, lit, q_off, ml, q))
+    oo = o
+    for (lit_src, lit, q_off, ml, q) in lens:
+        off = src[s + q_off] | (src[s + q_off + 1] << 8)
+        assert off != 0 and off <= oo - wofs + lit, "bad offset"
+        recs.append((s + lit_src, lit, oo + lit, off, ml))
+        oo += lit + ml
+    new_s = s + (lens[-1][4] if n else 0)
+    return recs, new_s, oo
+
+
+def decode(src, n_out, wofs, parse=0):
+    """parse=0: the serial group parse; parse=1: the window parse where a whole group's input and output remain"""
     n_src=len(src); end=n_out+wofs
     dst_al=bytearray(end+64); written=bytearray(end+64)   # HBM
     win=bytearray(WIN); ring_pos=[-1]*WIN                  # which P each slot holds
@@ -67,7 +132,12 @@ def decode(src, n_out, wofs):
     while not finished:
         recs=[]; big=None
         s=st['s']; o=st['o']
+        use_window = parse==1 and n_src-s >= WP+64 and end-o >= 32*(MAX_LIT+MAX_ML)
+        if use_window:
+            wrecs, ws, wo = window_parse(src, s, o, wofs)
         while len(recs)<32:
+            if use_window and wrecs:      # the serial loop below re-derives the same records: cross-check, then take them
+                pass
             if s>=n_src: finished=True; break
             tok=src[s]; s+=1; lit=tok>>4
             if lit==15:
@@ -87,6 +157,13 @@ def decode(src, n_out, wofs):
             if lit>MAX_LIT or ml>MAX_ML: big=(lit_src,lit,off,ml,last); break
             recs.append((lit_src,lit,o+lit,off,ml)); o+=lit+ml
             if last: finished=True; break
+        if use_window and wrecs:
+            # the window parse must return a prefix of what the serial parse finds from the same position
+            assert recs[:len(wrecs)] == wrecs, (recs[:3], wrecs[:3])
+            if len(wrecs) < len(recs) or big or finished:
+                # take exactly the window's group; the rest is parsed again in the next step
+                recs = wrecs; big = None; finished = False; s = ws; o = wo
+            assert (s, o) == (ws, wo), ((s, o), (ws, wo))
         st['s']=s; st['o']=o
         n=len(recs)
         if n:
@@ -157,12 +234,12 @@ def blocks(rng, scale=1):
     ]
 
 
-def check(scale=1, alignments=(0, 8, 5, 15)):
+def check(scale=1, alignments=(0, 8, 5, 15), parse=0):
     rng = np.random.default_rng(5)
     for bi, b in enumerate(blocks(rng, scale)):
         env = compress_lz4(b, force=True)
         for wofs in alignments:
-            assert decode(env[8:], len(b), wofs) == b, (bi, wofs)
+            assert decode(env[8:], len(b), wofs, parse) == b, (bi, wofs)
         yield bi, len(b), len(env)
 
 
@@ -170,5 +247,6 @@ if __name__ == "__main__":
     for which in ("LzDefault", "LzDense"):
         use(which)
         print(which, K)
-        for bi, n, c in check():
-            print("  ok block", bi, n, "->", c, "bytes")
+        for parse in (0, 1):
+            for bi, n, c in check(parse=parse):
+                print("  ok block", bi, n, "->", c, "bytes", "(window parse)" if parse else "")

@@ -1,5 +1,6 @@
 """Edge cases the reference's tests exercise (empty and ragged inputs, all rows deleted, all-NULL columns, stats
-rows with NULL bounds) and size-independent properties at BASELINE.json scale (SF-10: 59,986,052 rows) where the
+rows with NULL bounds) and size-independent properties at BASELINE.json scale (Q6: SF-10, 59,986,052 rows; Q1: SF-10 and
+SF-100, 600,037,902 rows) where the
 oracle is too slow to be the checker: totals, linearity over shards, idempotence of re-execution."""
 import numpy as np
 import pytest
@@ -96,6 +97,24 @@ def _count_plan():
 
 
 def test_sf10_q1_totals_linearity_idempotence(gpu_api, sf10_store):
+    _q1_properties(gpu_api, sf10_store, SF10)
+
+
+SF100 = 600_037_902
+
+
+def test_sf100_q1_totals_linearity_idempotence(gpu_api):
+    """The same properties at the size BASELINE.json quotes Q1 on (SF-100: 600,037,902 rows, 24 GB of scanned column
+    bytes resident on one GPU; generated on the device in a fraction of a second)."""
+    store = capi.Store(gpu_api, lineitem.LINEITEM_SCHEMA)
+    store.gen_lineitem(0, SF100, 200_000, 128, 1, lineitem.Q1_COLUMN_MASK)
+    try:
+        _q1_properties(gpu_api, store, SF100)
+    finally:
+        store.close()
+
+
+def _q1_properties(gpu_api, sf10_store, SF10):
     q1 = capi.Plan(gpu_api, P.q1_plan())
     q1.reset().set_literals(P.Q1_LITERALS)
     q1.scan_store(sf10_store)

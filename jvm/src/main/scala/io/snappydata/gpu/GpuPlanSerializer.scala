@@ -55,7 +55,40 @@ object GpuPlanSerializer {
   def writeLiterals(literals: Seq[Expression]): Long = ???
 
   /** per batch: value buffers via getColumnLob, deltas via the iterator's delta lookups (ColumnBatchIterator.scala:122-163) */
-  def submitBatch(plan: Long, it: ColumnBatchIterator, stats: ByteBuffer, desc: GpuPlanDesc): Unit = ???
+  def submitBatch(plan: Long, it: ColumnBatchIterator, stats: ByteBuffer, desc: GpuPlanDesc): Unit = {
+    val cols = desc.scan.output                              // scan columns in plan order
+    val nCols = cols.length
+    val nTableCols = desc.scan.relationSchema.length
+    val statsRow = org.apache.spark.sql.collection.SharedUtils.toUnsafeRow(stats, 1 + 3 * nTableCols)
+    // count < 0 marks a batch that carries delta updates (ColumnTableScan.scala:524-528); the engine takes the
+    // row count from here and never reads the count field of the stats row
+    val numRows = math.abs(statsRow.getInt(0))
+    // an old-format delta stats row means the full stats may be stale: no skipping for this batch (:536-539)
+    val passStats = it.getCurrentDeltaStats == null
+    val addrs = new Array[Long](nCols); val lens = new Array[Long](nCols); val heap = new Array[Array[Byte]](nCols)
+    val d0a = new Array[Long](nCols); val d0l = new Array[Long](nCols)
+    val d1a = new Array[Long](nCols); val d1l = new Array[Long](nCols)
+    def place(buf: ByteBuffer, i: Int, a: Array[Long], l: Array[Long], h: Array[Array[Byte]]): Unit = {
+      l(i) = buf.remaining()
+      if (buf.isDirect) a(i) = io.snappydata.gpu.DirectBuffers.address(buf) + buf.position() // GetDirectBufferAddress
+      else { a(i) = 0L; h(i) = buf.array() /* arrayOffset + position == 0 for store buffers (ColumnTableScan.scala:430-437) */ }
+    }
+    var i = 0
+    while (i < nCols) {
+      val tableCol = desc.scan.baseRelation.schema.fieldIndex(cols(i).name) + 1 // ColumnFormatKey.columnIndex is 1-based
+      place(it.getColumnLob(tableCol - 1), i, addrs, lens, heap)
+      // deltas are always direct/off-heap copies owned by the iterator (ColumnBatchIterator.scala:122-150)
+      val u0 = it.getUpdatedColumnBuffer(tableCol, 0); if (u0 ne null) place(u0, i, d0a, d0l, null)
+      val u1 = it.getUpdatedColumnBuffer(tableCol, 1); if (u1 ne null) place(u1, i, d1a, d1l, null)
+      i += 1
+    }
+    val del = it.getDeletedColumnBuffer
+    val (delAddr, delLen) = if (del eq null) (0L, 0L) else (DirectBuffers.address(del) + del.position(), del.remaining().toLong)
+    val (stAddr, stLen) = if (passStats) (DirectBuffers.addressOrCopy(stats), stats.remaining().toLong) else (0L, 0L)
+    // throws RuntimeException(sd_last_error()) on a non-zero status; the buffers may be released when it returns
+    SnappyGpuNative.batchSubmit(plan, numRows, nCols, addrs, lens, heap, d0a, d0l, d1a, d1l, delAddr, delLen,
+      stAddr, stLen, nTableCols, it.getCurrentBucketId, it.getCurrentBatchId)
+  }
 
   /** un-rolled-over rows as UnsafeRows (ColumnTableScan.scala:572-588) */
   def submitRowBuffer(plan: Long, rows: Iterator[InternalRow], desc: GpuPlanDesc): Unit = ???

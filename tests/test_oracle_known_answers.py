@@ -150,3 +150,24 @@ def test_basic_delete_and_update_counts(oracle_api):
     assert [cnt, mx, cs] == [1, 73, 1]
     (cnt, _, _), = _run(oracle_api, b.build(), [74], batches_upd)[0]
     assert cnt == 0                                                        # 74 became 74 + n
+
+
+def test_sha_sum_of_every_numeric_type_per_string_key(oracle_api):
+    """SHAByteBufferTest.scala:534-700 ("aggregate functions & grouping on each of spark data type"): ten rows i = 0..9 with
+    the value i in a column of the type under test (every other column NULL) and the key 'col{i/5}':
+    sum per key = 10 and 35 -- read with getLong for BYTE/SHORT/INT/LONG, with getDouble for FLOAT/DOUBLE."""
+    i = np.arange(10)
+    keys = np.array([b"col%d" % (x // 5) for x in i], dtype=object)
+    cases = [(T.BYTE, np.int8, int), (T.SHORT, np.int16, int), (T.INT, np.int32, int), (T.LONG, np.int64, int),
+             (T.FLOAT, np.float32, float), (T.DOUBLE, np.float64, float)]
+    for t, dt, py in cases:
+        schema = [("col000", T.INT, True), ("v", t, True), ("k", T.STRING, True)]
+        batch = build_batch(10, schema, {"col000": i.astype(np.int32), "v": i.astype(dt), "k": keys}, {})
+        b = PlanBuilder()
+        v, k = b.col(t, 1, True), b.col(T.STRING, 2, True)
+        b.group_by(k)
+        b.sum(v)
+        rows, _ = _run(oracle_api, b.build(), [], [batch])
+        got = {key: s for key, s in rows}
+        assert got == {b"col0": py(10), b"col1": py(35)}, (t, got)
+        assert all(type(s) is py for s in got.values()), (t, got)

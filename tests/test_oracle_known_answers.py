@@ -23,7 +23,13 @@ def _run(oracle_api, desc, lits, batches):
     pl = oracle.plan(desc).set_literals(lits)
     for b in batches:
         pl.submit(b)
-    return final_merge(oracle_api, desc, pl.finish_raw()), pl
+    raw = pl.finish_raw()
+    final = final_merge(oracle_api, desc, raw)
+    # the product's host-side final merge (sd_final_merge in libsnappygpu.so: no CUDA call) over the same partial rows
+    from snappydata_b200 import capi
+    product = final_merge(capi.product_api(), desc, raw)
+    assert sorted(map(repr, product)) == sorted(map(repr, final))
+    return final, pl
 
 
 def test_sha_one_nullable_string_key_closed_form(oracle_api):

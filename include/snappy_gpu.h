@@ -231,6 +231,10 @@ int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, vo
 int64_t sdx_lz4_decode_prefix(const void* src, int64_t src_len, void* dst, int64_t want);
 int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id,
                          int64_t* batch_id);
+/* the batch-skipping decision (ColumnTableScan.scala:820-963) of a plan's filter for one stats row: *pass = 0 when the
+ * batch would be skipped.  Host only, no CUDA call (test hook: tests/test_stats_predicate.py compares it with the oracle). */
+int sdx_stats_pass(const sd_plan_desc* desc, const sd_literal* lits, int32_t nlits, const void* stats,
+                   int64_t stats_len, int32_t stats_ncols, int32_t num_rows, int32_t* pass);
 /* expand n raw LZ4 blocks with the engine's device kernel (bench/test hook used by tools/lz4_bench.py): uploads the
  * blocks, places output i at a 16-byte boundary + dst_misalign, runs `reps` launches timed with CUDA events
  * (ms_per_launch = their mean) and copies output i to outs[i] when outs != NULL.  `dense` selects the kernel variant:

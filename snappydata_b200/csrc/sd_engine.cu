@@ -802,6 +802,24 @@ bool batch_passes_stats(const sd_plan* p, const StoredBatch& sb) {
   return r.isnull || r.v;   // only a definite FALSE skips the batch (:948-957)
 }
 
+// test hook (host only, no CUDA call): the batch-skipping decision of a plan for one stats row
+int stats_pass_hook(const sd_plan_desc* desc, const sd_literal* lits, int32_t nlits, const void* stats, int64_t stats_len,
+                    int32_t stats_ncols, int32_t num_rows, int32_t* pass) {
+  if (!desc || !pass || (nlits > 0 && !lits)) return set_error(SD_ERR_INVALID, "sdx_stats_pass: null argument");
+  PlanSpec spec;
+  std::string err;
+  int rc = analyze_plan(desc, spec, err);
+  if (rc) return set_error(rc, "sdx_stats_pass: %s", err.c_str());
+  if (nlits != (int)spec.literal_types.size()) return set_error(SD_ERR_INVALID, "sdx_stats_pass: plan has %zu literal slots", spec.literal_types.size());
+  std::vector<sd_literal> lv(lits, lits + nlits);
+  *pass = 1;
+  if (spec.filter < 0 || !stats || stats_len <= 0) return 0;
+  StatEval ev{spec, lv, reinterpret_cast<const uint8_t*>(stats), stats_len, 1 + 3 * stats_ncols, num_rows};
+  Tri r;
+  if (ev.eval(spec.filter, &r)) *pass = (r.isnull || r.v) ? 1 : 0;
+  return 0;
+}
+
 // find the kernel for a codegen variant of the plan: ahead-of-time registry first, else NVRTC
 int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int device, KernelEntry* out, PlanSpec* spec_out) {
   PlanSpec spec;
@@ -997,6 +1015,11 @@ int sd_init(int device) {
 }
 int sd_device_count(int* out) { SD_CUDA(cudaGetDeviceCount(out)); return 0; }
 const char* sd_version(void) { return "snappydata_b200 0.1.0 (sm_100a)"; }
+
+int sdx_stats_pass(const sd_plan_desc* desc, const sd_literal* lits, int32_t nlits, const void* stats, int64_t stats_len,
+                   int32_t stats_ncols, int32_t num_rows, int32_t* pass) {
+  return stats_pass_hook(desc, lits, nlits, stats, stats_len, stats_ncols, num_rows, pass);
+}
 
 int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   if (!out) return set_error(SD_ERR_INVALID, "sd_plan_create: null out");

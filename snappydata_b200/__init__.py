@@ -9,8 +9,10 @@ Only what the hot path needs lives here:
   lineitem         synthetic TPC-H lineitem-shaped column tables (counter-based generator,
                    identical on host/numpy and on device)
   capi             ctypes binding of include/snappy_gpu.h
-  operators        host-side mirror of the reference operator surface
-                   (ColumnFormatRelation / ColumnTableScan / SnappyHashAggregateExec)
+  plan             expression DSL that flattens to sd_plan_desc (what the Scala operators serialise)
+  exchange         the one cross-partition exchange of partial results (torch.distributed plumbing)
+  csrc/sd_operators.hpp   C++ mirror of the reference operator surface
+                   (ColumnBatchIterator / SnappyHashAggregateExec / CollectAggregateExec)
 """
 
 __version__ = "0.1.0"

@@ -18,12 +18,16 @@ N > 1) prints ONE JSON line on rank 0.  A "step" is one execution of the query o
 `--impl reference` times that CPU restatement as the reference arm (the reference itself is Scala on a
 Spark fork whose sources are absent and there is no JVM here: DESIGN.md).
 
-Workload: Q1 over an SF-100 lineitem column table (600,037,902 rows, 200,000-row batches, 24.0 GB of
-scanned column bytes) per GPU.  The path partitions by bucket, so N > 1 is one process per GPU, each holding and
-scanning its own table-sized partition set with no data-path collective (`"scaling": "weak"`, the default; the job is
-N x 600,037,902 rows per step) and ONE all-gather of the partial rows followed by the final merge on every rank.
-`--scaling strong` splits a single table into N contiguous batch ranges instead.  Q6 over SF-10 is measured in the
-same run and reported under "also".
+Workload: Q1 over ONE SF-100 lineitem column table (600,037,902 rows, 200,000-row batches, 24.0 GB of scanned
+column bytes).  The path partitions by bucket, so N > 1 is one process per GPU, each holding and scanning a contiguous
+range of the table's batches (`"scaling": "strong"`, the default: BASELINE.json's "Q1 on SF-100, 1->8 GPUs") with no
+data-path collective and ONE exchange per query: sd_plan_exchange = an ncclAllGather of every rank's partial rows inside
+libsnappygpu.so, merged on every rank, then the final merge.  `--scaling weak` gives every rank its own table-sized
+partition set instead.  Q6 over SF-10 is measured in the same run and reported under "also".
+
+`parity_check`: in the same run the oracle's generated-loop layer (CPU) scans the SAME ColumnBatch bytes at the
+benchmark's own size (every rank its shard; partial rows gathered and merged) and the GPU result must match: counts
+bit-exact, DOUBLE sums / averages within 1e-6 relative (BASELINE.json north_star).  A mismatch fails the run.
 """
 import argparse
 import ctypes as C
@@ -59,9 +63,10 @@ def parse_args():
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-lz4", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = every rank scans its own table-sized partition set (per-GPU work fixed, the job is "
-                         "N tables' worth of rows); strong = one table split into N contiguous batch ranges")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default, BASELINE.json: ONE SF-100 table over 1->8 GPUs) = the table split into N contiguous "
+                         "batch ranges, one partition set per GPU; weak = every rank scans its own table-sized partition set")
+    ap.add_argument("--no-parity", action="store_true", help="skip the GPU-vs-oracle parity check at the benchmark's own size")
     return ap.parse_args()
 
 
@@ -239,7 +244,7 @@ def workload_config(q1, total, gpus, scaling="weak"):
 class QueryRun:
     """One query over this rank's shard: resident store, plan, timing helpers."""
 
-    def __init__(self, api, torch, dist, q1, total_rows, rank, world, device, scaling="weak"):
+    def __init__(self, api, torch, dist, q1, total_rows, rank, world, device, scaling="strong", comm=None):
         from snappydata_b200 import capi, lineitem, plan as P
         self.api, self.torch, self.dist, self.q1, self.rank, self.world = api, torch, dist, q1, rank, world
         self.capi = capi
@@ -267,28 +272,31 @@ class QueryRun:
         self.kernel_ns = 0
         self.algo_bytes = 0
         self.final_raw = b""
-        if world > 1:
-            from snappydata_b200.exchange import PartialRowExchange
-            self.exchange = PartialRowExchange(torch, dist, world, "cuda")
+        self.lit_array = self.plan.literal_array(self.lits)
+        self._m = (C.c_int64 * capi.SD_NUM_METRICS)()
+        self.comm = comm   # capi.Comm (sd_comm: NCCL inside the library) or None
 
-    def exchange_and_merge(self, raw):
-        """The one exchange of the query: all-gather of the partial rows over NCCL, then the final merge
-        (SnappyHashAggregateExec(Final) / CollectAggregateExec) -- identical on every rank."""
-        if self.world > 1:
-            raw = self.exchange.all_gather(raw)
+    def exchange_and_merge(self, plan):
+        """The one exchange of the query (sd_plan_exchange: ncclAllGather of every rank's partial rows inside the library,
+        merged on every rank), then the final merge (SnappyHashAggregateExec(Final) / CollectAggregateExec)."""
+        if self.comm is not None:
+            plan.exchange(self.comm)
+        raw = plan.finish_raw()
         self.final_raw = self.merge_plan.final_merge_raw(raw)   # final rows of the query (parsed after the timed region)
         return len(raw)
 
     def step_resident(self):
+        """One execution of the cached plan over the resident shard: ONE C call (reset, literals, scan, exchange, partial
+        rows), then the final merge."""
         p = self.plan
-        p.reset().set_literals(self.lits)
-        p.scan_store(self.store)
-        raw = p.finish_raw()
-        m = p.metrics()
-        self.launches += m["kernelLaunches"]
-        self.kernel_ns += m["aggTimeNs"]
-        self.algo_bytes += m["algorithmicBytes"]
-        return self.exchange_and_merge(raw)
+        raw = p.execute_store_raw(self.store, self.lit_array, len(self.lits), self.comm)
+        self.api.plan_metrics(p.h, self._m)
+        m = self._m
+        self.launches += m[7]
+        self.kernel_ns += m[6]
+        self.algo_bytes += m[9]
+        self.final_raw = self.merge_plan.final_merge_raw(raw)
+        return len(raw)
 
     # ---- end to end: host buffers -> sd_batch_submit ---------------------------------------------
     def prepare_host_copy(self):
@@ -399,12 +407,12 @@ class QueryRun:
             if rc:
                 self.api.check(rc)
         t1 = time.perf_counter()
-        raw = p.finish_raw()
+        p.finish_raw()
         if os.environ.get("BENCH_DEBUG"):   # where a step's wall time goes: queueing on the host vs waiting for the device
             print(f"[e2e step] submit loop {1e3 * (t1 - t0):.1f} ms, finish {1e3 * (time.perf_counter() - t1):.1f} ms, "
                   f"{len(self.marshalled)} batches", file=sys.stderr)
         self.e2e_launches = p.metrics()["kernelLaunches"]
-        return self.exchange_and_merge(raw)
+        return self.exchange_and_merge(p)
 
     def cpu_baseline(self, seconds):
         """Generated-loop restatement over a bounded sample of this rank's host copy, all host threads."""
@@ -431,6 +439,93 @@ class QueryRun:
         return {"value": rows * reps / dt, "unit": "rows/s", "cores": cores, "kind": "port",
                 "sample": f"first {nsample} batches ({rows} rows) of rank 0's shard x {reps} passes in {dt:.1f} s",
                 "cpus": cpu_info}, res
+
+
+    # ---- parity at the benchmark's own size: GPU (C-ABI, same host bytes) vs the oracle's generated loops ----------
+    def oracle_partials(self, threads):
+        """This rank's shard through the oracle's generated-loop layer (CPU): -> (partial rows, rows scanned)."""
+        from oracle import oracle
+        n = len(self.marshalled)
+        ba = oracle.BatchArray.__new__(oracle.BatchArray)
+        ba.m = self.marshalled
+        ba.arr = (self.capi.sd_batch * max(1, n))(*[mb.c for mb in ba.m])
+        ba.n = n
+        rows = sum(mb.c.num_rows for mb in ba.m)
+        if self.q1:
+            return oracle.run_q1(ba, self.lits[0], threads), rows
+        total, matched = oracle.run_q6(ba, self.lits, threads)
+        return [[total, matched]], rows
+
+    def parity_check(self, gpu_final_rows, threads):
+        """Every rank scans ITS host copy with the oracle; partial rows are gathered and merged like the reference's final
+        stage (sums add, counts add, avg = sum / count); rank 0 compares with the GPU's final rows over the same bytes:
+        integers (COUNT) bit-exact, DOUBLE within 1e-6 relative."""
+        import math
+        t0 = time.perf_counter()
+        if getattr(self, "_oracle_parts", None) is None:
+            mine, rows = self.oracle_partials(threads)
+            parts, row_counts = [mine], [rows]
+            if self.world > 1:
+                parts, row_counts = [None] * self.world, [None] * self.world
+                self.dist.all_gather_object(parts, mine)
+                self.dist.all_gather_object(row_counts, rows)
+            self._oracle_parts = (parts, row_counts)
+        parts, row_counts = self._oracle_parts
+        if self.q1:
+            acc = {}
+            for part in parts:
+                for r in part:
+                    k = (r[0], r[1])
+                    if k not in acc:
+                        acc[k] = list(r[2:])
+                    else:
+                        a = acc[k]
+                        for i, v in enumerate(r[2:]):
+                            a[i] += v
+            want = []
+            for (k0, k1), a in acc.items():
+                sq, sp, sdp, sc, aq_s, aq_c, ap_s, ap_c, ad_s, ad_c, cnt = a
+                want.append([k0, k1, sq, sp, sdp, sc, aq_s / aq_c, ap_s / ap_c, ad_s / ad_c, cnt])
+            nkeys = 2
+        else:
+            tot, matched = None, 0
+            for part in parts:
+                t, m = part[0]
+                matched += m
+                if t is not None:
+                    tot = t if tot is None else tot + t
+            want = [[tot]]
+            nkeys = 0
+        got = [list(r) for r in gpu_final_rows]
+        key = lambda r: tuple(r[:nkeys])
+        got.sort(key=key)
+        want.sort(key=key)
+        ok = len(got) == len(want)
+        max_rel, ints_exact = 0.0, True
+        if ok:
+            for g, w in zip(got, want):
+                if key(g) != key(w) or len(g) != len(w):
+                    ok = False
+                    break
+                for x, y in zip(g[nkeys:], w[nkeys:]):
+                    if isinstance(x, float) or isinstance(y, float):
+                        if x is None or y is None:
+                            ok = ok and x is y
+                            continue
+                        rel = 0.0 if x == y else abs(x - y) / max(abs(x), abs(y))
+                        if math.isnan(rel):
+                            ok = ok and math.isnan(x) and math.isnan(y)
+                            continue
+                        max_rel = max(max_rel, rel)
+                    elif x != y:
+                        ints_exact = False
+        ok = ok and ints_exact and max_rel <= 1e-6
+        return {"ok": bool(ok), "rows": int(sum(row_counts)), "groups": len(want), "max_rel_err": max_rel, "counts_exact": bool(ints_exact),
+                "tolerance": 1e-6, "oracle_seconds": round(time.perf_counter() - t0, 2),
+                "checker": "oracle/scan_oracle.c generated-loop layer on the host cores over the same ColumnBatch bytes (every rank its shard, "
+                           "partials merged); GPU side = the e2e step through sd_batch_submit over exactly those bytes, after the exchange",
+                "gpu": [[x.decode() if isinstance(x, bytes) else x for x in r] for r in got[:8]],
+                "oracle": [[x.decode() if isinstance(x, bytes) else x for x in r] for r in want[:8]]}
 
 
 def timed_steps(torch, dist, world, fn, warmup, steps):
@@ -475,9 +570,17 @@ def main():
     api = capi.product_api()
     api.check(api.init(local_rank))
 
+    comm = None
+    if world > 1:   # sd_comm: NCCL inside libsnappygpu.so; torch.distributed only carries rank 0's 128-byte id
+        def bcast(b):
+            box = [b]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = capi.Comm(api, rank, world, local_rank, bcast)
+
     q1 = args.workload == "q1"
     total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
-    main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank, args.scaling)
+    main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank, args.scaling, comm)
     job_rows = main_run.job_rows   # rows all ranks scan per step
 
     def job_sum(x):   # sum of a per-rank count over the job
@@ -514,11 +617,33 @@ def main():
                                "(read + write), which a read-only stream like this scan can exceed: frac > 1 is not an error"}
     out["hbm_gbs_whole_job"] = job_rows * (40 if q1 else 28) / (ms / args.steps / 1e3) / 1e9
 
-    if not args.no_e2e:
+    threads = cgroup_cpu_limit() or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    parity_failed = False
+
+    def run_parity(run, tag, resident_rows):
+        """GPU (e2e step over the host copy) vs oracle over the same bytes; plus the resident-store result when it covers the same rows."""
+        nonlocal parity_failed
+        fs = run.desc.final_schema()
+        pc = run.parity_check(capi.parse_row_stream(run.final_raw, fs), threads)
+        same_rows = job_sum(1 if run.e2e_rows == run.local_rows else 0) == world
+        if same_rows:
+            rc = run.parity_check(resident_rows, threads)
+            pc["resident_store_result"] = {"ok": rc["ok"], "max_rel_err": rc["max_rel_err"], "counts_exact": rc["counts_exact"]}
+            pc["ok"] = pc["ok"] and rc["ok"]
+        else:
+            pc["resident_store_result"] = None
+        pc["workload"] = tag
+        parity_failed = parity_failed or not pc["ok"]
+        return pc
+
+    if not args.no_e2e or not args.no_parity:
         main_run.prepare_host_copy()
+    if not args.no_e2e:
         e_steps = max(1, args.e2e_steps)
         e2e_job_rows = job_sum(main_run.e2e_rows)
         ems = timed_steps(torch, dist, world, main_run.step_e2e, 1, e_steps)
+        if not args.no_parity:
+            out["parity_check"] = run_parity(main_run, "q1 sf100" if q1 else "q6 sf10", final_rows)
         out["e2e"] = {"value": e2e_job_rows * e_steps / (ems / 1e3), "unit": "rows/s", "h2d_bytes_per_step": main_run.h2d_bytes,
                       "rows_per_step": e2e_job_rows,
                       "d2h_bytes_per_step": 4096 if world > 1 else 1024, "ms_per_step": ems / e_steps, "steps": e_steps,
@@ -535,9 +660,17 @@ def main():
                               "ms_per_step": lms / e_steps, "steps": e_steps, "compressed_buffers": main_run.lz4_compressed_buffers,
                               "note": "same as e2e but the host holds the buffers in their stored LZ4 form ([-1][len][block], only when "
                                       "they shrink to <= 75 %); blocks are expanded on the device (sd_lz4.cu); not the headline e2e"}
+            if not args.no_parity:   # the stored-LZ4 leg's result against the same oracle answer
+                lp = main_run.parity_check(capi.parse_row_stream(main_run.final_raw, main_run.desc.final_schema()), threads)
+                out["e2e_lz4"]["parity_ok"] = lp["ok"]
+                out["e2e_lz4"]["max_rel_err"] = lp["max_rel_err"]
+                parity_failed = parity_failed or not lp["ok"]
         if rank == 0 and not args.no_cpu:
             cb, res = main_run.cpu_baseline(args.cpu_seconds)
             out["cpu_baseline"] = cb
+    elif not args.no_parity:
+        main_run.step_e2e()
+        out["parity_check"] = run_parity(main_run, "q1 sf100" if q1 else "q6 sf10", final_rows)
     if rank == 0:
         out["result_check"] = {"groups": len(final_rows), "first_row": [x.decode() if isinstance(x, bytes) else x for x in final_rows[0]] if final_rows else None}
 
@@ -547,7 +680,7 @@ def main():
         torch.cuda.empty_cache()
         oq1 = not q1
         ototal = SF100_ROWS if oq1 else SF10_ROWS
-        other = QueryRun(api, torch, dist, oq1, ototal, rank, world, local_rank, args.scaling)
+        other = QueryRun(api, torch, dist, oq1, ototal, rank, world, local_rank, args.scaling, comm)
         oms = timed_steps(torch, dist, world, other.step_resident, args.warmup, args.steps)
         okms = other.kernel_ns / 1e6 / max(1, other.launches)
         oalgo = other.algo_bytes / max(1, other.launches)
@@ -556,11 +689,20 @@ def main():
                        "roofline": {"bound": "hbm", "achieved": oalgo / (okms / 1e3) / 1e9 if okms > 0 else 0.0, "peak": peak,
                                     "unit": "GB/s", "frac": (oalgo / (okms / 1e3) / 1e9 / peak) if okms > 0 else 0.0,
                                     "kernel_ms_per_launch": okms}}
+        if not args.no_parity:
+            ofinal = capi.parse_row_stream(other.final_raw, other.desc.final_schema())
+            other.prepare_host_copy()
+            other.step_e2e()
+            out["also"]["parity_check"] = run_parity(other, "q1 sf100" if oq1 else "q6 sf10", ofinal)
+    if comm is not None:
+        out["exchange"] = dict(comm.info(), kind="sd_plan_exchange: ncclAllGather of partial rows by value inside libsnappygpu.so + merge on every rank")
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit("parity_check failed: GPU result differs from the oracle beyond the tolerance (see the JSON line)")
 
 
 if __name__ == "__main__":

@@ -213,6 +213,34 @@ int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t l
 int sd_plan_final_merge(sd_plan* p, const void* partial_rows, int64_t len,
                         void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
 
+/* partial rows of several partitions -> ONE merged set of partial rows (same schema; a combiner in front of the final
+ * stage).  sd_plan_exchange uses it after gathering every rank's rows. */
+int sd_partial_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len,
+                     void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);   /* host only */
+int sd_plan_partial_merge(sd_plan* p, const void* partial_rows, int64_t len,
+                          void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
+
+/* ---- the cross-partition exchange: partial -> Exchange -> final as SnappyStrategies plans it
+ *      (core/.../SnappyStrategies.scala:566-604).  One partition (= one sd_plan on one GPU) per rank; the exchange is ONE
+ *      ncclAllGather over NVLink of every rank's partial rows BY VALUE, merged on every rank.  NCCL is dlopen'ed
+ *      (libnccl.so.2, or $SD_NCCL_LIB); the caller only transports the 128-byte unique id from rank 0 to the others
+ *      (torch.distributed / Spark broadcast / any RPC). ------------------------------------------------------------ */
+typedef struct sd_comm sd_comm;
+#define SD_COMM_ID_BYTES 128
+int sd_comm_unique_id(void* out_id);                         /* rank 0 */
+int sd_comm_create(const void* id, int32_t rank, int32_t world, int32_t device, sd_comm** out);   /* collective */
+void sd_comm_destroy(sd_comm* c);
+/* [0] world [1] bytes per rank of the gather slot [2] all-gathers issued [3] times the slot had to grow */
+int sd_comm_info(sd_comm* c, int64_t out[4]);
+/* collective, after this execution's scans: gathers + merges; sd_plan_finish then returns the MERGED partial rows
+ * (identical on every rank; any number of groups -- the gather slot grows in lock step on all ranks) */
+int sd_plan_exchange(sd_plan* p, sd_comm* c);
+/* one execution of a cached plan over a resident store in one call:
+ * reset -> set_literals -> scan_store -> [exchange when comm != NULL] -> finish */
+int sd_plan_execute_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32_t nbuckets,
+                          const sd_literal* lits, int32_t nlits, sd_comm* comm,
+                          void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows);
+
 /* ---- export of the dense partial table for an on-device exchange (NCCL all-reduce over NVLink of
  *      per-GPU partials).  Writes nslots int64/double words per group into dev_out
  *      (device pointer) on the plan's stream.  Only for plans without string/hash keys. ---------- */

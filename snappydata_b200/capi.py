@@ -206,6 +206,15 @@ class Api:
         self.plan_final_merge = fn("plan_final_merge", C.c_int, vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
         self.plan_partials_layout = fn("plan_partials_layout", C.c_int, vp, C.POINTER(i32), C.POINTER(i32),
                                        C.POINTER(i32), required=False)
+        self.partial_merge = fn("partial_merge", C.c_int, C.POINTER(sd_plan_desc), vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
+        self.plan_partial_merge = fn("plan_partial_merge", C.c_int, vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
+        self.comm_unique_id = fn("comm_unique_id", C.c_int, vp, required=False)
+        self.comm_create = fn("comm_create", C.c_int, vp, i32, i32, i32, C.POINTER(vp), required=False)
+        self.comm_destroy = fn("comm_destroy", None, vp, required=False)
+        self.comm_info = fn("comm_info", C.c_int, vp, C.POINTER(i64), required=False)
+        self.plan_exchange = fn("plan_exchange", C.c_int, vp, vp, required=False)
+        self.plan_execute_store = fn("plan_execute_store", C.c_int, vp, vp, C.POINTER(i32), i32, C.POINTER(sd_literal), i32, vp,
+                                     vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
         self.plan_export_partials = fn("plan_export_partials", C.c_int, vp, vp, i64, required=False)
         self.plan_import_partials = fn("plan_import_partials", C.c_int, vp, vp, i64, required=False)
 
@@ -323,14 +332,44 @@ class Plan:
         self.h = h
         self._lits = None
 
-    def set_literals(self, values: Sequence[object]):
+    def literal_array(self, values: Sequence[object]):
         n = len(values)
         arr = (sd_literal * max(1, n))()
         for i, v in enumerate(values):
             arr[i] = make_literal(self.desc.literal_types_py[i], v)
+        return arr
+
+    def set_literals(self, values: Sequence[object]):
+        arr = self.literal_array(values)
         self._lits = arr
-        self.api.check(self.api.plan_set_literals(self.h, arr, n))
+        self.api.check(self.api.plan_set_literals(self.h, arr, len(values)))
         return self
+
+    def execute_store_raw(self, store: "Store", lit_array, nlits: int, comm: Optional["Comm"] = None) -> bytes:
+        """One execution of the cached plan over a resident store in ONE C call (sd_plan_execute_store): reset, literals,
+        scan, the NCCL exchange when `comm` is given, partial rows (merged over the ranks with `comm`)."""
+        if getattr(self, "_out_buf", None) is None:
+            self._out_buf = C.create_string_buffer(1 << 14)
+            self._out_len, self._out_rows = C.c_int64(), C.c_int64()
+        rc = self.api.plan_execute_store(self.h, store.h, None, 0, lit_array, nlits, comm.h if comm is not None else None,
+                                         self._out_buf, len(self._out_buf), C.byref(self._out_len), C.byref(self._out_rows))
+        if rc == SD_ERR_OVERFLOW:   # the execution is complete; only the caller's buffer was too small
+            self._out_buf = C.create_string_buffer(int(self._out_len.value) + 64)
+            return self.finish_raw()
+        if rc:
+            self.api.check(rc)
+        return C.string_at(self._out_buf, self._out_len.value)
+
+    def exchange(self, comm: "Comm"):
+        self.api.check(self.api.plan_exchange(self.h, comm.h))
+        return self
+
+    def partial_merge_raw(self, partial_raw: bytes) -> bytes:
+        cap = max(1 << 14, 2 * len(partial_raw) + 1024)
+        buf = C.create_string_buffer(cap)
+        out_len, out_rows = C.c_int64(), C.c_int64()
+        self.api.check(self.api.plan_partial_merge(self.h, _buf_ptr(partial_raw), len(partial_raw), buf, cap, C.byref(out_len), C.byref(out_rows)))
+        return buf.raw[: out_len.value]
 
     def submit(self, batch: ColumnBatch):
         mb = MarshalledBatch(batch, self.desc.table_cols)
@@ -420,6 +459,43 @@ def final_merge(api: Api, desc: PlanDesc, partial_raw: bytes) -> List[List[objec
     api.check(api.final_merge(C.byref(desc.c), _buf_ptr(partial_raw), len(partial_raw), buf, cap,
                               C.byref(out_len), C.byref(out_rows)))
     return parse_row_stream(buf.raw[: out_len.value], desc.final_schema())
+
+
+def partial_merge_raw(api: Api, desc: PlanDesc, partial_raw: bytes) -> bytes:
+    """Merged PARTIAL rows (host only: sd_partial_merge)."""
+    cap = max(1 << 16, 2 * len(partial_raw) + 1024)
+    buf = C.create_string_buffer(cap)
+    out_len, out_rows = C.c_int64(), C.c_int64()
+    api.check(api.partial_merge(C.byref(desc.c), _buf_ptr(partial_raw), len(partial_raw), buf, cap, C.byref(out_len), C.byref(out_rows)))
+    return buf.raw[: out_len.value]
+
+
+class Comm:
+    """sd_comm: the NCCL communicator of the partial -> final exchange.  `broadcast_bytes(b: bytes | None) -> bytes` moves
+    rank 0's 128-byte id to every rank (torch.distributed.broadcast_object_list, a Spark broadcast, ...)."""
+
+    def __init__(self, api: Api, rank: int, world: int, device: int, broadcast_bytes):
+        self.api = api
+        ident = None
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            api.check(api.comm_unique_id(buf))
+            ident = buf.raw
+        ident = broadcast_bytes(ident)
+        assert len(ident) == 128
+        h = C.c_void_p()
+        api.check(api.comm_create(ident, rank, world, device, C.byref(h)))
+        self.h = h
+
+    def info(self):
+        out = (C.c_int64 * 4)()
+        self.api.check(self.api.comm_info(self.h, out))
+        return {"world": out[0], "slot_bytes": out[1], "all_gathers": out[2], "regrows": out[3]}
+
+    def close(self):
+        if self.h:
+            self.api.comm_destroy(self.h)
+            self.h = None
 
 
 class Store:

@@ -262,8 +262,11 @@ struct sd_plan {
   int64_t pending_bytes = 0;
   // device state
   Arena scratch;                 // descriptors, aux tables (reset per execution)
-  uint64_t* d_result = nullptr;  // [result_cap] running result
-  uint64_t* h_pinned = nullptr;  // pinned host staging: identities out, result + counters back
+  // device state of one execution in ONE allocation so that it comes back in one copy:
+  //   d_state = [8 x uint64 counters][result_cap x uint64 running result]
+  uint64_t* d_state = nullptr;
+  uint64_t* d_result = nullptr;  // = d_state + STATE_HDR
+  uint64_t* h_pinned = nullptr;  // pinned host mirror of d_state: identities out, counters + result back
   size_t h_pinned_cap = 0;
   uint64_t* d_partials = nullptr;
   size_t partials_cap = 0;
@@ -320,19 +323,30 @@ std::string literal_key(const sd_plan* p) {
   return k;
 }
 
+constexpr size_t STATE_HDR = 8;   // uint64 words in front of the running result: [0] rows scanned, [1] rows passed
+
 int ensure_result(sd_plan* p, size_t entries) {
-  SD_CUDA(cudaSetDevice(p->device));
-  if (entries > p->result_cap) {
-    uint64_t* nr = nullptr;
-    SD_CUDA(cudaMalloc(&nr, entries * 8));
-    if (p->d_result) cudaFree(p->d_result);
-    p->d_result = nr;
-    p->result_cap = entries;
+  if (entries > p->result_cap || !p->d_state) {
+    SD_CUDA(cudaSetDevice(p->device));
+    const size_t cap = std::max<size_t>(entries, 64);
+    uint64_t* ns = nullptr;
+    SD_CUDA(cudaMalloc(&ns, (STATE_HDR + cap) * 8));
+    if (p->d_state) {   // the counters of the running execution move with the table
+      SD_CUDA(cudaStreamSynchronize(p->stream));
+      SD_CUDA(cudaMemcpy(ns, p->d_state, STATE_HDR * 8, cudaMemcpyDeviceToDevice));
+      cudaFree(p->d_state);
+    } else {
+      SD_CUDA(cudaMemset(ns, 0, STATE_HDR * 8));
+    }
+    p->d_state = ns;
+    p->d_result = ns + STATE_HDR;
+    p->d_counters = reinterpret_cast<unsigned long long*>(ns);
+    p->result_cap = cap;
     p->result_init = false;
   }
-  if (entries + 8 > p->h_pinned_cap) {
-    if (p->h_pinned) cudaFreeHost(p->h_pinned);
-    p->h_pinned_cap = entries + 8;
+  if (STATE_HDR + p->result_cap > p->h_pinned_cap) {
+    if (p->h_pinned) { SD_CUDA(cudaStreamSynchronize(p->stream)); cudaFreeHost(p->h_pinned); }
+    p->h_pinned_cap = STATE_HDR + p->result_cap;
     SD_CUDA(cudaMallocHost(&p->h_pinned, p->h_pinned_cap * 8));
   }
   return 0;
@@ -346,12 +360,13 @@ int init_result(sd_plan* p, int ngroups) {
   int rc = ensure_result(p, ne);
   if (rc) return rc;
   SD_CUDA(cudaStreamSynchronize(p->stream));   // the staging buffer may still be in use by a previous read-back
+  uint64_t* hid = p->h_pinned + STATE_HDR;
   for (size_t e = 0; e < ne; e++) {
     const int op = p->spec.slots[e % ns].op;
-    p->h_pinned[e] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+    hid[e] = op == SLOT_MIN_I64 ? 0x7fffffffffffffffull : op == SLOT_MAX_I64 ? 0x8000000000000000ull
                    : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull : op == SLOT_MAX_F64 ? 0xfff0000000000000ull : 0ull;
   }
-  SD_CUDA(cudaMemcpyAsync(p->d_result, p->h_pinned, ne * 8, cudaMemcpyHostToDevice, p->stream));
+  SD_CUDA(cudaMemcpyAsync(p->d_result, hid, ne * 8, cudaMemcpyHostToDevice, p->stream));
   p->result_init = true;
   return 0;
 }
@@ -654,6 +669,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     if (rc) return rc;
   }
   int table_mode = TABLE_PRIVATE;
+  int fresh = 0;
   int target_ctas = std::max(1, sp.min_ctas);
   if (sp.mode == MODE_GROUPS && ngroups <= REG_GROUPS_MAX && k == &p->kernel && p->kernel.staged && getenv("SD_TUNE_REG_GROUPS")) {
     // experimental (opt-in): measured slower than the private shared-memory tables, see DESIGN.md
@@ -701,8 +717,15 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     int rc = ensure_out(p, p->out_cap ? p->out_cap : (int64_t(1) << 20));
     if (rc) return rc;
   } else if (!p->result_init) {
-    int rc = init_result(p, ngroups);
-    if (rc) return rc;
+    if (table_mode == TABLE_GLOBAL_ATOMIC) {   // the kernel adds into the running result: it must hold the identities
+      int rc = init_result(p, ngroups);
+      if (rc) return rc;
+    } else {                                     // the last CTA overwrites it (ScanArgs.fresh): nothing to upload
+      int rc = ensure_result(p, ne);
+      if (rc) return rc;
+      fresh = 1;
+      p->result_init = true;
+    }
   } else if (ngroups != p->ngroups || memcmp(radix, p->radix, sizeof(radix)) != 0) {
     int rc = remap_result(p, p->radix, p->ngroups, radix, ngroups);
     if (rc) return rc;
@@ -746,6 +769,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.out_cap = p->out_cap;
   args.batch_base = batch_base;
   args.chunk_rows = p->chunk_rows;
+  args.fresh = fresh;
   memcpy(args.radix, radix, sizeof(radix));
   for (size_t i = 0; i < p->lits.size(); i++) {
     args.lits.i[i] = p->lits[i].i;
@@ -1023,7 +1047,7 @@ int sdx_stats_pass(const sd_plan_desc* desc, const sd_literal* lits, int32_t nli
 
 int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   if (!out) return set_error(SD_ERR_INVALID, "sd_plan_create: null out");
-  std::unique_ptr<sd_plan> p(new sd_plan());
+  std::unique_ptr<sd_plan, void (*)(sd_plan*)> p(new sd_plan(), sd_plan_destroy);   // a failure below releases what was created
   std::string err;
   int rc = analyze_plan(desc, p->spec, err);
   if (rc) return set_error(rc, "sd_plan_create: %s", err.c_str());
@@ -1047,9 +1071,9 @@ int sd_plan_create(const sd_plan_desc* desc, sd_plan** out) {
   SD_CUDA(cudaEventCreate(&p->ev_start));
   SD_CUDA(cudaEventCreate(&p->ev_stop));
   SD_CUDA(cudaMalloc(&p->d_ticket, 64));
-  SD_CUDA(cudaMalloc(&p->d_counters, 64));
   SD_CUDA(cudaMemset(p->d_ticket, 0, 64));
-  SD_CUDA(cudaMemset(p->d_counters, 0, 64));
+  rc = ensure_result(p.get(), 64);   // d_state: counters + room for a small group table
+  if (rc) return rc;
   p->scratch.device = p->device;
   p->scratch.slab_bytes = size_t(8) << 20;
   p->cache_arena.device = p->device;
@@ -1187,35 +1211,19 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks, c.needs_slow, &c.batches);
 }
 
-int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
-  if (!p || !out_len) return set_error(SD_ERR_INVALID, "sd_plan_finish: null argument");
-  SD_CUDA(cudaSetDevice(p->device));
-  int rc = flush_pending(p);
-  if (rc) return rc;
-  if (p->priv) { rc = store_lz4_check(p->priv); if (rc) return rc; }   // a corrupt compressed buffer fails the execution
+// partial rows of this execution's dense / no-key result -> p->finished_rows
+static int finish_dense(sd_plan* p) {
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
-  if (sp.mode == MODE_HASH || sp.mode == MODE_PROJECT) {
-    if (p->finished_nrows < 0) {
-      rc = sp.mode == MODE_HASH ? finish_hash(p) : finish_project(p);
-      if (rc) return rc;
-    }
-    p->metrics[0] = p->finished_nrows;
-    *out_len = (int64_t)p->finished_rows.size();
-    if (out_nrows) *out_nrows = p->finished_nrows;
-    if ((int64_t)p->finished_rows.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", p->finished_rows.size());
-    if (!p->finished_rows.empty()) memcpy(out_rows, p->finished_rows.data(), p->finished_rows.size());
-    return 0;
-  }
+  int rc = 0;
   if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
   const size_t ne = (size_t)p->ngroups * ns;
   rc = ensure_result(p, ne);
   if (rc) return rc;
-  SD_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_result, ne * 8, cudaMemcpyDeviceToHost, p->stream));
-  SD_CUDA(cudaMemcpyAsync(p->h_pinned + ne, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_state, (STATE_HDR + ne) * 8, cudaMemcpyDeviceToHost, p->stream));   // counters + table in one copy
   SD_CUDA(cudaStreamSynchronize(p->stream));
-  const uint64_t* h = p->h_pinned;
-  const unsigned long long counters[2] = {p->h_pinned[ne], p->h_pinned[ne + 1]};
+  const uint64_t* h = p->h_pinned + STATE_HDR;
+  const unsigned long long counters[2] = {p->h_pinned[0], p->h_pinned[1]};
   if (p->have_timing) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms;
@@ -1227,12 +1235,14 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   std::vector<int> types;
   for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
   for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
-  std::vector<uint8_t> out;
+  std::vector<uint8_t>& out = p->finished_rows;
+  out.clear();
   int64_t nrows = 0;
+  std::vector<HVal> vals;
   for (int g = 0; g < p->ngroups; g++) {
     const uint64_t* sv = &h[(size_t)g * ns];
     if (nk > 0 && sv[sp.rows_slot] == 0) continue;   // group never seen
-    std::vector<HVal> vals;
+    vals.clear();
     int rem = g, idx[MAX_KEYS];
     for (int k = nk - 1; k >= 0; k--) { idx[k] = rem % p->radix[k]; rem /= p->radix[k]; }
     for (int k = 0; k < nk; k++) {
@@ -1244,11 +1254,32 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
     emit_unsafe_row(out, types, vals);
     nrows++;
   }
-  p->metrics[0] = nrows;
-  *out_len = (int64_t)out.size();
-  if (out_nrows) *out_nrows = nrows;
-  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", out.size());
-  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
+  p->finished_nrows = nrows;
+  return 0;
+}
+
+// run what is pending and materialise this partition's partial rows in p->finished_rows (once per execution)
+static int collect_partial_rows(sd_plan* p) {
+  SD_CUDA(cudaSetDevice(p->device));
+  int rc = flush_pending(p);
+  if (rc) return rc;
+  if (p->priv) { rc = store_lz4_check(p->priv); if (rc) return rc; }   // a corrupt compressed buffer fails the execution
+  if (p->finished_nrows >= 0) return 0;
+  const int mode = p->spec.mode;
+  rc = mode == MODE_HASH ? finish_hash(p) : mode == MODE_PROJECT ? finish_project(p) : finish_dense(p);
+  if (rc) return rc;
+  p->metrics[0] = p->finished_nrows;
+  return 0;
+}
+
+int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+  if (!p || !out_len) return set_error(SD_ERR_INVALID, "sd_plan_finish: null argument");
+  int rc = collect_partial_rows(p);
+  if (rc) return rc;
+  *out_len = (int64_t)p->finished_rows.size();
+  if (out_nrows) *out_nrows = p->finished_nrows;
+  if ((int64_t)p->finished_rows.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", p->finished_rows.size());
+  if (!p->finished_rows.empty()) memcpy(out_rows, p->finished_rows.data(), p->finished_rows.size());
   return 0;
 }
 
@@ -1300,7 +1331,7 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
   if (p->ev_stop) cudaEventDestroy(p->ev_stop);
-  if (p->d_result) cudaFree(p->d_result);
+  if (p->d_state) cudaFree(p->d_state);
   if (p->h_pinned) cudaFreeHost(p->h_pinned);
   if (p->d_partials) cudaFree(p->d_partials);
   hash_free(p);
@@ -1308,7 +1339,6 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->d_out_count) cudaFree(p->d_out_count);
   if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);
-  if (p->d_counters) cudaFree(p->d_counters);
   if (p->priv) sd_store_destroy(p->priv);
   delete p;
 }
@@ -1324,6 +1354,7 @@ int sd_plan_partials_layout(sd_plan* p, int32_t* ngroups, int32_t* nslots, int32
 }
 int sd_plan_export_partials(sd_plan* p, void* dev_out, int64_t cap_bytes) {
   if (!p || !dev_out) return set_error(SD_ERR_INVALID, "null argument");
+  if (p->spec.mode == MODE_HASH || p->spec.mode == MODE_PROJECT) return set_error(SD_ERR_UNSUPPORTED, "dense partials exist only for no-key / dictionary-keyed plans");
   SD_CUDA(cudaSetDevice(p->device));
   int rc = flush_pending(p);
   if (rc) return rc;
@@ -1335,6 +1366,8 @@ int sd_plan_export_partials(sd_plan* p, void* dev_out, int64_t cap_bytes) {
 }
 int sd_plan_import_partials(sd_plan* p, const void* dev_in, int64_t bytes) {
   if (!p || !dev_in) return set_error(SD_ERR_INVALID, "null argument");
+  if (p->spec.mode == MODE_HASH || p->spec.mode == MODE_PROJECT) return set_error(SD_ERR_UNSUPPORTED, "dense partials exist only for no-key / dictionary-keyed plans");
+  p->finished_nrows = -1;
   SD_CUDA(cudaSetDevice(p->device));
   const size_t want = (size_t)p->ngroups * p->spec.slots.size() * 8;
   if ((size_t)bytes != want) return set_error(SD_ERR_INVALID, "import expects %zu bytes", want);
@@ -1417,9 +1450,22 @@ int sd_rows_submit(sd_plan* p, const void* rows, int64_t len, int32_t nrows) {
   return rc;
 }
 
-// ---- final merge (host; payload is a handful of rows) -------------------------------------------------
-static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
-                            int64_t* out_len, int64_t* out_nrows);
+// ---- merge of partial rows (host; payload is a handful of rows) ------------------------------------------
+// evaluate = true : SnappyHashAggregateExec(Final) / CollectAggregateExec: merged buffers -> results (avg = sum / count)
+// evaluate = false: the merged PARTIAL rows (keys ++ buffers), what a combiner in front of the final stage emits
+static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, bool evaluate, std::vector<uint8_t>& out, int64_t* out_nrows);
+
+static int merge_to_caller(const PlanSpec& sp, const void* partial_rows, int64_t len, bool evaluate, void* out_rows, int64_t cap,
+                           int64_t* out_len, int64_t* out_nrows) {
+  if (!out_len) return set_error(SD_ERR_INVALID, "merge: null out_len");
+  std::vector<uint8_t> out;
+  int rc = merge_rows_impl(sp, partial_rows, len, evaluate, out, out_nrows);
+  if (rc) return rc;
+  *out_len = (int64_t)out.size();
+  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "merge: output needs %zu bytes", out.size());
+  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
+  return 0;
+}
 
 int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
                    int64_t* out_len, int64_t* out_nrows) {
@@ -1427,18 +1473,45 @@ int sd_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t l
   std::string err;
   int rc = analyze_plan(desc, sp, err);
   if (rc) return set_error(rc, "sd_final_merge: %s", err.c_str());
-  return final_merge_impl(sp, partial_rows, len, out_rows, cap, out_len, out_nrows);
+  return merge_to_caller(sp, partial_rows, len, true, out_rows, cap, out_len, out_nrows);
 }
 
 /* same merge, reusing the analysis of an existing plan handle (no per-call plan analysis) */
 int sd_plan_final_merge(sd_plan* p, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
                         int64_t* out_len, int64_t* out_nrows) {
   if (!p) return set_error(SD_ERR_INVALID, "null plan");
-  return final_merge_impl(p->spec, partial_rows, len, out_rows, cap, out_len, out_nrows);
+  return merge_to_caller(p->spec, partial_rows, len, true, out_rows, cap, out_len, out_nrows);
 }
 
-static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
-                            int64_t* out_len, int64_t* out_nrows) {
+/* partial rows of several partitions -> one merged set of PARTIAL rows (same schema) */
+int sd_partial_merge(const sd_plan_desc* desc, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                     int64_t* out_len, int64_t* out_nrows) {
+  PlanSpec sp;
+  std::string err;
+  int rc = analyze_plan(desc, sp, err);
+  if (rc) return set_error(rc, "sd_partial_merge: %s", err.c_str());
+  return merge_to_caller(sp, partial_rows, len, false, out_rows, cap, out_len, out_nrows);
+}
+int sd_plan_partial_merge(sd_plan* p, const void* partial_rows, int64_t len, void* out_rows, int64_t cap,
+                          int64_t* out_len, int64_t* out_nrows) {
+  if (!p) return set_error(SD_ERR_INVALID, "null plan");
+  return merge_to_caller(p->spec, partial_rows, len, false, out_rows, cap, out_len, out_nrows);
+}
+
+static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t len, bool evaluate, std::vector<uint8_t>& out, int64_t* out_nrows) {
+  out.clear();
+  if (sp.mode == MODE_PROJECT) {   // projected rows of several partitions: concatenation
+    const uint8_t* r = reinterpret_cast<const uint8_t*>(partial_rows);
+    int64_t pos = 0, n = 0;
+    while (pos + 8 <= len) {
+      const int64_t sz = rd_i64(r + pos);
+      if (sz < 0 || pos + 8 + sz > len) return set_error(SD_ERR_INVALID, "merge: bad row size");
+      pos += 8 + sz; n++;
+    }
+    out.assign(r, r + pos);
+    if (out_nrows) *out_nrows = n;
+    return 0;
+  }
   const int nk = (int)sp.keys.size();
   std::vector<int> types;
   for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
@@ -1449,12 +1522,13 @@ static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_
   std::map<std::string, size_t> index;
   const uint8_t* r = reinterpret_cast<const uint8_t*>(partial_rows);
   int64_t pos = 0;
+  std::vector<HVal> f((size_t)n);
+  std::string key;
   while (pos + 8 <= len) {
     const int64_t sz = rd_i64(r + pos);
     if (sz < 0 || pos + 8 + sz > len) return set_error(SD_ERR_INVALID, "sd_final_merge: bad row size");
-    std::vector<HVal> f((size_t)n);
     for (int i = 0; i < n; i++) if (!unsafe_field(r + pos + 8, sz, n, i, types[i], &f[i])) return set_error(SD_ERR_INVALID, "sd_final_merge: malformed partial row");
-    std::string key;
+    key.clear();
     for (int k = 0; k < nk; k++) {
       key.push_back(f[k].isnull ? 'N' : 'V');
       if (!f[k].isnull) {
@@ -1463,7 +1537,7 @@ static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_
         else key.append(reinterpret_cast<const char*>(&f[k].i), 8);
       }
     }
-    auto it = index.find(key);
+    auto it = nk > 0 ? index.find(key) : (groups.empty() ? index.end() : index.begin());
     Group* g;
     if (it == index.end()) {
       index.emplace(key, groups.size());
@@ -1509,26 +1583,143 @@ static int final_merge_impl(const PlanSpec& sp, const void* partial_rows, int64_
     groups.push_back(g);
   }
   std::vector<int> otypes(types.begin(), types.begin() + nk);
-  for (auto& m : sp.agg_map) otypes.push_back(m.fn == SD_AGG_AVG ? (int)SD_DOUBLE : m.buf_type);
-  std::vector<uint8_t> out;
+  if (evaluate) { for (auto& m : sp.agg_map) otypes.push_back(m.fn == SD_AGG_AVG ? (int)SD_DOUBLE : m.buf_type); }
+  else otypes = types;
+  std::vector<HVal> vals;
   for (auto& g : groups) {
-    std::vector<HVal> vals(g.keys);
-    int k = 0;
-    for (auto& m : sp.agg_map) {
-      if (m.fn == SD_AGG_AVG) {   // Average.evaluateExpression: sum / count, NULL when count == 0
-        HVal v;
-        if (g.bufs[k + 1].i == 0) v.isnull = true; else v.d = g.bufs[k].d / (double)g.bufs[k + 1].i;
-        vals.push_back(v);
-        k += 2;
-      } else { vals.push_back(g.bufs[k]); k++; }
+    vals.assign(g.keys.begin(), g.keys.end());
+    if (!evaluate) vals.insert(vals.end(), g.bufs.begin(), g.bufs.end());
+    else {
+      int k = 0;
+      for (auto& m : sp.agg_map) {
+        if (m.fn == SD_AGG_AVG) {   // Average.evaluateExpression: sum / count, NULL when count == 0
+          HVal v;
+          if (g.bufs[k + 1].i == 0) v.isnull = true; else v.d = g.bufs[k].d / (double)g.bufs[k + 1].i;
+          vals.push_back(v);
+          k += 2;
+        } else { vals.push_back(g.bufs[k]); k++; }
+      }
     }
     emit_unsafe_row(out, otypes, vals);
   }
-  *out_len = (int64_t)out.size();
   if (out_nrows) *out_nrows = (int64_t)groups.size();
-  if ((int64_t)out.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_final_merge: output needs %zu bytes", out.size());
-  if (!out.empty()) memcpy(out_rows, out.data(), out.size());
   return 0;
+}
+
+// ---- the one exchange of the path: every partition's partial rows -> all ranks, merged ----------
+// Partial rows travel BY VALUE (keys as bytes, like the reference's shuffle of UnsafeRows between the partial and the
+// final HashAggregate, SnappyStrategies.scala:566-604): dictionary ids are private to a partition.  One ncclAllGather
+// of a fixed-capacity blob per rank [magic:4][flags:4][len:8][rows]; a rank whose rows do not fit says so in its header,
+// every rank sees every header, so all of them grow the capacity and repeat in lock step (the capacity sticks).
+struct sd_comm {
+  void* nccl = nullptr;
+  int rank = 0, world = 1, device = 0;
+  size_t cap = 2048;               // bytes per rank, header included
+  uint8_t *d_send = nullptr, *d_recv = nullptr, *h_send = nullptr, *h_recv = nullptr;
+  size_t alloc_cap = 0;
+  int64_t exchanges = 0, regrows = 0;
+};
+static int comm_buffers(sd_comm* c) {
+  if (c->alloc_cap >= c->cap) return 0;
+  if (c->d_send) { cudaFree(c->d_send); cudaFree(c->d_recv); cudaFreeHost(c->h_send); cudaFreeHost(c->h_recv); c->d_send = c->d_recv = c->h_send = c->h_recv = nullptr; }
+  SD_CUDA(cudaMalloc(&c->d_send, c->cap));
+  SD_CUDA(cudaMalloc(&c->d_recv, c->cap * (size_t)c->world));
+  SD_CUDA(cudaMallocHost(&c->h_send, c->cap));
+  SD_CUDA(cudaMallocHost(&c->h_recv, c->cap * (size_t)c->world));
+  c->alloc_cap = c->cap;
+  return 0;
+}
+constexpr uint32_t COMM_MAGIC = 0x53445831u;   // "SDX1"
+
+int sd_comm_unique_id(void* out_id) {
+  if (!out_id) return set_error(SD_ERR_INVALID, "sd_comm_unique_id: null argument");
+  return comm_unique_id(out_id);
+}
+int sd_comm_create(const void* id, int32_t rank, int32_t world, int32_t device, sd_comm** out) {
+  if (!id || !out || world < 1 || rank < 0 || rank >= world) return set_error(SD_ERR_INVALID, "sd_comm_create: bad arguments");
+  SD_CUDA(cudaSetDevice(device));
+  std::unique_ptr<sd_comm> c(new sd_comm());
+  c->rank = rank; c->world = world; c->device = device;
+  int rc = comm_init(id, rank, world, &c->nccl);
+  if (rc) return rc;
+  *out = c.release();
+  return 0;
+}
+void sd_comm_destroy(sd_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  comm_destroy(c->nccl);
+  if (c->d_send) { cudaFree(c->d_send); cudaFree(c->d_recv); cudaFreeHost(c->h_send); cudaFreeHost(c->h_recv); }
+  delete c;
+}
+int sd_comm_info(sd_comm* c, int64_t out[4]) {
+  if (!c || !out) return set_error(SD_ERR_INVALID, "null argument");
+  out[0] = c->world; out[1] = (int64_t)c->cap; out[2] = c->exchanges; out[3] = c->regrows;
+  return 0;
+}
+
+int sd_plan_exchange(sd_plan* p, sd_comm* c) {
+  if (!p || !c) return set_error(SD_ERR_INVALID, "sd_plan_exchange: null argument");
+  if (c->device != p->device) return set_error(SD_ERR_INVALID, "communicator lives on device %d, plan on %d", c->device, p->device);
+  int rc = collect_partial_rows(p);
+  if (rc) return rc;
+  const std::vector<uint8_t>& mine = p->finished_rows;
+  for (;;) {
+    rc = comm_buffers(c);
+    if (rc) return rc;
+    const size_t room = c->cap - 16, n = mine.size(), sent = std::min(n, room);
+    const uint32_t hdr32[2] = {COMM_MAGIC, n > room ? 1u : 0u};
+    const uint64_t len64 = n;
+    memcpy(c->h_send, hdr32, 8);
+    memcpy(c->h_send + 8, &len64, 8);
+    if (sent) memcpy(c->h_send + 16, mine.data(), sent);
+    SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16 + sent, cudaMemcpyHostToDevice, p->stream));
+    rc = comm_all_gather_bytes(c->nccl, c->d_send, c->d_recv, c->cap, p->stream);
+    if (rc) return rc;
+    SD_CUDA(cudaMemcpyAsync(c->h_recv, c->d_recv, c->cap * (size_t)c->world, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaStreamSynchronize(p->stream));
+    c->exchanges++;
+    size_t maxlen = 0;
+    for (int r = 0; r < c->world; r++) {
+      const uint8_t* h = c->h_recv + (size_t)r * c->cap;
+      uint32_t magic; uint64_t l;
+      memcpy(&magic, h, 4); memcpy(&l, h + 8, 8);
+      if (magic != COMM_MAGIC) return set_error(SD_ERR_CUDA, "sd_plan_exchange: bad header from rank %d", r);
+      maxlen = std::max<size_t>(maxlen, (size_t)l);
+    }
+    if (maxlen <= room) break;
+    size_t ncap = c->cap;
+    while (ncap - 16 < maxlen) ncap *= 2;
+    c->cap = ncap;   // every rank computes the same value from the same headers
+    c->regrows++;
+  }
+  std::vector<uint8_t> all;
+  for (int r = 0; r < c->world; r++) {
+    const uint8_t* h = c->h_recv + (size_t)r * c->cap;
+    uint64_t l; memcpy(&l, h + 8, 8);
+    all.insert(all.end(), h + 16, h + 16 + l);
+  }
+  std::vector<uint8_t> merged;
+  int64_t nrows = 0;
+  rc = merge_rows_impl(p->spec, all.data(), (int64_t)all.size(), false, merged, &nrows);
+  if (rc) return rc;
+  p->finished_rows.swap(merged);
+  p->finished_nrows = nrows;
+  return 0;
+}
+
+// one execution of a cached plan over a resident store, in one call: reset -> literals -> scan -> [exchange] ->
+// partial rows (merged over all ranks when `comm` is given).  What a re-executed cached plan does per query in the
+// reference (SnappySession plan cache: new literal values, same generated code).
+int sd_plan_execute_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32_t nbuckets, const sd_literal* lits, int32_t nlits,
+                          sd_comm* comm, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+  int rc = sd_plan_reset(p);
+  if (rc) return rc;
+  if (lits || nlits) { rc = sd_plan_set_literals(p, lits, nlits); if (rc) return rc; }
+  rc = sd_plan_scan_store(p, s, bucket_ids, nbuckets);
+  if (rc) return rc;
+  if (comm) { rc = sd_plan_exchange(p, comm); if (rc) return rc; }
+  return sd_plan_finish(p, out_rows, cap, out_len, out_nrows);
 }
 
 }  // extern "C"

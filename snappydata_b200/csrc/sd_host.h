@@ -58,6 +58,12 @@ struct Lz4Job { const uint8_t* src; uint8_t* dst; int64_t src_len; int64_t dst_l
 int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t want);
 int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error);
 
+// ---- NCCL behind sd_comm (sd_nccl.cpp; dlopen'ed) --------------------------------------------------------
+int comm_unique_id(void* out128);
+int comm_init(const void* id128, int rank, int world, void** out);
+void comm_destroy(void* c);
+int comm_all_gather_bytes(void* c, const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t stream);
+
 // ---- device memory arena: bump allocation out of large slabs ---------------------------------------
 struct Arena {
   int device = 0;

@@ -1046,7 +1046,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
       const int op = PLAN::slot_op_rt(e % NSLOT);
       uint64_t v = slot_identity(op);
       for (unsigned bk = 0; bk < gridDim.x; bk++) v = slot_combine(op, v, __ldcg(&args.partials[(size_t)bk * NE + e]));
-      args.result[e] = slot_combine(op, args.result[e], v);
+      args.result[e] = args.fresh ? v : slot_combine(op, args.result[e], v);
     }
   }
   if (is_last && tid == 0) *args.ticket = 0;

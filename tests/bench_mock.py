@@ -32,6 +32,9 @@ class FakeApi:
     def check(self, rc): assert rc == 0
     def init(self, d): return 0
     def batch_submit(self, h, b): return 0
+    def plan_metrics(self, h, m):
+        m[6], m[7], m[9] = 3_500_000, 1, 24_000_000_000
+        return 0
 class FakeStore:
     def __init__(self, api, schema, device=0): self.h = 0; self.n = 0
     def gen_lineitem(self, first_row, nrows, rpb, nb, seed, mask):
@@ -48,9 +51,16 @@ class FakePlan:
     def set_literals(self, l): return self
     def scan_store(self, s): return self
     def finish_raw(self): return b""
+    def literal_array(self, vals): return None
+    def execute_store_raw(self, store, lit_array, nlits, comm=None): return b""
+    def exchange(self, comm): return self
     def metrics(self): return {"kernelLaunches": 1, "aggTimeNs": 3_500_000, "algorithmicBytes": 24_000_000_000}
     def final_merge_raw(self, raw): return b""
     def kernel_name(self): return "aot:Plan_x"
+class FakeComm:
+    def __init__(self, api, rank, world, device, bcast): self.h = 0; assert len(bcast(b"x" * 128)) == 128
+    def info(self): return {"world": WORLD, "slot_bytes": 2048, "all_gathers": 1, "regrows": 0}
+capi.Comm = FakeComm
 capi.product_api = lambda: FakeApi()
 capi.Store = FakeStore
 capi.Plan = FakePlan
@@ -63,6 +73,7 @@ capi.MarshalledBatch = FakeMB
 spec = importlib.util.spec_from_file_location("bench", __import__("os").path.join(ROOT, "bench.py")); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
 # C.byref(ln) -> our fake lib reads ._obj
 b.QueryRun.cpu_baseline = lambda self, s: ({"value": 1.0, "unit": "rows/s", "cores": 1, "kind": "port", "sample": "mock"}, None)
+b.QueryRun.parity_check = lambda self, rows, threads: {"ok": True, "rows": self.e2e_rows, "groups": 0, "max_rel_err": 0.0, "counts_exact": True}
 b.QueryRun.prepare_compressed_copy = lambda self, threads=32: (setattr(self, 'marshalled_lz4', self.marshalled), setattr(self, 'lz4_h2d_bytes', 1), setattr(self, 'lz4_compressed_buffers', 0))
 import os
 os.environ["BENCH_NO_CLOCKS"] = "1"
@@ -73,6 +84,7 @@ dist.init_process_group = lambda *a, **k: None
 dist.barrier = lambda: None
 dist.all_reduce = lambda t, op=None: t.mul_(WORLD) if op == dist.ReduceOp.SUM else t
 dist.destroy_process_group = lambda: None
+dist.broadcast_object_list = lambda box, src=0: None
 _tt = torch.tensor
 torch.tensor = lambda data, dtype=None, device=None: _tt(data, dtype=dtype)
 import snappydata_b200.exchange as ex

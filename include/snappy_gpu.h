@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2
 
 typedef enum sd_status {
   SD_OK = 0,
@@ -45,7 +45,8 @@ typedef enum sd_type {
   SD_DATE = 8,       /* int32 days since epoch       */
   SD_TIMESTAMP = 9,  /* int64 microseconds           */
   SD_STRING = 10,    /* UTF8String                   */
-  SD_DECIMAL = 11    /* precision <= 18, int64 unscaled (enc/Uncompressed.scala:95-98) */
+  SD_DECIMAL = 11    /* column values: precision <= 18, int64 unscaled (enc/Uncompressed.scala:95-98); aggregate
+                        buffers / results may be wider (SUM: DECIMAL(p+10,s), up to 128-bit unscaled), see sd_agg */
 } sd_type;
 
 /* One projected scan column (ColumnTableScan.output attribute). */
@@ -55,6 +56,7 @@ typedef struct sd_column {
                              (enc/ColumnEncoding.scala:817-822)                       */
   int32_t table_ordinal;  /* 0-based column of the table (ColumnFormatKey.columnIndex-1) */
   int32_t scale;          /* SD_DECIMAL scale; else 0                                 */
+  int32_t precision;      /* SD_DECIMAL precision (1..18 for a scan column); else 0   */
 } sd_column;
 
 /* Expression tree, flattened; children always precede parents.  Mirrors the Catalyst trees that
@@ -79,8 +81,17 @@ typedef enum sd_op {
 typedef struct sd_expr {
   int32_t op;    /* sd_op                     */
   int32_t type;  /* sd_type of the result     */
-  int32_t a, b, c;
+  int32_t a, b, c;   /* SD_DECIMAL-typed LIT / CAST nodes: c = (precision << 8) | scale of the node's type (a COL node takes
+                        them from its column, NEG from its child; DECIMAL literal values are unscaled at that scale) */
 } sd_expr;
+#define SD_DEC_PS(precision, scale) (((precision) << 8) | (scale))
+
+/* CAST follows Spark 2.1.1 Cast for the pairs the GPU path executes; every other pair is SD_ERR_UNSUPPORTED:
+ *   integral <-> integral (wraps), integral/fp -> fp, fp -> integral (Java (int)/(long): NaN -> 0, saturating),
+ *   numeric -> BOOLEAN (v != 0), BOOLEAN -> numeric (1 / 0), DECIMAL(p,s) -> DOUBLE/FLOAT (unscaled / 10^s),
+ *   integral -> DECIMAL(p,s) (v * 10^s, NULL when it does not fit p digits), DECIMAL(p1,s1) -> DECIMAL(p2,s2 >= s1)
+ *   (rescale, NULL when it does not fit).  Casts involving STRING, DATE or TIMESTAMP (other than the identity),
+ *   DECIMAL -> integral and down-scaling DECIMAL casts are refused. */
 
 /* Aggregate functions (Spark DeclarativeAggregate) and their partial
  * buffer fields, in the order SnappyHashAggregateExec lays them out
@@ -88,7 +99,11 @@ typedef struct sd_expr {
  *   COUNT_STAR / COUNT : [count LONG]
  *   SUM                : [sum LONG (integral input) | DOUBLE (float/double input)]   (nullable)
  *   AVG                : [sum DOUBLE, count LONG]
- *   MIN / MAX          : [value of the input type]                                   (nullable) */
+ *   MIN / MAX          : [value of the input type]                                   (nullable)
+ * DECIMAL(p,s) input (Spark 2.1.1 Sum / Average): SUM buffer and result DECIMAL(p+10,s); AVG buffers
+ * [sum DECIMAL(p+10,s), count LONG], result DECIMAL(p+4,s+4) = sum / count rounded HALF_UP.  In UnsafeRows a DECIMAL
+ * of precision <= 18 is its unscaled int64 in the fixed slot; wider ones are (offset << 32 | size) + the
+ * BigInteger two's-complement big-endian bytes in a 16-byte reserved region (UnsafeRowWriter.write(Decimal)). */
 typedef enum sd_agg_fn {
   SD_AGG_COUNT_STAR = 1, SD_AGG_COUNT = 2, SD_AGG_SUM = 3, SD_AGG_AVG = 4, SD_AGG_MIN = 5, SD_AGG_MAX = 6
 } sd_agg_fn;

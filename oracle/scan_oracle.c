@@ -90,7 +90,14 @@ typedef struct val {
   double d;           /* FLOAT (float-rounded) and DOUBLE                            */
   const uint8_t* s;   /* STRING                                                      */
   int32_t slen;
+  __int128 w;         /* DECIMAL aggregate buffers / results wider than 18 digits (java.math.BigDecimal unscaled value
+                         in the reference: Decimal.scala falls back to BigDecimal beyond MAX_LONG_DIGITS)            */
 } val;
+/* field type codes for rows: sd_type in the low byte, DECIMAL (precision << 8 | scale) above it */
+#define FT(t, ps) ((t) == SD_DECIMAL ? ((t) | ((ps) << 8)) : (t))
+#define FT_BASE(ft) ((ft) & 0xff)
+#define FT_PREC(ft) (((ft) >> 16) & 0xff)
+static __int128 pow10_w(int k) { __int128 r = 1; while (k-- > 0) r *= 10; return r; }
 
 static int is_integral(int t) {
   return t == SD_BOOLEAN || t == SD_BYTE || t == SD_SHORT || t == SD_INT || t == SD_LONG || t == SD_DATE ||
@@ -397,6 +404,7 @@ struct oracle_plan {
   /* aggregation state */
   int nbuf;                 /* number of buffer fields per group                   */
   int* buf_type;            /* sd_type per buffer field                            */
+  int* buf_ps;              /* DECIMAL buffer fields: (precision << 8) | scale     */
   int* buf_nullable;
   int* expr_nullable;       /* static nullability per expression node              */
   /* groups in insertion order (SHAMap appends value bytes back to back: SHAMap.scala:21-41) */
@@ -411,6 +419,13 @@ struct oracle_plan {
 };
 
 static val eval(const oracle_plan* p, int node, const val* cols);
+/* (precision << 8) | scale of a DECIMAL-typed node: columns carry it, LIT / CAST nodes in sd_expr.c */
+static int dec_ps(const oracle_plan* p, int node) {
+  const sd_expr* e = &p->exprs[node];
+  if (e->op == SD_OP_COL) return (p->cols[e->a].precision << 8) | p->cols[e->a].scale;
+  if (e->op == SD_OP_NEG) return dec_ps(p, e->a);
+  return e->c;
+}
 
 static val eval_node(const oracle_plan* p, const sd_expr* e, const val* cols) {
   val r; memset(&r, 0, sizeof(r));
@@ -453,7 +468,20 @@ static val eval_node(const oracle_plan* p, const sd_expr* e, const val* cols) {
       val a = eval(p, e->a, cols);
       if (a.isnull) { r.isnull = 1; return r; }
       int from = p->exprs[e->a].type, to = e->type;
-      if (is_integral(from) && is_integral(to)) r.i = wrap_int(a.i, to);
+      /* Spark 2.1.1 Cast (the pairs include/snappy_gpu.h lists; the rest is refused at plan creation) */
+      if (from == SD_DECIMAL && is_fp(to)) {                       /* Decimal.toDouble */
+        double x = (double)a.i / pow(10.0, dec_ps(p, e->a) & 0xff);
+        r.d = to == SD_FLOAT ? (double)(float)x : x;
+      } else if (to == SD_DECIMAL && from != SD_DECIMAL) {         /* Decimal(long).changePrecision(p, s) or NULL */
+        int ps = dec_ps(p, (int)(e - p->exprs));
+        __int128 v = (__int128)a.i * pow10_w(ps & 0xff), lim = pow10_w(ps >> 8);
+        if (v >= lim || v <= -lim) r.isnull = 1; else r.i = (int64_t)v;
+      } else if (to == SD_DECIMAL) {                                /* DECIMAL -> DECIMAL with a scale that does not shrink */
+        int ps0 = dec_ps(p, e->a), ps1 = dec_ps(p, (int)(e - p->exprs));
+        __int128 v = (__int128)a.i * pow10_w((ps1 & 0xff) - (ps0 & 0xff)), lim = pow10_w(ps1 >> 8);
+        if (v >= lim || v <= -lim) r.isnull = 1; else r.i = (int64_t)v;
+      } else if (to == SD_BOOLEAN) r.i = is_fp(from) ? (a.d != 0.0) : (a.i != 0);   /* castToBoolean: _ != 0 */
+      else if (is_integral(from) && is_integral(to)) r.i = wrap_int(a.i, to);
       else if (is_integral(from) && to == SD_DOUBLE) r.d = (double)a.i;
       else if (is_integral(from) && to == SD_FLOAT) r.d = (float)a.i;
       else if (is_fp(from) && to == SD_DOUBLE) r.d = a.d;
@@ -529,7 +557,8 @@ static void compute_nullability(oracle_plan* p) {
       case SD_OP_LIT: n = 0; break;
       case SD_OP_DIV: n = 1; break;
       case SD_OP_ISNULL: case SD_OP_ISNOTNULL: n = 0; break;
-      case SD_OP_NEG: case SD_OP_CAST: case SD_OP_NOT: n = p->expr_nullable[e->a]; break;
+      case SD_OP_CAST: n = p->expr_nullable[e->a] || e->type == SD_DECIMAL; break;   /* Cast.forceNullable(_, DecimalType) */
+      case SD_OP_NEG: case SD_OP_NOT: n = p->expr_nullable[e->a]; break;
       case SD_OP_IN: n = p->expr_nullable[e->a]; break;
       default: n = p->expr_nullable[e->a] || p->expr_nullable[e->b]; break;
     }
@@ -538,14 +567,35 @@ static void compute_nullability(oracle_plan* p) {
 }
 
 /* buffer schema (SnappyHashAggregateExec.scala:174-210) */
-static int sum_buffer_type(int t) { return is_fp(t) ? SD_DOUBLE : SD_LONG; }
+static int sum_buffer_type(int t) { return is_fp(t) ? SD_DOUBLE : (t == SD_DECIMAL ? SD_DECIMAL : SD_LONG); }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* casts the path executes (mirrors the product's plan validation) */
+static int check_casts(const oracle_plan* p) {
+  for (int i = 0; i < p->desc.nexprs; i++) {
+    const sd_expr* e = &p->exprs[i];
+    if (e->op != SD_OP_CAST) continue;
+    int from = p->exprs[e->a].type, to = e->type;
+    int tf = from == SD_DATE || from == SD_TIMESTAMP, tt = to == SD_DATE || to == SD_TIMESTAMP;
+    if (from == SD_STRING || to == SD_STRING) return fail(SD_ERR_UNSUPPORTED, "casts involving STRING");
+    if ((tf || tt) && from != to) return fail(SD_ERR_UNSUPPORTED, "casts involving DATE / TIMESTAMP");
+    if (from == SD_DECIMAL && !(is_fp(to) || to == SD_DECIMAL)) return fail(SD_ERR_UNSUPPORTED, "this cast from DECIMAL");
+    if (to == SD_DECIMAL && !(from == SD_BYTE || from == SD_SHORT || from == SD_INT || from == SD_LONG || from == SD_DECIMAL))
+      return fail(SD_ERR_UNSUPPORTED, "this cast to DECIMAL");
+    if (from == SD_DECIMAL && to == SD_DECIMAL && (dec_ps(p, i) & 0xff) < (dec_ps(p, e->a) & 0xff))
+      return fail(SD_ERR_UNSUPPORTED, "DECIMAL cast that reduces the scale");
+  }
+  return 0;
+}
 
 static int build_buffer_schema(oracle_plan* p) {
   int n = 0;
   for (int i = 0; i < p->desc.naggs; i++) n += p->aggs[i].fn == SD_AGG_AVG ? 2 : 1;
   p->nbuf = n;
   p->buf_type = (int*)calloc(n + 1, sizeof(int));
+  p->buf_ps = (int*)calloc(n + 1, sizeof(int));
   p->buf_nullable = (int*)calloc(n + 1, sizeof(int));
+  { int rc0 = check_casts(p); if (rc0) return rc0; }
   int k = 0, keyed = p->desc.nkeys > 0;
   for (int i = 0; i < p->desc.naggs; i++) {
     const sd_agg* a = &p->aggs[i];
@@ -553,17 +603,18 @@ static int build_buffer_schema(oracle_plan* p) {
     int cn = a->expr >= 0 ? p->expr_nullable[a->expr] : 0;
     if (a->expr >= 0 && (ct == SD_STRING) && a->fn != SD_AGG_COUNT)
       return fail(SD_ERR_UNSUPPORTED, "aggregate over STRING input not supported");
-    if ((a->fn == SD_AGG_SUM || a->fn == SD_AGG_AVG) && ct == SD_DECIMAL)
-      return fail(SD_ERR_UNSUPPORTED, "SUM/AVG over DECIMAL not supported");
+    int cps = ct == SD_DECIMAL ? dec_ps(p, a->expr) : 0;
+    /* Sum / Average over DECIMAL(p,s): sumDataType = DecimalType.bounded(p + 10, s) (Spark 2.1.1 Sum.scala / Average.scala) */
+    int sum_ps = (imin(38, (cps >> 8) + 10) << 8) | (cps & 0xff);
     switch (a->fn) {
       case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: p->buf_type[k] = SD_LONG; p->buf_nullable[k++] = 0; break;
       /* grouped: non-nullable when the child is (bufferAttributesForGroup :174-204);
        * no keys: plain Spark buffers, nullable (doProduceWithoutKeys :337-346) */
-      case SD_AGG_SUM: p->buf_type[k] = sum_buffer_type(ct); p->buf_nullable[k++] = keyed ? cn : 1; break;
+      case SD_AGG_SUM: p->buf_type[k] = sum_buffer_type(ct); p->buf_ps[k] = sum_ps; p->buf_nullable[k++] = keyed ? cn : 1; break;
       case SD_AGG_AVG:
-        p->buf_type[k] = SD_DOUBLE; p->buf_nullable[k++] = 0;   /* Average.sum starts at 0.0 */
+        p->buf_type[k] = ct == SD_DECIMAL ? SD_DECIMAL : SD_DOUBLE; p->buf_ps[k] = sum_ps; p->buf_nullable[k++] = 0;   /* Average.sum starts at 0 */
         p->buf_type[k] = SD_LONG; p->buf_nullable[k++] = 0; break;
-      case SD_AGG_MIN: case SD_AGG_MAX: p->buf_type[k] = ct; p->buf_nullable[k++] = keyed ? cn : 1; break;
+      case SD_AGG_MIN: case SD_AGG_MAX: p->buf_type[k] = ct; p->buf_ps[k] = cps; p->buf_nullable[k++] = keyed ? cn : 1; break;
       default: return fail(SD_ERR_INVALID, "unknown aggregate function");
     }
   }
@@ -600,15 +651,20 @@ static void update_buffers(const oracle_plan* p, val* b, const val* cols) {
       case SD_AGG_SUM:
         if (!v.isnull) {
           if (is_fp(t)) b[k].d = (b[k].isnull ? 0.0 : b[k].d) + v.d;
+          else if (t == SD_DECIMAL) { b[k].w = (b[k].isnull ? (__int128)0 : b[k].w) + v.i; b[k].i = (int64_t)b[k].w; }   /* Decimal + Decimal, exact */
           else b[k].i = (int64_t)((uint64_t)(b[k].isnull ? 0 : b[k].i) + (uint64_t)v.i);
           b[k].isnull = 0;
         }
         k++; break;
       case SD_AGG_AVG:
-        if (!v.isnull) { b[k].d += to_f64(&v, t); b[k + 1].i += 1; }
+        if (!v.isnull) {
+          if (t == SD_DECIMAL) { b[k].w += v.i; b[k].i = (int64_t)b[k].w; } else b[k].d += to_f64(&v, t);
+          b[k + 1].i += 1;
+        }
         k += 2; break;
       case SD_AGG_MIN: case SD_AGG_MAX:
         if (!v.isnull) {
+          v.w = v.i;
           if (b[k].isnull) { b[k] = v; }
           else {
             int c = cmp_val(&v, &b[k], t);
@@ -697,7 +753,10 @@ static void out_reserve(oracle_plan* p, int64_t more) {
 }
 static void emit_row(oracle_plan* p, int n, const int* types, const val* vals) {
   int64_t bits = ((n + 63) / 64) * 8, fixed = bits + 8 * (int64_t)n, var = 0;
-  for (int i = 0; i < n; i++) if (types[i] == SD_STRING && !vals[i].isnull) var += (vals[i].slen + 7) & ~7;
+  for (int i = 0; i < n; i++) {
+    if (types[i] == SD_STRING && !vals[i].isnull) var += (vals[i].slen + 7) & ~7;
+    if (FT_BASE(types[i]) == SD_DECIMAL && FT_PREC(types[i]) > 18) var += 16;   /* UnsafeRowWriter.write(Decimal): 16 bytes always reserved */
+  }
   int64_t sz = fixed + var;
   out_reserve(p, 8 + sz);
   uint8_t* r = p->out + p->out_len;
@@ -705,8 +764,20 @@ static void emit_row(oracle_plan* p, int n, const int* types, const val* vals) {
   memset(r, 0, sz);
   int64_t voff = fixed;
   for (int i = 0; i < n; i++) {
-    if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); continue; }
     uint8_t* slot = r + bits + 8 * (int64_t)i;
+    if (FT_BASE(types[i]) == SD_DECIMAL && FT_PREC(types[i]) > 18) {
+      /* precision > MAX_LONG_DIGITS: BigInteger.toByteArray() (minimal big-endian two's complement) in a 16-byte region */
+      if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); int64_t ol = voff << 32; memcpy(slot, &ol, 8); voff += 16; continue; }
+      uint8_t be[16]; __int128 v = vals[i].w;
+      for (int k = 15; k >= 0; k--) { be[k] = (uint8_t)(v & 0xff); v >>= 8; }
+      int first = 0;
+      while (first < 15 && ((be[first] == 0 && !(be[first + 1] & 0x80)) || (be[first] == 0xff && (be[first + 1] & 0x80)))) first++;
+      memcpy(r + voff, be + first, 16 - first);
+      int64_t ol = (voff << 32) | (16 - first); memcpy(slot, &ol, 8); voff += 16;
+      continue;
+    }
+    if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); continue; }
+    if (FT_BASE(types[i]) == SD_DECIMAL) { int64_t v = (int64_t)vals[i].w; memcpy(slot, &v, 8); continue; }
     switch (types[i]) {
       case SD_STRING: { int64_t ol = (voff << 32) | (uint32_t)vals[i].slen; memcpy(slot, &ol, 8);
                         memcpy(r + voff, vals[i].s, vals[i].slen); voff += (vals[i].slen + 7) & ~7; break; }
@@ -731,6 +802,13 @@ static int unsafe_field(const uint8_t* row, int64_t len, int nfields, int idx, i
   memset(out, 0, sizeof(*out));
   if (row[idx >> 3] & (1u << (idx & 7))) { out->isnull = 1; return 0; }
   const uint8_t* slot = row + bits + 8 * (int64_t)idx;
+  if (FT_BASE(type) == SD_DECIMAL) {   /* UnsafeRow.getDecimal */
+    if (FT_PREC(type) <= 18) { out->i = ld_i64(slot); out->w = out->i; return 0; }
+    int64_t ol = ld_i64(slot); const uint8_t* b = row + (ol >> 32); int ln = (int)(ol & 0xffffffff);
+    __int128 v = (ln > 0 && (b[0] & 0x80)) ? -1 : 0;
+    for (int k = 0; k < ln; k++) v = (v << 8) | b[k];
+    out->w = v; out->i = (int64_t)v; return 0;
+  }
   switch (type) {
     case SD_STRING: { int64_t ol = ld_i64(slot); out->s = row + (ol >> 32); out->slen = (int32_t)(ol & 0xffffffff); break; }
     case SD_BOOLEAN: out->i = slot[0] != 0; break;
@@ -985,13 +1063,13 @@ int oracle_plan_finish(oracle_plan* p, void* out_rows, int64_t cap, int64_t* out
     int nk = p->desc.nkeys, n = nk + p->nbuf;
     int* types = (int*)malloc(sizeof(int) * (n + 1));
     val* vals = (val*)malloc(sizeof(val) * (n + 1));
-    for (int i = 0; i < nk; i++) types[i] = p->exprs[p->keys[i]].type;
-    for (int i = 0; i < p->nbuf; i++) types[nk + i] = p->buf_type[i];
+    for (int i = 0; i < nk; i++) types[i] = FT(p->exprs[p->keys[i]].type, p->exprs[p->keys[i]].type == SD_DECIMAL ? dec_ps(p, p->keys[i]) : 0);
+    for (int i = 0; i < p->nbuf; i++) types[nk + i] = FT(p->buf_type[i], p->buf_ps[i]);
     if (nk == 0 && p->ngroups == 0) {            /* no-key aggregate always outputs one row */
       val none; memset(&none, 0, sizeof(none)); find_or_insert_group(p, &none);
     }
     for (int g = 0; g < p->ngroups; g++) {       /* insertion order */
-      for (int i = 0; i < nk; i++) vals[i] = p->gkeys[g][i];
+      for (int i = 0; i < nk; i++) { vals[i] = p->gkeys[g][i]; vals[i].w = vals[i].i; }
       for (int i = 0; i < p->nbuf; i++) vals[nk + i] = p->gbufs[g][i];
       emit_row(p, n, types, vals);
     }
@@ -1023,7 +1101,7 @@ void oracle_plan_destroy(oracle_plan* p) {
   free(p->gkeys); free(p->gbufs); free(p->ghash); free(p->htab);
   for (int i = 0; i < p->desc.nliterals; i++) free(p->lit_strs[i]);
   free(p->cols); free(p->exprs); free(p->keys); free(p->aggs); free(p->proj); free(p->lit_types);
-  free(p->lits); free(p->lit_strs); free(p->buf_type); free(p->buf_nullable); free(p->expr_nullable); free(p->out);
+  free(p->lits); free(p->lit_strs); free(p->buf_type); free(p->buf_ps); free(p->buf_nullable); free(p->expr_nullable); free(p->out);
   free(p);
 }
 
@@ -1036,8 +1114,8 @@ int oracle_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64
   if (rc) return rc;
   int nk = desc->nkeys, n = nk + p->nbuf;
   int* types = (int*)malloc(sizeof(int) * (n + 1));
-  for (int i = 0; i < nk; i++) types[i] = p->exprs[p->keys[i]].type;
-  for (int i = 0; i < p->nbuf; i++) types[nk + i] = p->buf_type[i];
+  for (int i = 0; i < nk; i++) types[i] = FT(p->exprs[p->keys[i]].type, p->exprs[p->keys[i]].type == SD_DECIMAL ? dec_ps(p, p->keys[i]) : 0);
+  for (int i = 0; i < p->nbuf; i++) types[nk + i] = FT(p->buf_type[i], p->buf_ps[i]);
   val* f = (val*)malloc(sizeof(val) * (n + 1));
   const uint8_t* r = (const uint8_t*)partial_rows; int64_t pos = 0;
   while (pos + 8 <= len) {
@@ -1053,11 +1131,14 @@ int oracle_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64
         case SD_AGG_SUM:
           if (!in->isnull) {
             if (p->buf_type[k] == SD_DOUBLE) b[k].d = (b[k].isnull ? 0.0 : b[k].d) + in->d;
+            else if (p->buf_type[k] == SD_DECIMAL) { b[k].w = (b[k].isnull ? (__int128)0 : b[k].w) + in->w; b[k].i = (int64_t)b[k].w; }
             else b[k].i = (int64_t)((uint64_t)(b[k].isnull ? 0 : b[k].i) + (uint64_t)in->i);
             b[k].isnull = 0;
           }
           k++; break;
-        case SD_AGG_AVG: b[k].d += in->d; b[k + 1].i += in[1].i; k += 2; break;
+        case SD_AGG_AVG:
+          if (p->buf_type[k] == SD_DECIMAL) { b[k].w += in->w; b[k].i = (int64_t)b[k].w; } else b[k].d += in->d;
+          b[k + 1].i += in[1].i; k += 2; break;
         default:
           if (!in->isnull) {
             if (b[k].isnull) b[k] = *in;
@@ -1074,15 +1155,37 @@ int oracle_final_merge(const sd_plan_desc* desc, const void* partial_rows, int64
   int* otypes = (int*)malloc(sizeof(int) * (nout + 1));
   val* ov = (val*)malloc(sizeof(val) * (nout + 1));
   for (int g = 0; g < p->ngroups; g++) {
-    for (int i = 0; i < nk; i++) { otypes[i] = types[i]; ov[i] = p->gkeys[g][i]; }
+    for (int i = 0; i < nk; i++) { otypes[i] = types[i]; ov[i] = p->gkeys[g][i]; ov[i].w = ov[i].i; }
     int k = 0;
     for (int i = 0; i < desc->naggs; i++) {
       val* b = p->gbufs[g]; val o; memset(&o, 0, sizeof(o));
-      if (p->aggs[i].fn == SD_AGG_AVG) {          /* Average.evaluateExpression: sum / count, NULL when count = 0 */
+      if (p->aggs[i].fn == SD_AGG_AVG && p->buf_type[k] == SD_DECIMAL) {
+        /* Average over DECIMAL(p,s): Cast(Cast(sum, (p+14,s+4)) / Cast(count, (p+14,s+4)), resultType = bounded(p+4, s+4)):
+         * java.math.BigDecimal division, the quotient rounded HALF_UP to scale s+4; NULL when it does not fit p+4 digits */
+        int in_ps = dec_ps(p, p->aggs[i].expr);
+        int rp = imin(38, (in_ps >> 8) + 4), rs = imin(38, (in_ps & 0xff) + 4);
+        otypes[nk + i] = FT(SD_DECIMAL, (rp << 8) | rs);
+        if (b[k + 1].i == 0) o.isnull = 1;
+        else {
+          __int128 num = b[k].w * pow10_w(rs - (in_ps & 0xff)), den = b[k + 1].i;
+          __int128 q = num / den, rem = num % den;
+          if (rem < 0) rem = -rem;
+          if (rem * 2 >= den) q += num < 0 ? -1 : 1;
+          if (q >= pow10_w(rp) || q <= -pow10_w(rp)) o.isnull = 1; else { o.w = q; o.i = (int64_t)q; }
+        }
+        k += 2;
+      } else if (p->aggs[i].fn == SD_AGG_AVG) {   /* Average.evaluateExpression: sum / count, NULL when count = 0 */
         otypes[nk + i] = SD_DOUBLE;
         if (b[k + 1].i == 0) o.isnull = 1; else o.d = b[k].d / (double)b[k + 1].i;
         k += 2;
-      } else { otypes[nk + i] = p->buf_type[k]; o = b[k]; k++; }
+      } else {
+        otypes[nk + i] = FT(p->buf_type[k], p->buf_ps[k]); o = b[k];
+        if (p->aggs[i].fn == SD_AGG_SUM && p->buf_type[k] == SD_DECIMAL && !o.isnull) {   /* more than p+10 digits: changePrecision fails -> NULL */
+          __int128 lim = pow10_w(p->buf_ps[k] >> 8);
+          if (o.w >= lim || o.w <= -lim) o.isnull = 1;
+        }
+        k++;
+      }
       ov[nk + i] = o;
     }
     emit_row(p, nout, otypes, ov);

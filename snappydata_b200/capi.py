@@ -15,7 +15,7 @@ import numpy as np
 
 from .column_format import ColumnBatch, SqlType, parse_row_stream
 
-SD_ABI_VERSION = 1
+SD_ABI_VERSION = 2
 SD_NUM_METRICS = 12
 SD_OPT_RETAIN_BUFFERS = 1
 METRIC_NAMES = ["numOutputRows", "numRowsBuffer", "columnBatchesSeen", "updatedColumnCount",
@@ -45,7 +45,8 @@ class AggFn:
 
 
 class sd_column(C.Structure):
-    _fields_ = [("type", C.c_int32), ("nullable", C.c_int32), ("table_ordinal", C.c_int32), ("scale", C.c_int32)]
+    _fields_ = [("type", C.c_int32), ("nullable", C.c_int32), ("table_ordinal", C.c_int32), ("scale", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 class sd_expr(C.Structure):
@@ -261,7 +262,8 @@ class PlanDesc:
         self.filter = filter_node
         self._cols = (sd_column * max(1, len(self.cols_py)))()
         for i, c in enumerate(self.cols_py):
-            self._cols[i] = sd_column(int(c[0]), int(bool(c[1])), int(c[2]), int(c[3]) if len(c) > 3 else 0)
+            self._cols[i] = sd_column(int(c[0]), int(bool(c[1])), int(c[2]), int(c[3]) if len(c) > 3 else 0,
+                                      int(c[4]) if len(c) > 4 else (18 if int(c[0]) == int(SqlType.DECIMAL) else 0))
         self._exprs = (sd_expr * max(1, len(self.exprs_py)))()
         for i, e in enumerate(self.exprs_py):
             self._exprs[i] = sd_expr(*[int(x) for x in e])
@@ -288,37 +290,59 @@ class PlanDesc:
         return [c[2] for c in self.cols_py]
 
     # -- schemas of the rows the plan emits ----------------------------------------------------
-    def _sum_type(self, t: SqlType) -> SqlType:
+    # a field is a SqlType, or (SqlType.DECIMAL, precision, scale): Spark 2.1.1 Sum / Average over DECIMAL(p,s) have the
+    # buffer DECIMAL(p+10,s); Average's result is DECIMAL(p+4,s+4)
+    def _ps(self, node: int):
+        op, _, a, _, c = self.exprs_py[node]
+        if op == Op.COL:
+            col = self.cols_py[a]
+            return (col[4] if len(col) > 4 else 18), (col[3] if len(col) > 3 else 0)
+        if op == Op.NEG:
+            return self._ps(a)
+        return c >> 8, c & 0xFF
+
+    def _ftype(self, node: int):
+        t = SqlType(self.exprs_py[node][1])
+        return (t,) + self._ps(node) if t == SqlType.DECIMAL else t
+
+    def _sum_type(self, node: int):
+        t = SqlType(self.exprs_py[node][1])
+        if t == SqlType.DECIMAL:
+            p, s = self._ps(node)
+            return (SqlType.DECIMAL, min(38, p + 10), s)
         return SqlType.DOUBLE if t in (SqlType.FLOAT, SqlType.DOUBLE) else SqlType.LONG
 
-    def partial_schema(self) -> List[SqlType]:
+    def partial_schema(self) -> List[object]:
         if not self.aggs_py and not self.keys_py:
-            return [SqlType(self.exprs_py[n][1]) for n in self.proj_py]
-        out = [SqlType(self.exprs_py[k][1]) for k in self.keys_py]
+            return [self._ftype(n) for n in self.proj_py]
+        out = [self._ftype(k) for k in self.keys_py]
         for fn, e in self.aggs_py:
-            t = SqlType(self.exprs_py[e][1]) if e >= 0 else SqlType.LONG
             if fn in (AggFn.COUNT_STAR, AggFn.COUNT):
                 out.append(SqlType.LONG)
             elif fn == AggFn.SUM:
-                out.append(self._sum_type(t))
+                out.append(self._sum_type(e))
             elif fn == AggFn.AVG:
-                out += [SqlType.DOUBLE, SqlType.LONG]
+                st = self._sum_type(e)
+                out += [st if isinstance(st, tuple) else SqlType.DOUBLE, SqlType.LONG]
             else:
-                out.append(t)
+                out.append(self._ftype(e))
         return out
 
-    def final_schema(self) -> List[SqlType]:
-        out = [SqlType(self.exprs_py[k][1]) for k in self.keys_py]
+    def final_schema(self) -> List[object]:
+        out = [self._ftype(k) for k in self.keys_py]
         for fn, e in self.aggs_py:
-            t = SqlType(self.exprs_py[e][1]) if e >= 0 else SqlType.LONG
             if fn in (AggFn.COUNT_STAR, AggFn.COUNT):
                 out.append(SqlType.LONG)
             elif fn == AggFn.SUM:
-                out.append(self._sum_type(t))
+                out.append(self._sum_type(e))
             elif fn == AggFn.AVG:
-                out.append(SqlType.DOUBLE)
+                if SqlType(self.exprs_py[e][1]) == SqlType.DECIMAL:
+                    p, s = self._ps(e)
+                    out.append((SqlType.DECIMAL, min(38, p + 4), min(38, s + 4)))
+                else:
+                    out.append(SqlType.DOUBLE)
             else:
-                out.append(t)
+                out.append(self._ftype(e))
         return out
 
 
@@ -507,7 +531,7 @@ class Store:
         self.schema = [(SqlType(t), bool(n)) for t, n in schema]
         arr = (sd_column * max(1, len(self.schema)))()
         for i, (t, n) in enumerate(self.schema):
-            arr[i] = sd_column(int(t), int(n), i, 0)
+            arr[i] = sd_column(int(t), int(n), i, 0, 18 if int(t) == int(SqlType.DECIMAL) else 0)
         h = C.c_void_p()
         api.check(api.store_create(device, len(self.schema), arr, C.byref(h)))
         self.h = h

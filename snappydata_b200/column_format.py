@@ -301,17 +301,26 @@ def unsafe_row(fields: Sequence[Tuple[SqlType, object]]) -> bytes:
     return bytes(bitset) + bytes(slots) + bytes(var)
 
 
-def parse_unsafe_row(buf: bytes, types: Sequence[SqlType], base: int = 0) -> List[object]:
+def parse_unsafe_row(buf: bytes, types: Sequence[object], base: int = 0) -> List[object]:
+    """`types`: SqlType per field, or (SqlType.DECIMAL, precision, scale) -- a DECIMAL comes back as its unscaled int
+    (precision > 18: BigInteger bytes in the variable-length region, UnsafeRow.getDecimal)."""
     n = len(types)
     bitset_len = ((n + 63) // 64) * 8
     out: List[object] = []
     for i, t in enumerate(types):
+        prec = 18
+        if isinstance(t, tuple):
+            t, prec = t[0], t[1]
         t = SqlType(t)
         if buf[base + (i >> 3)] & (1 << (i & 7)):
             out.append(None)
             continue
         off = base + bitset_len + 8 * i
-        if t == SqlType.STRING:
+        if t == SqlType.DECIMAL and prec > 18:
+            (ol,) = struct.unpack_from("<q", buf, off)
+            o, ln = ol >> 32, ol & 0xFFFFFFFF
+            out.append(int.from_bytes(bytes(buf[base + o: base + o + ln]), "big", signed=True))
+        elif t == SqlType.STRING:
             (ol,) = struct.unpack_from("<q", buf, off)
             o, ln = ol >> 32, ol & 0xFFFFFFFF
             out.append(bytes(buf[base + o: base + o + ln]))

@@ -23,7 +23,33 @@ bool type_is_integral(int t) {
          t == SD_TIMESTAMP || t == SD_DECIMAL;
 }
 bool type_is_fp(int t) { return t == SD_FLOAT || t == SD_DOUBLE; }
-int sum_buffer_type(int t) { return type_is_fp(t) ? SD_DOUBLE : SD_LONG; }
+int sum_buffer_type(int t) { return type_is_fp(t) ? SD_DOUBLE : (t == SD_DECIMAL ? SD_DECIMAL : SD_LONG); }
+
+int decimal_ps(const PlanSpec& p, int node) {
+  const sd_expr& e = p.exprs[node];
+  if (e.op == SD_OP_COL) return (p.cols[e.a].precision << 8) | p.cols[e.a].scale;
+  if (e.op == SD_OP_NEG) return decimal_ps(p, e.a);
+  return e.c;
+}
+std::vector<int> partial_field_types(const PlanSpec& p) {
+  std::vector<int> t;
+  for (int k : p.keys) t.push_back(field_type(p.exprs[k].type, p.exprs[k].type == SD_DECIMAL ? decimal_ps(p, k) : 0));
+  for (auto& m : p.agg_map) { t.push_back(field_type(m.buf_type, m.buf_ps)); if (m.fn == SD_AGG_AVG) t.push_back(SD_LONG); }
+  return t;
+}
+std::vector<int> final_field_types(const PlanSpec& p) {
+  std::vector<int> t;
+  for (int k : p.keys) t.push_back(field_type(p.exprs[k].type, p.exprs[k].type == SD_DECIMAL ? decimal_ps(p, k) : 0));
+  for (auto& m : p.agg_map) {
+    if (m.fn == SD_AGG_AVG) {
+      if (m.buf_type == SD_DECIMAL) {   // Average.resultType: DecimalType.bounded(p + 4, s + 4)
+        const int pr = std::min(38, (m.in_ps >> 8) + 4), sc = std::min(38, (m.in_ps & 0xff) + 4);
+        t.push_back(field_type(SD_DECIMAL, (pr << 8) | sc));
+      } else t.push_back(SD_DOUBLE);
+    } else t.push_back(field_type(m.buf_type, m.buf_ps));
+  }
+  return t;
+}
 
 int kind_of_type(int t) {
   switch (t) {
@@ -91,6 +117,7 @@ static std::string expr_text(const PlanSpec& p, int node) {
   const sd_expr& e = p.exprs[node];
   std::ostringstream o;
   o << opname(e.op) << ":" << tname(e.type);
+  if (e.type == SD_DECIMAL) o << "[" << decimal_ps(p, node) << "]";
   if (e.op == SD_OP_COL) o << "(c" << e.a << ")";
   else if (e.op == SD_OP_LIT) o << "(l" << e.a << ")";
   else if (e.op == SD_OP_IN) o << "(" << expr_text(p, e.a) << ",l" << e.b << "x" << e.c << ")";
@@ -167,6 +194,8 @@ struct Gen {
     if ((int)p.cols.size() > 64) return fail(SD_ERR_UNSUPPORTED, "more than 64 scan columns in one fused plan");
     if ((int)p.literal_types.size() > MAX_LITERALS) return fail(SD_ERR_UNSUPPORTED, "more than 64 literal slots");
     for (auto& c : p.cols) if (kind_of_type(c.type) < 0) return fail(SD_ERR_INVALID, "unknown column type");
+    for (auto& c : p.cols) if (c.type == SD_DECIMAL && (c.precision < 1 || c.precision > 18 || c.scale < 0 || c.scale > c.precision))
+      return fail(SD_ERR_INVALID, "DECIMAL scan column needs 1 <= precision <= 18 (int64 unscaled values, enc/Uncompressed.scala:95-98)");
     for (int i = 0; i < ne; i++) {
       const sd_expr& e = p.exprs[i];
       if (e.op == SD_OP_COL) { if (e.a < 0 || e.a >= (int)p.cols.size()) return fail(SD_ERR_INVALID, "column reference out of range"); }
@@ -177,6 +206,10 @@ struct Gen {
         if (e.op == SD_OP_IN && (e.b < 0 || e.c < 1 || e.b + e.c > (int)p.literal_types.size())) return fail(SD_ERR_INVALID, "IN list out of range");
       }
       if (kind_of_type(e.type) < 0) return fail(SD_ERR_INVALID, "unknown expression type");
+      if (e.type == SD_DECIMAL) {
+        const int ps = decimal_ps(p, i), pr = ps >> 8, sc = ps & 0xff;
+        if (pr < 1 || pr > 18 || sc > pr) return fail(SD_ERR_INVALID, "DECIMAL expression needs 1 <= precision <= 18 and scale <= precision (sd_expr.c / sd_column)");
+      }
     }
     auto chk = [&](int n) { return n >= 0 && n < ne; };
     if (p.filter >= 0 && (!chk(p.filter) || p.exprs[p.filter].type != SD_BOOLEAN)) return fail(SD_ERR_INVALID, "filter must be a BOOLEAN expression");
@@ -197,7 +230,8 @@ struct Gen {
         case SD_OP_LIT: n = 1; break;   // a ParamLiteral's value (incl. NULL) is only known at run time
         case SD_OP_DIV: n = 1; break;
         case SD_OP_ISNULL: case SD_OP_ISNOTNULL: n = 0; break;
-        case SD_OP_NEG: case SD_OP_CAST: case SD_OP_NOT: n = p.expr_nullable[e.a]; break;
+        case SD_OP_CAST: n = p.expr_nullable[e.a] || e.type == SD_DECIMAL; break;   // Cast.forceNullable: -> DECIMAL may overflow to NULL
+        case SD_OP_NEG: case SD_OP_NOT: n = p.expr_nullable[e.a]; break;
         case SD_OP_IN: n = 1; break;
         default: n = p.expr_nullable[e.a] || p.expr_nullable[e.b]; break;
       }
@@ -214,7 +248,8 @@ struct Gen {
       case SD_OP_LIT: return 0;
       case SD_OP_DIV: return 1;
       case SD_OP_ISNULL: case SD_OP_ISNOTNULL: return 0;
-      case SD_OP_NEG: case SD_OP_CAST: case SD_OP_NOT: case SD_OP_IN: return static_nullable(e.a);
+      case SD_OP_CAST: return static_nullable(e.a) || e.type == SD_DECIMAL;
+      case SD_OP_NEG: case SD_OP_NOT: case SD_OP_IN: return static_nullable(e.a);
       default: return static_nullable(e.a) || static_nullable(e.b);
     }
   }
@@ -246,8 +281,23 @@ struct Gen {
       if (a.fn != SD_AGG_COUNT_STAR && a.expr < 0) return fail(SD_ERR_INVALID, "aggregate without input expression");
       if (a.expr >= 0 && it == SD_STRING && a.fn != SD_AGG_COUNT)
         return fail(SD_ERR_UNSUPPORTED, "aggregate over a STRING input is not supported by the GPU path");
-      if ((a.fn == SD_AGG_SUM || a.fn == SD_AGG_AVG) && it == SD_DECIMAL)
-        return fail(SD_ERR_UNSUPPORTED, "SUM/AVG over DECIMAL is not supported by the GPU path");
+      m.value_slot2 = -1;
+      if (it == SD_DECIMAL) {
+        m.in_ps = decimal_ps(p, a.expr);
+        m.buf_ps = m.in_ps;   // MIN / MAX keep the input type
+      }
+      if ((a.fn == SD_AGG_SUM || a.fn == SD_AGG_AVG) && it == SD_DECIMAL) {
+        // Spark 2.1.1 Sum / Average over DECIMAL(p,s): buffer DECIMAL(p+10,s) -- up to 28 digits, i.e. wider than int64.
+        // The value is summed as two int64 slots (high / low 32 bits), exact for < 2^31 rows, and recombined on the host.
+        m.buf_type = SD_DECIMAL;
+        m.buf_ps = (std::min(38, (m.in_ps >> 8) + 10) << 8) | (m.in_ps & 0xff);
+        m.value_slot = add_slot(SLOT_ADD_I64, a.expr, GATE_VALUE_HI32);
+        m.value_slot2 = add_slot(SLOT_ADD_I64, a.expr, GATE_VALUE_LO32);
+        if (a.fn == SD_AGG_SUM) { m.buf_nullable = keyed ? in_null : 1; if (m.buf_nullable) m.count_slot = count_slot_for(a.expr); }
+        else m.count_slot = count_slot_for(a.expr);
+        p.agg_map.push_back(m);
+        continue;
+      }
       switch (a.fn) {
         case SD_AGG_COUNT_STAR:
           m.value_slot = add_slot(SLOT_ADD_I64, -1, GATE_ONE); m.buf_type = SD_LONG; break;
@@ -340,14 +390,36 @@ struct Gen {
         else o << "    const " << T << " v" << N << " = (" << T << ")(0 - (uint64_t)" << V(e.a) << ");";
         o << " const bool n" << N << " = " << NL(e.a) << ";\n";
         return 0;
-      case SD_OP_CAST: {
+      case SD_OP_CAST: {   // Spark 2.1.1 Cast for the pairs listed in include/snappy_gpu.h; anything else is refused
         const int from = p.exprs[e.a].type, to = e.type;
-        std::string v;
+        std::string v, extra_null;
+        auto is_time = [](int t) { return t == SD_DATE || t == SD_TIMESTAMP; };
+        auto pow10 = [](int k) { std::string r = "1"; for (int i = 0; i < k; i++) r += "0"; return r + "ll"; };
         if (from == SD_STRING || to == SD_STRING) return fail(SD_ERR_UNSUPPORTED, "casts involving STRING");
-        if (type_is_fp(from) && (to == SD_LONG || to == SD_TIMESTAMP || to == SD_DECIMAL)) v = "sd::f64_to_i64((double)" + V(e.a) + ")";
+        if ((is_time(from) || is_time(to)) && from != to) return fail(SD_ERR_UNSUPPORTED, "casts involving DATE / TIMESTAMP (time-zone dependent in Spark)");
+        if (from == SD_DECIMAL || to == SD_DECIMAL) {
+          if (from == SD_DECIMAL && type_is_fp(to)) {   // Decimal.toDouble: unscaled / 10^s
+            const int sc = decimal_ps(p, e.a) & 0xff;
+            v = std::string("(") + T + ")((double)" + V(e.a) + " / 1e" + std::to_string(sc) + ")";
+          } else if (to == SD_DECIMAL && (from == SD_BYTE || from == SD_SHORT || from == SD_INT || from == SD_LONG)) {
+            const int ps = decimal_ps(p, node), pr = ps >> 8, sc = ps & 0xff;   // v * 10^s, NULL when it needs more than p digits
+            const std::string lim = pow10(pr - sc);
+            v = "(int64_t)" + V(e.a) + " * " + pow10(sc);
+            extra_null = " || (int64_t)" + V(e.a) + " >= " + lim + " || (int64_t)" + V(e.a) + " <= -" + lim;
+          } else if (from == SD_DECIMAL && to == SD_DECIMAL) {
+            const int ps0 = decimal_ps(p, e.a), ps1 = decimal_ps(p, node);
+            const int up = (ps1 & 0xff) - (ps0 & 0xff);
+            if (up < 0) return fail(SD_ERR_UNSUPPORTED, "DECIMAL cast that reduces the scale (needs HALF_UP rounding)");
+            const std::string lim = pow10((ps1 >> 8) - up);
+            v = V(e.a) + " * " + pow10(up);
+            extra_null = " || " + V(e.a) + " >= " + lim + " || " + V(e.a) + " <= -" + lim;
+          } else return fail(SD_ERR_UNSUPPORTED, "this cast to / from DECIMAL");
+        }
+        else if (to == SD_BOOLEAN) v = "(uint8_t)(" + V(e.a) + " != 0)";                       // castToBoolean: _ != 0
+        else if (type_is_fp(from) && (to == SD_LONG)) v = "sd::f64_to_i64((double)" + V(e.a) + ")";
         else if (type_is_fp(from) && type_is_integral(to)) v = std::string("(") + T + ")sd::f64_to_i32((double)" + V(e.a) + ")";
         else v = std::string("(") + T + ")" + V(e.a);
-        o << "    const " << T << " v" << N << " = " << v << "; const bool n" << N << " = " << NL(e.a) << ";\n";
+        o << "    const " << T << " v" << N << " = " << v << "; const bool n" << N << " = " << NL(e.a) << extra_null << ";\n";
         if (to == SD_BOOLEAN) o << "    const int t" << N << " = n" << N << " ? 2 : (v" << N << " ? 1 : 0);\n";
         return 0;
       }
@@ -385,6 +457,8 @@ struct Gen {
           return 0;
         }
         if (p.exprs[e.b].type != ot) return fail(SD_ERR_INVALID, "comparison operands must have the same type");
+        if (ot == SD_DECIMAL && (decimal_ps(p, e.a) & 0xff) != (decimal_ps(p, e.b) & 0xff))
+          return fail(SD_ERR_INVALID, "DECIMAL comparison operands must have the same scale (Catalyst casts them to a common type)");
         std::string c;
         if (type_is_fp(ot)) {
           const char* f = e.op == SD_OP_EQ ? "f_eq" : e.op == SD_OP_NE ? "f_eq" : e.op == SD_OP_LT ? "f_lt" : e.op == SD_OP_LE ? "f_le"
@@ -497,6 +571,8 @@ struct Gen {
       slt << "    sv[" << s << "] = ";
       if (x.gate == GATE_ONE) slt << "1ull;\n";
       else if (x.gate == GATE_NONNULL_COUNT) slt << NL << " ? 0ull : 1ull;\n";
+      else if (x.gate == GATE_VALUE_HI32) slt << NL << " ? 0ull : (uint64_t)((int64_t)" << V << " >> 32);\n";
+      else if (x.gate == GATE_VALUE_LO32) slt << NL << " ? 0ull : ((uint64_t)(int64_t)" << V << " & 0xffffffffull);\n";
       else {
         const bool f = x.op == SLOT_ADD_F64 || x.op == SLOT_MIN_F64 || x.op == SLOT_MAX_F64;
         char ident[32];

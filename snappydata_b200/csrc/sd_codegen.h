@@ -20,7 +20,9 @@ struct TableSpec {
   int key;    // TABLE_KEYMAP: index into keys
 };
 
-enum SlotGate { GATE_VALUE = 0, GATE_NONNULL_COUNT = 1, GATE_ONE = 2 };
+// GATE_VALUE_HI32 / GATE_VALUE_LO32: the two halves of a wide (128-bit) integer sum: v = (v >> 32) * 2^32 + (v & 0xffffffff);
+// each half is summed in its own int64 slot (exact for < 2^31 rows per execution), recombined on the host
+enum SlotGate { GATE_VALUE = 0, GATE_NONNULL_COUNT = 1, GATE_ONE = 2, GATE_VALUE_HI32 = 3, GATE_VALUE_LO32 = 4 };
 
 struct SlotSpec {
   int op;     // SLOT_*
@@ -36,7 +38,16 @@ struct AggMap {
   int in_type;      // sd_type of the input
   int buf_type;     // sd_type of the (first) buffer field
   int buf_nullable;
+  int value_slot2;  // DECIMAL SUM/AVG: the low-half slot (value_slot holds the high half); -1 otherwise
+  int in_ps;        // DECIMAL input: (precision << 8) | scale; 0 otherwise
+  int buf_ps;       // DECIMAL buffer: SUM/AVG (p + 10, s) bounded to 38; MIN/MAX = input
 };
+
+// field type codes used for rows on the host: sd_type in the low byte, DECIMAL precision/scale above it
+inline int field_type(int sd_type, int ps) { return sd_type == SD_DECIMAL ? (sd_type | (ps << 8)) : sd_type; }
+inline int ft_base(int ft) { return ft & 0xff; }
+inline int ft_precision(int ft) { return (ft >> 16) & 0xff; }
+inline int ft_scale(int ft) { return (ft >> 8) & 0xff; }
 
 struct PlanSpec {
   // deep copy of the descriptor
@@ -86,6 +97,11 @@ int analyze_plan(const sd_plan_desc* desc, PlanSpec& out, std::string& err, cons
 int eval_string_predicate(const PlanSpec& p, int node, const char* s, int slen, const sd_literal* lits);
 
 int sum_buffer_type(int t);
+// (precision << 8) | scale of a DECIMAL-typed expression node
+int decimal_ps(const PlanSpec& p, int node);
+// partial-row field types (keys ++ aggregate buffers) and final-row field types (keys ++ results) as field_type codes
+std::vector<int> partial_field_types(const PlanSpec& p);
+std::vector<int> final_field_types(const PlanSpec& p);
 bool type_is_integral(int t);
 bool type_is_fp(int t);
 int kind_of_type(int t);

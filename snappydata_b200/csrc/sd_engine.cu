@@ -25,12 +25,15 @@ inline double rd_f64(const uint8_t* p) { double v; memcpy(&v, p, 8); return v; }
 inline float rd_f32(const uint8_t* p) { float v; memcpy(&v, p, 4); return v; }
 
 // ---- host values (stats rows, partial rows) -------------------------------------------------------
+typedef __int128 i128;
 struct HVal {
   bool isnull = false;
   int64_t i = 0;
   double d = 0;
+  i128 w = 0;      // DECIMAL unscaled value (any precision); `i` mirrors it when the precision is <= 18
   std::string s;
 };
+i128 pow10_128(int k) { i128 r = 1; for (int j = 0; j < k; j++) r *= 10; return r; }
 
 int cmp_str(const std::string& a, const std::string& b) {
   size_t n = std::min(a.size(), b.size());
@@ -42,19 +45,32 @@ int cmp_f64(double x, double y) {   // Utils.nanSafeCompareDoubles
   if (xn || yn) return xn && yn ? 0 : (xn ? 1 : -1);
   return x < y ? -1 : (x > y ? 1 : 0);
 }
-int cmp_hval(const HVal& a, const HVal& b, int t) {
+int cmp_hval(const HVal& a, const HVal& b, int ft) {
+  const int t = ft_base(ft);
   if (t == SD_STRING) return cmp_str(a.s, b.s);
   if (type_is_fp(t)) return cmp_f64(a.d, b.d);
+  if (t == SD_DECIMAL) return a.w < b.w ? -1 : (a.w > b.w ? 1 : 0);
   return a.i < b.i ? -1 : (a.i > b.i ? 1 : 0);
 }
 
 // field `idx` of a Spark UnsafeRow with `nfields` fields
-bool unsafe_field(const uint8_t* row, int64_t len, int nfields, int idx, int type, HVal* out) {
+bool unsafe_field(const uint8_t* row, int64_t len, int nfields, int idx, int ftype, HVal* out) {
   const int64_t bits = ((nfields + 63) / 64) * 8;
   if (idx < 0 || idx >= nfields || bits + 8 * (int64_t)nfields > len) return false;
   *out = HVal();
   if (row[idx >> 3] & (1u << (idx & 7))) { out->isnull = true; return true; }
   const uint8_t* slot = row + bits + 8 * (int64_t)idx;
+  const int type = ft_base(ftype);
+  if (type == SD_DECIMAL) {   // UnsafeRow.getDecimal: long for precision <= 18, else BigInteger bytes (big-endian two's complement)
+    if (ft_precision(ftype) <= 18) { out->i = rd_i64(slot); out->w = out->i; return true; }
+    const int64_t ol = rd_i64(slot);
+    const int64_t off = ol >> 32, ln = ol & 0xffffffff;
+    if (off < 0 || ln > 16 || off + ln > len) return false;
+    i128 v = (ln > 0 && (row[off] & 0x80)) ? -1 : 0;
+    for (int64_t k = 0; k < ln; k++) v = (v << 8) | row[off + k];
+    out->w = v; out->i = (int64_t)v;
+    return true;
+  }
   switch (type) {
     case SD_STRING: {
       const int64_t ol = rd_i64(slot);
@@ -78,7 +94,10 @@ void emit_unsafe_row(std::vector<uint8_t>& out, const std::vector<int>& types, c
   const int n = (int)types.size();
   const int64_t bits = ((n + 63) / 64) * 8, fixed = bits + 8 * (int64_t)n;
   int64_t var = 0;
-  for (int i = 0; i < n; i++) if (types[i] == SD_STRING && !vals[i].isnull) var += ((int64_t)vals[i].s.size() + 7) & ~int64_t(7);
+  for (int i = 0; i < n; i++) {
+    if (types[i] == SD_STRING && !vals[i].isnull) var += ((int64_t)vals[i].s.size() + 7) & ~int64_t(7);
+    if (ft_base(types[i]) == SD_DECIMAL && ft_precision(types[i]) > 18) var += 16;   // always reserved (UnsafeRowWriter.write(Decimal))
+  }
   const int64_t sz = fixed + var;
   const size_t base = out.size();
   out.resize(base + 8 + sz, 0);
@@ -87,8 +106,29 @@ void emit_unsafe_row(std::vector<uint8_t>& out, const std::vector<int>& types, c
   r += 8;
   int64_t voff = fixed;
   for (int i = 0; i < n; i++) {
-    if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); continue; }
     uint8_t* slot = r + bits + 8 * (int64_t)i;
+    if (ft_base(types[i]) == SD_DECIMAL) {
+      const bool wide = ft_precision(types[i]) > 18;
+      if (vals[i].isnull) {
+        r[i >> 3] |= (uint8_t)(1u << (i & 7));
+        if (wide) { const int64_t ol = voff << 32; memcpy(slot, &ol, 8); voff += 16; }   // offset kept, size 0
+        continue;
+      }
+      if (!wide) { const int64_t v = (int64_t)vals[i].w; memcpy(slot, &v, 8); continue; }
+      // BigInteger.toByteArray(): minimal big-endian two's complement
+      uint8_t be[16];
+      i128 v = vals[i].w;
+      for (int k = 15; k >= 0; k--) { be[k] = (uint8_t)(v & 0xff); v >>= 8; }
+      int first = 0;
+      while (first < 15 && ((be[first] == 0x00 && !(be[first + 1] & 0x80)) || (be[first] == 0xff && (be[first + 1] & 0x80)))) first++;
+      const int nb = 16 - first;
+      memcpy(r + voff, be + first, (size_t)nb);
+      const int64_t ol = (voff << 32) | (int64_t)nb;
+      memcpy(slot, &ol, 8);
+      voff += 16;
+      continue;
+    }
+    if (vals[i].isnull) { r[i >> 3] |= (uint8_t)(1u << (i & 7)); continue; }
     switch (types[i]) {
       case SD_STRING: {
         const int64_t ol = (voff << 32) | (uint32_t)vals[i].s.size();
@@ -868,6 +908,13 @@ void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>
     HVal v;
     const uint64_t raw = sv[m.value_slot];
     const int64_t cnt = m.count_slot >= 0 ? (int64_t)sv[m.count_slot] : 1;
+    if (m.value_slot2 >= 0) {   // DECIMAL SUM / AVG: high and low halves summed separately (sd_codegen.cpp build_slots)
+      v.w = (i128)(int64_t)sv[m.value_slot] * ((i128)1 << 32) + (i128)(int64_t)sv[m.value_slot2];
+      v.i = (int64_t)v.w;
+      if (m.fn == SD_AGG_SUM) { if (m.buf_nullable && cnt == 0) v.isnull = true; vals.push_back(v); }
+      else { vals.push_back(v); HVal c; c.i = cnt; vals.push_back(c); }
+      continue;
+    }
     switch (m.fn) {
       case SD_AGG_COUNT_STAR: case SD_AGG_COUNT: v.i = (int64_t)raw; vals.push_back(v); break;
       case SD_AGG_SUM:
@@ -880,7 +927,7 @@ void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>
       }
       default:
         if (m.buf_nullable && cnt == 0) v.isnull = true;
-        else if (type_is_fp(m.buf_type)) memcpy(&v.d, &raw, 8); else v.i = (int64_t)raw;
+        else if (type_is_fp(m.buf_type)) memcpy(&v.d, &raw, 8); else { v.i = (int64_t)raw; v.w = v.i; }
         vals.push_back(v); break;
     }
   }
@@ -932,9 +979,7 @@ int finish_hash(sd_plan* p) {
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
-  std::vector<int> types;
-  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
-  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  const std::vector<int> types = partial_field_types(sp);
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
   for (uint32_t g = 0; g < count; g++) {
@@ -945,7 +990,7 @@ int finish_hash(sd_plan* p) {
       if ((hn[g] >> k) & 1u) v.isnull = true;
       else if (types[k] == SD_STRING) v.s = p->key_vals[k][(size_t)code];
       else if (type_is_fp(types[k])) memcpy(&v.d, &code, 8);
-      else v.i = code;
+      else { v.i = code; v.w = code; }
       vals.push_back(v);
     }
     append_agg_fields(sp, &hv[(size_t)g * ns], vals);
@@ -986,7 +1031,7 @@ int finish_project(sd_plan* p) {
   std::vector<int> str_col(np, -1);
   for (int j = 0; j < np; j++) {
     const sd_expr& e = sp.exprs[sp.proj[j]];
-    types.push_back(e.type);
+    types.push_back(field_type(e.type, e.type == SD_DECIMAL ? decimal_ps(sp, sp.proj[j]) : 0));
     if (e.type == SD_STRING) str_col[j] = e.a;
   }
   std::vector<uint8_t>& out = p->finished_rows;
@@ -1010,7 +1055,7 @@ int finish_project(sd_plan* p) {
         if (code < 0 || code >= (int64_t)sc.dict_strings.size() || code == sc.dev.dict_n) { if (code == sc.dev.dict_n) v.isnull = true; else return set_error(SD_ERR_CUDA, "dictionary code %lld out of range", (long long)code); }
         else v.s = sc.dict_strings[(size_t)code];
       } else if (type_is_fp(types[j])) memcpy(&v.d, &raw, 8);
-      else v.i = (int64_t)raw;
+      else { v.i = (int64_t)raw; v.w = v.i; }
     }
     emit_unsafe_row(out, types, vals);
   }
@@ -1232,9 +1277,7 @@ static int finish_dense(sd_plan* p) {
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
   // partial rows: UnsafeRow(group keys ++ aggregate buffers) (SnappyHashAggregateExec.scala:1148-1178)
-  std::vector<int> types;
-  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
-  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  const std::vector<int> types = partial_field_types(sp);
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
   int64_t nrows = 0;
@@ -1513,9 +1556,7 @@ static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t
     return 0;
   }
   const int nk = (int)sp.keys.size();
-  std::vector<int> types;
-  for (int k = 0; k < nk; k++) types.push_back(sp.exprs[sp.keys[k]].type);
-  for (auto& m : sp.agg_map) { types.push_back(m.buf_type); if (m.fn == SD_AGG_AVG) types.push_back(SD_LONG); }
+  const std::vector<int> types = partial_field_types(sp);
   const int n = (int)types.size();
   struct Group { std::vector<HVal> keys; std::vector<HVal> bufs; };
   std::vector<Group> groups;   // insertion order
@@ -1556,11 +1597,14 @@ static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t
           case SD_AGG_SUM:
             if (!in.isnull) {
               if (m.buf_type == SD_DOUBLE) b.d = (b.isnull ? 0.0 : b.d) + in.d;
+              else if (m.buf_type == SD_DECIMAL) { b.w = (b.isnull ? (i128)0 : b.w) + in.w; b.i = (int64_t)b.w; }
               else b.i = (int64_t)((uint64_t)(b.isnull ? 0 : b.i) + (uint64_t)in.i);
               b.isnull = false;
             }
             k++; break;
-          case SD_AGG_AVG: b.d += in.d; g->bufs[k + 1].i += f[nk + k + 1].i; k += 2; break;
+          case SD_AGG_AVG:
+            if (m.buf_type == SD_DECIMAL) { b.w += in.w; b.i = (int64_t)b.w; } else b.d += in.d;
+            g->bufs[k + 1].i += f[nk + k + 1].i; k += 2; break;
           default:
             if (!in.isnull) {
               if (b.isnull) b = in;
@@ -1582,9 +1626,7 @@ static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t
     }
     groups.push_back(g);
   }
-  std::vector<int> otypes(types.begin(), types.begin() + nk);
-  if (evaluate) { for (auto& m : sp.agg_map) otypes.push_back(m.fn == SD_AGG_AVG ? (int)SD_DOUBLE : m.buf_type); }
-  else otypes = types;
+  const std::vector<int> otypes = evaluate ? final_field_types(sp) : types;
   std::vector<HVal> vals;
   for (auto& g : groups) {
     vals.assign(g.keys.begin(), g.keys.end());
@@ -1594,10 +1636,29 @@ static int merge_rows_impl(const PlanSpec& sp, const void* partial_rows, int64_t
       for (auto& m : sp.agg_map) {
         if (m.fn == SD_AGG_AVG) {   // Average.evaluateExpression: sum / count, NULL when count == 0
           HVal v;
-          if (g.bufs[k + 1].i == 0) v.isnull = true; else v.d = g.bufs[k].d / (double)g.bufs[k + 1].i;
+          const int64_t cnt = g.bufs[k + 1].i;
+          if (cnt == 0) v.isnull = true;
+          else if (m.buf_type == SD_DECIMAL) {
+            // Cast(Cast(sum, DECIMAL(p+14,s+4)) / Cast(count, ...), DECIMAL(p+4,s+4)): the quotient at scale s+4, HALF_UP
+            const int ft = otypes[vals.size()];
+            const i128 num = g.bufs[k].w * pow10_128(ft_scale(ft) - (m.in_ps & 0xff)), den = cnt;
+            i128 q = num / den, rem = num % den;
+            if (rem < 0) rem = -rem;
+            if (2 * rem >= den) q += (num < 0 ? -1 : 1);
+            if (q >= pow10_128(ft_precision(ft)) || q <= -pow10_128(ft_precision(ft))) v.isnull = true;   // does not fit: NULL
+            else { v.w = q; v.i = (int64_t)q; }
+          } else v.d = g.bufs[k].d / (double)cnt;
           vals.push_back(v);
           k += 2;
-        } else { vals.push_back(g.bufs[k]); k++; }
+        } else {
+          HVal v = g.bufs[k];
+          if (m.fn == SD_AGG_SUM && m.buf_type == SD_DECIMAL && !v.isnull) {   // a sum that needs more than p+10 digits is NULL (changePrecision fails)
+            const i128 lim = pow10_128(m.buf_ps >> 8);
+            if (v.w >= lim || v.w <= -lim) v.isnull = true;
+          }
+          vals.push_back(v);
+          k++;
+        }
       }
     }
     emit_unsafe_row(out, otypes, vals);

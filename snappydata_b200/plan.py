@@ -20,7 +20,7 @@ class E:
     """Expression node under construction."""
 
     def __init__(self, b: "PlanBuilder", op: int, t: SqlType, a: object = 0, bb: object = 0, c: int = 0):
-        self.b, self.op, self.t, self.a, self.bb, self.c = b, op, SqlType(t), a, bb, c
+        self.b, self.op, self.t, self.a, self.bb, self.c = b, op, SqlType(t), a, bb, c   # DECIMAL LIT / CAST: c = (precision << 8) | scale
 
     # -- arithmetic (operands must already have the same type; use cast()) ---------------------
     def _bin(self, op, other, t=None):
@@ -50,7 +50,10 @@ class E:
 
     def is_null(self): return E(self.b, Op.ISNULL, SqlType.BOOLEAN, self)
     def is_not_null(self): return E(self.b, Op.ISNOTNULL, SqlType.BOOLEAN, self)
-    def cast(self, t: SqlType): return self if SqlType(t) == self.t else E(self.b, Op.CAST, t, self)
+    def cast(self, t: SqlType, precision: int = 0, scale: int = 0):
+        if SqlType(t) == self.t and SqlType(t) != SqlType.DECIMAL:
+            return self
+        return E(self.b, Op.CAST, t, self, 0, (precision << 8) | scale if SqlType(t) == SqlType.DECIMAL else 0)
     def startswith(self, lit: "E"): return E(self.b, Op.STARTSWITH, SqlType.BOOLEAN, self, lit)
 
     def isin(self, n: int):
@@ -71,14 +74,16 @@ class PlanBuilder:
         self._proj: List[E] = []
 
     # scan columns (ColumnTableScan.output)
-    def col(self, t: SqlType, table_ordinal: int, nullable: bool = False, scale: int = 0) -> E:
-        self.cols.append((SqlType(t), bool(nullable), int(table_ordinal), int(scale)))
+    def col(self, t: SqlType, table_ordinal: int, nullable: bool = False, scale: int = 0, precision: int = 0) -> E:
+        if SqlType(t) == SqlType.DECIMAL and not precision:
+            precision = 18
+        self.cols.append((SqlType(t), bool(nullable), int(table_ordinal), int(scale), int(precision)))
         return E(self, Op.COL, t, len(self.cols) - 1)
 
-    def lit(self, t: SqlType) -> E:
-        """A runtime literal slot."""
+    def lit(self, t: SqlType, precision: int = 0, scale: int = 0) -> E:
+        """A runtime literal slot (a DECIMAL literal's value is its unscaled integer at `scale`)."""
         self.literal_types.append(SqlType(t))
-        return E(self, Op.LIT, t, len(self.literal_types) - 1)
+        return E(self, Op.LIT, t, len(self.literal_types) - 1, 0, (precision << 8) | scale if SqlType(t) == SqlType.DECIMAL else 0)
 
     def coerce(self, x, t: SqlType) -> E:
         if isinstance(x, E):
@@ -104,11 +109,11 @@ class PlanBuilder:
             if id(e) in memo:
                 return memo[id(e)]
             if e.op in (Op.COL, Op.LIT):
-                rec = (e.op, int(e.t), int(e.a), 0, 0)
+                rec = (e.op, int(e.t), int(e.a), 0, int(e.c))
             elif e.op == Op.IN:
                 rec = (e.op, int(e.t), emit(e.a), int(e.bb), int(e.c))
             elif e.op in (Op.NEG, Op.CAST, Op.NOT, Op.ISNULL, Op.ISNOTNULL):
-                rec = (e.op, int(e.t), emit(e.a), 0, 0)
+                rec = (e.op, int(e.t), emit(e.a), 0, int(e.c) if e.op == Op.CAST else 0)
             else:
                 ia = emit(e.a)
                 ib = emit(e.bb)

@@ -205,6 +205,62 @@ def case_sha_sum_of_every_numeric_type_per_string_key(_run):
         assert all(type(s) is py for s in got.values()), (t, got)
 
 
+def case_sha_decimal_sum_and_avg_per_string_key(_run):
+    """SHAByteBufferTest.scala:710-731 ("Big Decimal with precision < 18 as aggregate column"): decimal(12,5) column holding
+    0.3 * i for i = 0..9, key 'col{i/5}': sum = 3.0 and 10.5 (the test allows 0.1; here the unscaled values are exact).
+    Spark 2.1.1: Sum(DECIMAL(12,5)) -> DECIMAL(22,5) (wider than 18 digits -> BigInteger bytes in the UnsafeRow),
+    Average -> DECIMAL(16,9) = sum / count rounded HALF_UP."""
+    i = np.arange(10)
+    keys = np.array([b"col%d" % (x // 5) for x in i], dtype=object)
+    unscaled = (30000 * i).astype(np.int64)                      # 0.3 * i at scale 5
+    schema = [("v", T.DECIMAL, True), ("k", T.STRING, True)]
+    batch = build_batch(10, schema, {"v": unscaled, "k": keys}, {})
+    b = PlanBuilder()
+    v, k = b.col(T.DECIMAL, 0, True, scale=5, precision=12), b.col(T.STRING, 1, True)
+    b.group_by(k)
+    b.sum(v).avg(v).min(v).max(v).count(v)
+    desc = b.build()
+    assert desc.final_schema()[1:3] == [(T.DECIMAL, 22, 5), (T.DECIMAL, 16, 9)]
+    rows, _ = _run(desc, [], [batch])
+    got = {r[0]: r[1:] for r in rows}
+    assert got[b"col0"] == [300000, 600000000, 0, 120000, 5]              # 3.00000, 0.600000000, 0, 1.2
+    assert got[b"col1"] == [1050000, 2100000000, 150000, 270000, 5]       # 10.50000, 2.100000000, 1.5, 2.7
+    # a sum that does not fit 18 digits, and HALF_UP rounding of the average (negative and positive)
+    big = np.array([999_999_999_999_999_999, 999_999_999_999_999_999, 1], dtype=np.int64)     # DECIMAL(18,0)
+    small = np.array([1, 1, 0], dtype=np.int64)                                               # avg = 2/3 -> 0.6667
+    neg = -small
+    batch = build_batch(3, [("a", T.DECIMAL, False), ("b", T.DECIMAL, False), ("c", T.DECIMAL, False)], {"a": big, "b": small, "c": neg}, {})
+    b = PlanBuilder()
+    ca, cb, cc = b.col(T.DECIMAL, 0, False, 0, 18), b.col(T.DECIMAL, 1, False, 0, 18), b.col(T.DECIMAL, 2, False, 0, 18)
+    b.sum(ca).avg(cb).avg(cc)
+    (s, a1, a2), = _run(b.build(), [], [batch])[0]
+    assert s == 1_999_999_999_999_999_999 and a1 == 6667 and a2 == -6667
+
+
+def case_casts_follow_spark(_run):
+    """Spark 2.1.1 Cast restated: to BOOLEAN is `v != 0` (256 is TRUE: no truncation through a byte),
+    DECIMAL(p,s) -> DOUBLE divides by 10^s, INT -> DECIMAL(p,s) multiplies by 10^s and yields NULL when p digits do not hold it."""
+    ints = np.array([0, 256, -1, 65536, 7], dtype=np.int32)
+    dec = np.array([12345, -250, 0, 99999, 100], dtype=np.int64)     # DECIMAL(7,2): 123.45, -2.50, 0, 999.99, 1.00
+    batch = build_batch(5, [("i", T.INT, False), ("d", T.DECIMAL, False)], {"i": ints, "d": dec}, {})
+    b = PlanBuilder()
+    ci, cd = b.col(T.INT, 0, False), b.col(T.DECIMAL, 1, False, scale=2, precision=7)
+    b.filter(ci.cast(T.BOOLEAN))
+    b.count().sum(cd.cast(T.DOUBLE)).sum(ci.cast(T.DECIMAL, 6, 2)).count(ci.cast(T.DECIMAL, 6, 2))
+    (cnt, sd, sdec, cdec), = _run(b.build(), [], [batch])[0]
+    assert cnt == 4                                   # 256, -1, 65536, 7 are TRUE
+    assert abs(sd - (-2.5 + 0.0 + 999.99 + 1.0)) < 1e-9
+    assert cdec == 3 and sdec == (256 - 1 + 7) * 100  # 65536 needs 5 integral digits: DECIMAL(6,2) holds 4 -> NULL
+    import pytest
+    from snappydata_b200.capi import SdError
+    for bad in (lambda b, ci, cd: cd.cast(T.INT), lambda b, ci, cd: ci.cast(T.DATE), lambda b, ci, cd: cd.cast(T.DECIMAL, 7, 1)):
+        b = PlanBuilder()
+        ci, cd = b.col(T.INT, 0, False), b.col(T.DECIMAL, 1, False, scale=2, precision=7)
+        b.count(bad(b, ci, cd))
+        with pytest.raises(SdError):
+            _run(b.build(), [], [batch])
+
+
 CASES = [case_sha_one_nullable_string_key_closed_form, case_sha_two_nullable_string_keys_closed_form,
          case_delta_stats_point_filters_after_updates, case_basic_delete_and_update_counts,
-         case_sha_sum_of_every_numeric_type_per_string_key]
+         case_sha_sum_of_every_numeric_type_per_string_key, case_sha_decimal_sum_and_avg_per_string_key, case_casts_follow_spark]

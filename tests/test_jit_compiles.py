@@ -36,6 +36,12 @@ def _plans():
     b.group_by(s)
     b.count().sum(f).max(h)
     out["groups_nullable"] = b.build()
+    b = PlanBuilder()   # DECIMAL aggregates (two-slot wide sums), Spark casts incl. overflow-to-NULL
+    dc, ic, sk = b.col(T.DECIMAL, 0, True, scale=5, precision=12), b.col(T.INT, 1, False), b.col(T.STRING, 2, True)
+    b.filter(ic.cast(T.BOOLEAN) & (dc >= b.lit(T.DECIMAL, 12, 5)))
+    b.group_by(sk)
+    b.sum(dc).avg(dc).min(dc).sum(dc.cast(T.DOUBLE)).sum(ic.cast(T.DECIMAL, 9, 2)).sum(dc.cast(T.DECIMAL, 15, 7))
+    out["decimal"] = b.build()
     return out
 
 
@@ -72,7 +78,7 @@ def _compile(source, name):
     return dt
 
 
-@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable"])
+@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable", "decimal"])
 def test_every_kernel_variant_compiles_for_sm_100a(label):
     desc = _plans()[label]
     seen = set()

@@ -216,7 +216,7 @@ struct Gen {
     for (int k : p.keys) if (!chk(k)) return fail(SD_ERR_INVALID, "key expression out of range");
     for (auto& a : p.aggs) if (a.expr != -1 && !chk(a.expr)) return fail(SD_ERR_INVALID, "aggregate input out of range");
     for (int k : p.proj) if (!chk(k)) return fail(SD_ERR_INVALID, "projection expression out of range");
-    if ((int)p.keys.size() > MAX_KEYS) return fail(SD_ERR_UNSUPPORTED, "more than 4 grouping keys");
+    if ((int)p.keys.size() > MAX_HASH_KEYS) return fail(SD_ERR_UNSUPPORTED, "more than 32 grouping keys");
     return 0;
   }
 
@@ -582,7 +582,7 @@ struct Gen {
         slt << NL << " ? " << ident << " : " << (f ? "sd::f2u((double)" + V + ")" : "(uint64_t)(int64_t)" + V) << ";\n";
       }
     }
-    if ((int)p.tables.size() > MAX_TABLES) return fail(SD_ERR_UNSUPPORTED, "more than 16 dictionary lookup tables in one plan");
+    if ((int)p.tables.size() > MAX_TABLES) return fail(SD_ERR_UNSUPPORTED, "more than 40 dictionary lookup tables in one plan");
     sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups << ";litnull=" << p.lit_nullable << ";slow=" << p.slow_paths;
     p.signature = sig.str();
     char hbuf[32];
@@ -675,7 +675,8 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
       if (!(e.op == SD_OP_COL && e.type == SD_STRING)) all_dict_strings = false;
       if (e.type == SD_STRING && e.op != SD_OP_COL) { err = "STRING group key that is not a dictionary column"; return SD_ERR_UNSUPPORTED; }
     }
-    out.mode = (all_dict_strings && !(opt && opt->force_hash)) ? MODE_GROUPS : MODE_HASH;
+    // dense table: <= 4 dictionary-string keys; anything else (other key types, more keys) goes through the hash table
+    out.mode = (all_dict_strings && (int)out.keys.size() <= MAX_KEYS && !(opt && opt->force_hash)) ? MODE_GROUPS : MODE_HASH;
   }
   // kernel shape (see tools/sweep.sh for the measurements behind the defaults): staged fast path on;
   // 4 rows per thread per tile; narrow no-key scans run 3 CTAs per SM, register-table group-bys 1.

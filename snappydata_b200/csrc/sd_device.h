@@ -49,8 +49,9 @@ constexpr int tile_smem_bytes(int nc, int rpt) {
 }
 
 constexpr int MAX_LITERALS = 64;
-constexpr int MAX_TABLES = 16;   // per-batch lookup tables (truth tables + key maps) of one plan
-constexpr int MAX_KEYS = 4;
+constexpr int MAX_TABLES = 40;   // per-batch lookup tables (truth tables + key maps) of one plan
+constexpr int MAX_KEYS = 4;        // dense group table (MODE_GROUPS): mixed-radix index over <= 4 dictionary keys
+constexpr int MAX_HASH_KEYS = 32;  // hash table (MODE_HASH): one NULL bit per key in a 32-bit word
 
 // One update delta of one column (enc/ColumnDeltaEncoder.scala:300-331): ascending positions +
 // values in the column's normal encoding; null bits index the relative entry.

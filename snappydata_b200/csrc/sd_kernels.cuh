@@ -542,10 +542,15 @@ struct StageInfo {
   static constexpr int BYTES = stage_col_off<PLAN>(PLAN::NC);
 };
 
+// one bit per scan column: 32 bits for plans of <= 32 columns (the common case keeps its register budget), 64 beyond
+template <bool WIDE> struct CMaskT { typedef uint32_t T; };
+template <> struct CMaskT<true> { typedef uint64_t T; };
+#define SD_CMASK(PLAN) typename CMaskT<(PLAN::NC > 32)>::T
+
 // element width of column C in this batch (dictionary indexes are int16 or int32)
 template <class PLAN, int C>
-__device__ __forceinline__ int col_width(uint32_t c16) {
-  return PLAN::kind(C) == K_CODE ? (((c16 >> C) & 1u) ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
+__device__ __forceinline__ int col_width(SD_CMASK(PLAN) c16) {
+  return PLAN::kind(C) == K_CODE ? (((c16 >> C) & 1) ? 2 : 4) : (int)sizeof(typename KindT<PLAN::kind(C)>::T);
 }
 
 // per-chunk copy of the descriptor fields the producer needs (with the SM's shared memory carved out for the ring
@@ -565,7 +570,7 @@ __device__ __forceinline__ void load_producer_cols(const DevBatch<PLAN::NC>& b, 
 // ordinal; with NULLs the tile's stored values are [tile_start - nulls_before(tile_start), ... ) and their count is
 // rows - nulls_in_tile, both from the host-computed prefix (one entry per NULL_PREFIX_ROWS rows)
 template <class PLAN, int C>
-__device__ __forceinline__ void col_copy_range(const int32_t* tile_nulls, uint32_t c16, int64_t tile_start, int rows, int64_t* src_off, uint32_t* bytes) {
+__device__ __forceinline__ void col_copy_range(const int32_t* tile_nulls, SD_CMASK(PLAN) c16, int64_t tile_start, int rows, int64_t* src_off, uint32_t* bytes) {
   const int w = col_width<PLAN, C>(c16);
   int64_t first = tile_start;
   int cnt = rows;
@@ -580,7 +585,7 @@ __device__ __forceinline__ void col_copy_range(const int32_t* tile_nulls, uint32
   *bytes = cnt > 0 ? (uint32_t)(((off & 15) + (int64_t)cnt * w + 15) & ~int64_t(15)) : 0u;   // buffers are padded: over-reading is safe
 }
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void issue_tile_copies(const ProducerCols<PLAN::NC>& pc, uint32_t c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
+__device__ __forceinline__ void issue_tile_copies(const ProducerCols<PLAN::NC>& pc, SD_CMASK(PLAN) c16, int64_t tile_start, int rows, uint8_t* stage, uint64_t* bar, Seq<Cs...>) {
   int64_t off[PLAN::NC > 0 ? PLAN::NC : 1];
   uint32_t bytes[PLAN::NC > 0 ? PLAN::NC : 1];
   uint32_t total = 0;
@@ -593,7 +598,7 @@ __device__ __forceinline__ void issue_tile_copies(const ProducerCols<PLAN::NC>& 
 
 // consumer: registers <- stage (conflict-free: consecutive lanes read consecutive 16/8/4/2 bytes)
 template <class PLAN, int C>
-__device__ __forceinline__ void load_col_staged(uint32_t c16, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
+__device__ __forceinline__ void load_col_staged(SD_CMASK(PLAN) c16, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
   typedef typename KindT<PLAN::kind(C)>::T T;
   constexpr int K = PLAN::kind(C);
   const uint8_t* base = stage + stage_col_off<PLAN>(C);
@@ -602,7 +607,7 @@ __device__ __forceinline__ void load_col_staged(uint32_t c16, const uint8_t* sta
   for (int u = 0; u < PLAN::RPT / 2; u++) {
     const int p = u * 2 * THREADS + 2 * (int)threadIdx.x;
     if (K == K_CODE) {
-      if ((c16 >> C) & 1u) {
+      if ((c16 >> C) & 1) {
         uint32_t x = *reinterpret_cast<const uint32_t*>(base + p * 2);
         regs.v[2 * u] = (T)(int16_t)(x & 0xffffu);
         regs.v[2 * u + 1] = (T)(int16_t)(x >> 16);
@@ -633,7 +638,7 @@ __device__ __forceinline__ void load_col_staged(uint32_t c16, const uint8_t* sta
 // consumer, column with NULLs: row -> (is null, value index) through the null words; the value sits in the stage at
 // [shift + (k - first) * w] where `first` is the tile's first stored value
 template <class PLAN, int C>
-__device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, uint32_t c16, int64_t tile_start, int num_rows,
+__device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, SD_CMASK(PLAN) c16, int64_t tile_start, int num_rows,
                                                       const TileSmem<PLAN>& sm, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
   typedef typename KindT<PLAN::kind(C)>::T T;
   constexpr int K = PLAN::kind(C);
@@ -665,19 +670,19 @@ __device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, uint32_
   }
 }
 template <class PLAN, int C>
-__device__ __forceinline__ void load_col_staged_any(const DevCol& col, uint32_t c16, int64_t tile_start, int num_rows,
+__device__ __forceinline__ void load_col_staged_any(const DevCol& col, SD_CMASK(PLAN) c16, int64_t tile_start, int num_rows,
                                                     const TileSmem<PLAN>& sm, const uint8_t* stage, ColRegs<PLAN, C>& regs) {
   if (PLAN::col_nullable(C) && col.nulls) load_col_staged_nulls<PLAN, C>(col, c16, tile_start, num_rows, sm, stage, regs);
   else load_col_staged<PLAN, C>(c16, stage, regs);
 }
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void load_all_staged_nulls(const DevBatch<PLAN::NC>& b, uint32_t c16, int64_t tile_start, const TileSmem<PLAN>& sm,
+__device__ __forceinline__ void load_all_staged_nulls(const DevBatch<PLAN::NC>& b, SD_CMASK(PLAN) c16, int64_t tile_start, const TileSmem<PLAN>& sm,
                                                       const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
   int dummy[] = {0, (load_col_staged_any<PLAN, Cs>(b.cols[Cs], c16, tile_start, b.num_rows, sm, stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
   (void)dummy;
 }
 template <class PLAN, int... Cs>
-__device__ __forceinline__ void load_all_staged(uint32_t c16, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
+__device__ __forceinline__ void load_all_staged(SD_CMASK(PLAN) c16, const uint8_t* stage, AllCols<PLAN, Seq<Cs...>>& regs, Seq<Cs...>) {
   int dummy[] = {0, (load_col_staged<PLAN, Cs>(c16, stage, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
   (void)dummy;
 }
@@ -727,9 +732,10 @@ __device__ __forceinline__ void load_tables(RowCtx& ctx, const uint8_t* aux) {
 
 // bit c set: K_CODE column c of this batch uses int16 dictionary indexes (else int32)
 template <class PLAN, int... Cs>
-__device__ __forceinline__ uint32_t code16_mask(const DevBatch<PLAN::NC>& b, Seq<Cs...>) {
-  uint32_t m = 0;
-  int dummy[] = {0, (PLAN::kind(Cs) == K_CODE ? (m |= (b.cols[Cs].enc == ENC_DICTIONARY ? 1u : 0u) << Cs, 0) : 0)...};
+__device__ __forceinline__ SD_CMASK(PLAN) code16_mask(const DevBatch<PLAN::NC>& b, Seq<Cs...>) {
+  typedef SD_CMASK(PLAN) M;
+  M m = 0;
+  int dummy[] = {0, (PLAN::kind(Cs) == K_CODE ? (m |= (M)(b.cols[Cs].enc == ENC_DICTIONARY ? 1 : 0) << Cs, 0) : 0)...};
   (void)dummy;
   return m;
 }
@@ -777,7 +783,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           const int num_rows = b.num_rows;
           const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;
           const int tile0 = chunk * CHUNK_TILES, tile_end = min(tile0 + CHUNK_TILES, ntiles);
-          const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
+          const SD_CMASK(PLAN) c16 = code16_mask<PLAN>(b, ColSeq());
           ProducerCols<PLAN::NC> pc;
           load_producer_cols<PLAN>(b, pc, ColSeq());
           for (int tile = tile0; tile < tile_end; tile++) {
@@ -837,7 +843,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     // else reaching it is a host-side bug: stop loudly instead of aggregating garbage
     if (!PLAN::SLOW_PATHS && !fast) __trap();
     load_tables<PLAN::NTABLES>(ctx, b.aux);
-    const uint32_t c16 = code16_mask<PLAN>(b, ColSeq());
+    const SD_CMASK(PLAN) c16 = code16_mask<PLAN>(b, ColSeq());
     uint32_t c_scanned = 0, c_passed = 0;
     const int tile0 = chunk * CHUNK_TILES;
     const int ntiles = (num_rows + TILE_ROWS - 1) / TILE_ROWS;

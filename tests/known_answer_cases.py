@@ -261,6 +261,42 @@ def case_casts_follow_spark(_run):
             _run(b.build(), [], [batch])
 
 
+def case_sha_null_key_bit_masking_1_to_32_key_columns(_run):
+    """SHAByteBufferTest.scala:407-528 ("null grouping key bit masking for 1 to 100 columns in group by"), second half, for
+    n = 1..32 key columns (this engine's limit is 32 grouping keys): 100 rows (1, 2, 'col-3'..'col-{n+2}') and 100 rows
+    (4, 8, the same keys but the n-th NULL) -> exactly two groups, sums 100 / 200 and 400 / 800, the group with the NULL
+    last key carrying 400."""
+    rows_per = 100
+    for nkeys in (1, 2, 3, 4, 5, 8, 17, 32):
+        names = ["col%d" % j for j in range(3, nkeys + 3)]
+        schema = [("num1", T.INT, True), ("num2", T.INT, True)] + [(nm, T.STRING, True) for nm in names]
+        data = {"num1": np.array([1] * rows_per + [4] * rows_per, dtype=np.int32),
+                "num2": np.array([2] * rows_per + [8] * rows_per, dtype=np.int32)}
+        nulls = {}
+        for j, nm in enumerate(names):
+            data[nm] = np.array([b"col-%d" % (j + 3)] * (2 * rows_per), dtype=object)
+            nulls[nm] = np.array([False] * rows_per + [j == nkeys - 1] * rows_per)
+        batch = build_batch(2 * rows_per, schema, data, nulls)
+        b = PlanBuilder()
+        n1, n2 = b.col(T.INT, 0, True), b.col(T.INT, 1, True)
+        keys = [b.col(T.STRING, 2 + j, True) for j in range(nkeys)]
+        b.group_by(*keys)
+        b.sum(n1).sum(n2)
+        rows, _ = _run(b.build(), [], [batch])
+        assert len(rows) == 2, (nkeys, rows)
+        found_null = False
+        for r in rows:
+            ks, (s1, s2) = r[:nkeys], r[nkeys:]
+            assert ks[:-1] == [b"col-%d" % (j + 3) for j in range(nkeys - 1)]
+            if ks[-1] is None:
+                found_null = True
+                assert (s1, s2) == (rows_per * 4, rows_per * 8)
+            else:
+                assert ks[-1] == b"col-%d" % (nkeys + 2) and (s1, s2) == (rows_per * 1, rows_per * 2)
+        assert found_null
+
+
 CASES = [case_sha_one_nullable_string_key_closed_form, case_sha_two_nullable_string_keys_closed_form,
          case_delta_stats_point_filters_after_updates, case_basic_delete_and_update_counts,
-         case_sha_sum_of_every_numeric_type_per_string_key, case_sha_decimal_sum_and_avg_per_string_key, case_casts_follow_spark]
+         case_sha_sum_of_every_numeric_type_per_string_key, case_sha_decimal_sum_and_avg_per_string_key, case_casts_follow_spark,
+         case_sha_null_key_bit_masking_1_to_32_key_columns]

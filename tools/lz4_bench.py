@@ -37,14 +37,21 @@ def main():
     L.sdx_lz4_expand.restype = C.c_int
     L.sdx_lz4_expand.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_double)]
-    tables = [dict(kinds(rows, np.random.default_rng(100 + i))) for i in range(nbuf)]   # nbuf different buffers per kind
-    for name in tables[0]:
-        raws = [t[name] for t in tables]
-        blocks = [compress_lz4(b, force=True)[8:] for b in raws]
+    want_kinds = [int(x) for x in os.environ.get("LZ4_KINDS", "0,1,2,3,4").split(",")]
+    want_variants = [int(x) for x in os.environ.get("LZ4_VARIANTS", "0,1,2,3").split(",")]
+    ndistinct = min(nbuf, int(os.environ.get("LZ4_DISTINCT", "256")))   # distinct buffers per kind (the launch cycles through them)
+    names = [n for n, _ in kinds(8, np.random.default_rng(0))]
+    for ki in want_kinds:
+        name = names[ki]
+        base = [dict(kinds(rows, np.random.default_rng(100 + i)))[name] for i in range(ndistinct)]
+        raws = [base[i % ndistinct] for i in range(nbuf)]
+        cblocks = [compress_lz4(b, force=True)[8:] for b in base]
+        blocks = [cblocks[i % ndistinct] for i in range(nbuf)]
         ratio = sum(map(len, blocks)) / sum(map(len, raws))
-        for variant in (0, 1, 2, 3):   # bit 0: dense kernel shape, bit 1: window parse
+        for variant in want_variants:   # bit 0: dense kernel shape, bit 1: window parse
             for mis in ((0, 8) if variant == 0 else (8,)):
-                keep = [C.create_string_buffer(b, len(b)) for b in blocks]
+                keep = [C.create_string_buffer(b, len(b)) for b in cblocks]
+                keep = [keep[i % ndistinct] for i in range(nbuf)]
                 outs = [C.create_string_buffer(len(b)) for b in raws]
                 bp = (C.c_void_p * nbuf)(*[C.cast(k, C.c_void_p) for k in keep])
                 op = (C.c_void_p * nbuf)(*[C.cast(o, C.c_void_p) for o in outs])

@@ -143,8 +143,10 @@ typedef struct sd_literal {
  * sd_plan_desc.cols.  Buffers may be heap or direct memory; the library has finished reading (or
  * copied) them when sd_batch_submit returns (ownership rule).  A buffer whose first
  * int32 is negative is a compressed envelope (encoders/.../store/CompressionUtils.scala:53-61): LZ4 (-1)
- * envelopes are accepted -- only the compressed bytes are copied and the block is expanded on the device;
- * Snappy (-2) is refused. */
+ * envelopes are accepted -- only the compressed bytes are copied and the block is expanded on the device (run-length
+ * and variable-width STRING bodies, whose layout needs a host walk, are expanded on the host instead); Snappy (-2)
+ * envelopes, compressed update deltas and compressed delete masks are decompressed on the host, as the reference's own
+ * iterator does (ColumnBatchIterator.scala:102-113). */
 typedef struct sd_batch {
   int32_t num_rows;
   int32_t ncols;
@@ -272,6 +274,9 @@ int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, vo
                          int64_t* out_len);
 /* host LZ4 prefix decoder used to lay out compressed column buffers (test hook) */
 int64_t sdx_lz4_decode_prefix(const void* src, int64_t src_len, void* dst, int64_t want);
+/* host decompression of a stored envelope [-codecId][uncompressedLen][payload] (LZ4 = 1, Snappy = 2), as the engine
+ * applies it to update deltas, delete masks and Snappy column buffers (test hook; no CUDA call) */
+int sdx_decompress_envelope(const void* buf, int64_t len, void* out, int64_t cap, int64_t* out_len);
 int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id,
                          int64_t* batch_id);
 /* the batch-skipping decision (ColumnTableScan.scala:820-963) of a plan's filter for one stats row: *pass = 0 when the

@@ -422,6 +422,56 @@ def compress_lz4(buf: bytes, force: bool = False) -> bytes:
     return struct.pack("<ii", -CODEC_LZ4, len(buf)) + dst.raw[:n]
 
 
+def compress_snappy(buf: bytes) -> bytes:
+    """[-2][uncompressedLen][Snappy raw stream] (CompressionCodecId.SNAPPY_ID = 2, CompressionUtils.scala:125-168).
+    A small greedy encoder for fixtures (no snappy library in this image): varint length, then literals and 2-byte-offset
+    copies found through a hash of 4-byte windows -- every element kind the decoder must handle except 4-byte offsets."""
+    n = len(buf)
+    out = bytearray()
+    v = n
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            break
+
+    def literal(lo, hi):
+        while lo < hi:
+            ln = min(hi - lo, 1 << 16)
+            if ln <= 60:
+                out.append((ln - 1) << 2)
+            elif ln <= 256:
+                out.extend(bytes([60 << 2, ln - 1]))
+            else:
+                out.extend(bytes([61 << 2, (ln - 1) & 0xFF, (ln - 1) >> 8]))
+            out.extend(buf[lo:lo + ln])
+            lo += ln
+
+    table = {}
+    i = lit = 0
+    while i + 4 <= n:
+        key = buf[i:i + 4]
+        j = table.get(key)
+        table[key] = i
+        if j is not None and 0 < i - j < 65536:
+            ln = 4
+            while i + ln < n and ln < 64 and buf[j + ln] == buf[i + ln]:
+                ln += 1
+            literal(lit, i)
+            off = i - j
+            if 4 <= ln <= 11 and off < 2048:
+                out += bytes([1 | ((ln - 4) << 2) | ((off >> 8) << 5), off & 0xFF])
+            else:
+                out += bytes([2 | ((ln - 1) << 2), off & 0xFF, off >> 8])
+            i += ln
+            lit = i
+        else:
+            i += 1
+    literal(lit, n)
+    return struct.pack("<ii", -CODEC_SNAPPY, n) + bytes(out)
+
+
 def decompress(buf: bytes) -> bytes:
     (first,) = struct.unpack_from("<i", buf, 0)
     if first >= 0:

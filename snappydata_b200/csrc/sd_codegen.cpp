@@ -434,7 +434,33 @@ struct Gen {
             t = (int)p.tables.size() - 1;
             table_of_node[node] = t;
           } else t = it->second;
-          o << "    const int t" << N << " = ctx.table(" << t << ")[r.c" << col << "];\n";
+          // dictionary batch: truth table indexed by the code.  Raw (variable-width) batch: compare the bytes on the device
+          const std::string C = std::to_string(col), rec = "ctx.strbase[" + C + "] + (uint32_t)r.c" + C;
+          const std::string rnull = p.cols[col].nullable ? "r.n" + C : std::string("false");
+          auto lnull = [&](int slot) { return p.lit_nullable ? "(((ctx.L->nullmask >> " + std::to_string(slot) + ") & 1ull) != 0)" : std::string("false"); };
+          std::string raw;
+          if (is_cmp(e.op)) {
+            const bool col_left = p.exprs[e.a].op == SD_OP_COL;
+            const int slot = p.exprs[col_left ? e.b : e.a].a;
+            int op = e.op;   // literal on the left: cmp(lit, col) = -cmp(col, lit)
+            if (!col_left) op = op == SD_OP_LT ? SD_OP_GT : op == SD_OP_LE ? SD_OP_GE : op == SD_OP_GT ? SD_OP_LT : op == SD_OP_GE ? SD_OP_LE : op;
+            const char* sym = op == SD_OP_EQ ? "==" : op == SD_OP_NE ? "!=" : op == SD_OP_LT ? "<" : op == SD_OP_LE ? "<=" : op == SD_OP_GT ? ">" : ">=";
+            raw = "((" + rnull + " || " + lnull(slot) + ") ? 2 : (sd::str_cmp_rec(" + rec + ", ctx.lit_bytes(" + std::to_string(slot) + "), ctx.lit_len(" +
+                  std::to_string(slot) + ")) " + sym + " 0 ? 1 : 0))";
+          } else if (e.op == SD_OP_STARTSWITH) {
+            const int slot = p.exprs[e.b].a;
+            raw = "((" + rnull + " || " + lnull(slot) + ") ? 2 : (sd::str_starts_rec(" + rec + ", ctx.lit_bytes(" + std::to_string(slot) + "), ctx.lit_len(" +
+                  std::to_string(slot) + ")) ? 1 : 0))";
+          } else {   // IN: TRUE on a match, else NULL when a literal is NULL, else FALSE; NULL value -> NULL
+            std::string any, anynull;
+            for (int k = 0; k < e.c; k++) {
+              const std::string S = std::to_string(e.b + k);
+              any += std::string(k ? " || " : "") + "(!" + lnull(e.b + k) + " && sd::str_cmp_rec(" + rec + ", ctx.lit_bytes(" + S + "), ctx.lit_len(" + S + ")) == 0)";
+              anynull += std::string(k ? " || " : "") + lnull(e.b + k);
+            }
+            raw = "(" + rnull + " ? 2 : ((" + any + ") ? 1 : ((" + anynull + ") ? 2 : 0)))";
+          }
+          o << "    const int t" << N << " = ctx.strbase[" << C << "] ? " << raw << " : (int)ctx.table(" << t << ")[r.c" << col << "];\n";
           finish_bool();
           return 0;
         }
@@ -493,7 +519,7 @@ struct Gen {
 
   int generate() {
     std::ostringstream sig;
-    sig << "v1;cols=";
+    sig << "v2;cols=";
     for (size_t c = 0; c < p.cols.size(); c++) sig << (c ? "," : "") << p.kinds[c] << (p.cols[c].nullable ? "n" : "");
     sig << ";filter=" << (p.filter >= 0 ? expr_text(p, p.filter) : std::string("-")) << ";keys=";
     for (size_t k = 0; k < p.keys.size(); k++) sig << (k ? "," : "") << expr_text(p, p.keys[k]);
@@ -538,15 +564,17 @@ struct Gen {
       }
     }
     std::ostringstream keyfn;
+    uint32_t strkeymask = 0;
     if (p.mode == MODE_HASH) {
       std::fill(done.begin(), done.end(), 0);
       for (size_t k = 0; k < p.keys.size(); k++) {
         const sd_expr& e = p.exprs[p.keys[k]];
-        if (e.op == SD_OP_COL && e.type == SD_STRING) {   // dictionary column: query-global id from the per-batch key map
-          p.tables.push_back(TableSpec{TABLE_KEYMAP, e.a, -1, (int)k});
+        if (e.op == SD_OP_COL && e.type == SD_STRING) {   // held by reference: address of the value's [len][bytes] record
+          p.tables.push_back(TableSpec{TABLE_KEYPTR, e.a, -1, (int)k});
           const int t = (int)p.tables.size() - 1;
-          keyfn << "    kc[" << k << "] = ctx.key_id(" << t << ", r.c" << e.a << ");\n";
-          if (p.cols[e.a].nullable) keyfn << "    if (r.n" << e.a << ") { knull |= " << (1u << k) << "u; kc[" << k << "] = 0; }\n";
+          strkeymask |= 1u << k;
+          if (p.cols[e.a].nullable) keyfn << "    if (r.n" << e.a << ") { knull |= " << (1u << k) << "u; kc[" << k << "] = 0; } else";
+          keyfn << "    kc[" << k << "] = ctx.str_ref(" << e.a << ", " << t << ", r.c" << e.a << ");\n";
         } else {
           int rc = emit_node(p.keys[k], done, keyfn);
           if (rc) return rc;
@@ -607,6 +635,8 @@ struct Gen {
     o << "  static constexpr int REG_GROUPS = " << p.reg_groups << ";\n";
     o << "  static constexpr bool SLOW_PATHS = " << (p.slow_paths ? "true" : "false") << ";\n";
     o << "  static constexpr int NTABLES = " << p.tables.size() << ";\n";
+    o << "  static constexpr unsigned STRKEYMASK = " << strkeymask << "u;\n";
+    { bool anys = false; for (auto& c : p.cols) anys = anys || c.type == SD_STRING; o << "  static constexpr bool ANY_STRING = " << (anys ? "true" : "false") << ";\n"; }
     o << "  __host__ __device__ static constexpr int kind(int c) { return ";
     for (int c = 0; c < nc; c++) o << "c == " << c << " ? " << p.kinds[c] << " : ";
     o << "0; }\n";

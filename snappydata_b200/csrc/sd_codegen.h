@@ -10,7 +10,9 @@
 
 namespace sd {
 
-enum TableKind { TABLE_TRUTH = 0, TABLE_KEYMAP = 1 };
+// TABLE_KEYPTR: per dictionary code the device address (int64) of the entry's [len][bytes] record -- string keys of the
+// hash table are held by reference and compared by their bytes
+enum TableKind { TABLE_TRUTH = 0, TABLE_KEYMAP = 1, TABLE_KEYPTR = 2 };
 
 // A per-batch lookup table indexed by a STRING column's dictionary code.
 struct TableSpec {

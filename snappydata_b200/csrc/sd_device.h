@@ -12,6 +12,7 @@ typedef int int32_t;
 typedef unsigned int uint32_t;
 typedef long long int64_t;
 typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
 #else
 #include <stdint.h>
 #endif
@@ -19,13 +20,19 @@ typedef unsigned long long uint64_t;
 namespace sd {
 
 // ---- column encodings as the kernels see them (enc/ColumnEncoding.scala:766-773) -------------
-enum : int32_t { ENC_UNCOMPRESSED = 0, ENC_RUN_LENGTH = 1, ENC_DICTIONARY = 2, ENC_BIG_DICTIONARY = 3, ENC_BOOLEAN_BITSET = 4 };
+enum : int32_t { ENC_UNCOMPRESSED = 0, ENC_RUN_LENGTH = 1, ENC_DICTIONARY = 2, ENC_BIG_DICTIONARY = 3, ENC_BOOLEAN_BITSET = 4,
+                 // engine-internal view of an Uncompressed variable-width STRING body (back-to-back [len:int32][bytes]
+                 // records, enc/Uncompressed.scala:116-161): DevCol.data = int32 byte position of every stored value's record
+                 // (built once at upload by walking the sequential cursor), DevCol.dict = the body the positions point into
+                 ENC_STR_RAW = 5 };
 
 // ---- register value kinds of a scan column ---------------------------------------------------
-// K_CODE: a STRING column travels through the kernel as its per-batch dictionary index ("code");
-// predicates on it are per-batch truth tables and group keys per-batch code->group maps, both
-// prepared on the host from the (tiny) dictionaries -- the reference's own dictionary-array
-// shortcut (SnappyHashAggregateExec.scala:1340-1369) taken to its conclusion.
+// K_CODE: a STRING column travels through the kernel as a 32-bit reference.  Dictionary-encoded batches: the per-batch
+// dictionary index ("code"); predicates on it are per-batch truth tables and group keys per-batch code->group maps,
+// both prepared on the host from the (tiny) dictionaries -- the reference's own dictionary-array shortcut
+// (SnappyHashAggregateExec.scala:1340-1369) taken to its conclusion.  Uncompressed variable-width batches
+// (ENC_STR_RAW): the byte position of the value's [len][bytes] record; predicates compare the bytes on the device and
+// hash-table keys are compared / hashed by their bytes.  Which of the two a batch uses is uniform per (batch, column).
 enum : int32_t { K_I8 = 0, K_I16 = 1, K_I32 = 2, K_I64 = 3, K_F32 = 4, K_F64 = 5, K_BOOL = 6, K_CODE = 7 };
 
 // ---- tiling ----------------------------------------------------------------------------------
@@ -160,6 +167,7 @@ struct ScanArgs {
   int64_t out_cap;                // MODE_PROJECT: capacity in records
   int32_t batch_base;             // MODE_PROJECT: ordinal of this launch's first batch within the execution
   int32_t chunk_rows;             // rows per work item (multiple of every tile size; default CHUNK_ROWS)
+  const uint8_t* lit_pool;        // bytes of the STRING literals of this execution (literal slot k: lits.i[k] = offset << 32 | length)
   int32_t fresh;                  // 1: first launch of an execution -- the last CTA OVERWRITES `result` (no host-side
                                   // identity upload, one dependent operation less in front of the kernel)
   int32_t pad2_;

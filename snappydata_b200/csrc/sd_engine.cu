@@ -290,6 +290,11 @@ struct sd_plan {
   std::vector<sd_literal> lits;
   std::vector<std::string> lit_strs;
   bool lits_set = false;
+  // bytes of the STRING literals on the device (raw-string predicates compare against them); slot k: packed offset | length
+  uint8_t* d_litpool = nullptr;
+  size_t litpool_cap = 0;
+  bool litpool_dirty = true;
+  std::vector<int64_t> lit_packed;
   // streams / events
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -457,6 +462,7 @@ struct BuiltScan {
   const void* d_batches = nullptr; const int32_t* d_prefix = nullptr; int nbatches = 0; int total_chunks = 0;
   int64_t rows = 0, algo_bytes = 0, updated_cols = 0, deleted_batches = 0;
   int needs_slow = 0;   // some batch needs the kernel variant with the per-row paths
+  int needs_hash = 0;   // a key column of a dense-table plan is a raw (variable-width) string in some batch
 };
 
 // Build the device descriptors + per-batch tables for a list of resident batches.
@@ -493,12 +499,12 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
       dc[c] = sc.dev;
       all_fast = all_fast && sc.fast;
       {
-        const bool simple = (sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||
+        const bool simple = (sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY || sc.dev.enc == ENC_STR_RAW)) ||
                             (sp.kinds[c] != K_CODE && sc.dev.enc == ENC_UNCOMPRESSED);
         simple_enc = simple_enc && simple && (!sc.has_nulls || sp.cols[c].nullable);   // NULLs in a column the plan calls non-nullable: per-row path
         any_delta = any_delta || sc.delta[0].present || sc.delta[1].present;
       }
-      base_fast = base_fast && !sc.has_nulls && ((sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY)) ||
+      base_fast = base_fast && !sc.has_nulls && ((sp.kinds[c] == K_CODE && (sc.dev.enc == ENC_DICTIONARY || sc.dev.enc == ENC_BIG_DICTIONARY || sc.dev.enc == ENC_STR_RAW)) ||
                                                  (sp.kinds[c] != K_CODE && sc.dev.enc == ENC_UNCOMPRESSED));
       out->algo_bytes += sc.algo_bytes;
       if (sc.delta[0].present || sc.delta[1].present) out->updated_cols++;
@@ -520,10 +526,17 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
         const StoredCol& sc = sb.cols[sb.positional ? ts.col : sp.cols[ts.col].table_ordinal];
         const int n = sc.dev.dict_n;                         // NULL code of a nullable column
         const bool nullable = sp.cols[ts.col].nullable != 0;
+        if (sc.raw_str) {   // no code space: predicates / keys of this batch work on the bytes (the table stays empty)
+          if (ts.kind == TABLE_KEYMAP) out->needs_hash = 1;   // a dense group table needs dictionary ids: this plan must use the hash table
+          while (aux.size() % 8) aux.push_back(0);
+          const int32_t off0 = (int32_t)(aux.size() - base);
+          memcpy(aux.data() + base + 4 * (size_t)ti, &off0, 4);
+          continue;
+        }
         // codes: [0,n) base dictionary; n = NULL (nullable columns) or an unused placeholder when update
         // deltas appended strings; (n, ...) strings that occur only in update deltas
         const int ncodes = std::max((int)sc.dict_strings.size(), nullable ? n + 1 : n);
-        while (aux.size() % 4) aux.push_back(0);
+        while (aux.size() % 8) aux.push_back(0);
         const int32_t off = (int32_t)(aux.size() - base);
         memcpy(aux.data() + base + 4 * (size_t)ti, &off, 4);
         uint64_t kpack = ~0ull;
@@ -534,6 +547,11 @@ int build_scan(sd_plan* p, const std::vector<const StoredBatch*>& list, Arena& a
             const bool isnull = code == n || code >= (int)sc.dict_strings.size();
             const std::string* s = isnull ? nullptr : &sc.dict_strings[code];
             aux.push_back((uint8_t)eval_string_predicate(sp, ts.node, s ? s->data() : nullptr, s ? (int)s->size() : 0, p->lits.data()));
+          }
+        } else if (ts.kind == TABLE_KEYPTR) {   // device address of every code's [len][bytes] record
+          for (int code = 0; code < ncodes; code++) {
+            const int64_t ptr = code < (int)sc.dict_rec_ptr.size() ? sc.dict_rec_ptr[code] : 0;
+            aux.insert(aux.end(), reinterpret_cast<const uint8_t*>(&ptr), reinterpret_cast<const uint8_t*>(&ptr) + 8);
           }
         } else {
           for (int code = 0; code < ncodes; code++) {
@@ -650,8 +668,62 @@ int plan_variant(sd_plan* p, int litnull, int slow, const KernelEntry** out) {
 }
 
 int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks, int needs_slow,
-                const std::vector<const StoredBatch*>* blist = nullptr, int replay_batch_base = -1) {
+                const std::vector<const StoredBatch*>* blist = nullptr, int replay_batch_base = -1);
+
+// A dense-table plan (dictionary-string keys) has to give up its table: too many key combinations, or a key column
+// arrives as raw variable-width strings (no dictionary ids).  The plan becomes its hash-table variant for good and
+// whatever this execution has launched so far is rebuilt (the per-batch tables differ) and launched again.
+int switch_to_hash(sd_plan* p) {
+  CodegenOptions opt;
+  opt.force_hash = 1;
+  PlanSpec hspec;
+  KernelEntry hk;
+  sd_plan_desc dv = p->spec.desc_view();
+  int rc = resolve_kernel(dv, opt, p->device, &hk, &hspec);
+  if (rc) return rc;
+  const std::vector<sd_plan::Launch> earlier(p->launch_log);
+  const std::vector<const StoredBatch*> exec(p->exec_batches);
+  p->launch_log.clear();
+  p->exec_batches.clear();
+  p->spec = hspec;
+  p->kernel = hk;
+  p->force_hash = true;
+  for (int v = 0; v < 4; v++) p->variant_state[v] = 0;
+  p->active = nullptr;
+  p->last_kernel = nullptr;
+  p->last_smem = (size_t)-1;
+  p->result_init = false;
+  p->hash_init = false;
+  p->cache.valid = false;
+  p->chunk_rows = CHUNK_ROWS;
+  SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
+  for (auto& l : earlier) {
+    std::vector<const StoredBatch*> list(exec.begin() + l.batch_base, exec.begin() + l.batch_base + l.nbatches);
+    BuiltScan bs;
+    rc = build_scan(p, list, p->scratch, p->stream, &bs);
+    if (rc) return rc;
+    rc = launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks, bs.needs_slow, &list);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int nbatches, int total_chunks, int needs_slow,
+                const std::vector<const StoredBatch*>* blist, int replay_batch_base) {
   const bool replay = replay_batch_base >= 0;
+  if (!replay && p->spec.mode == MODE_GROUPS) {   // dense table still possible with the dictionaries seen so far?
+    int64_t ng = 1;
+    for (size_t k = 0; k < p->spec.keys.size(); k++) ng *= std::max<int64_t>(1, (int64_t)p->key_vals[k].size());
+    if (ng > (1 << 16)) {
+      if (!blist) return set_error(SD_ERR_STATE, "dense group table overflow without a batch list");
+      int rc = switch_to_hash(p);
+      if (rc) return rc;
+      BuiltScan bs;
+      rc = build_scan(p, *blist, p->scratch, p->stream, &bs);
+      if (rc) return rc;
+      return launch_scan(p, bs.d_batches, bs.d_prefix, bs.nbatches, bs.total_chunks, bs.needs_slow, blist);
+    }
+  }
   int batch_base = replay ? replay_batch_base : (int)p->exec_batches.size();
   if (!replay && p->spec.mode != MODE_NOKEY) {
     p->launch_log.push_back({d_batches, d_prefix, nbatches, total_chunks, batch_base, needs_slow});
@@ -664,35 +736,9 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   // group radices from the current key dictionaries
   int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
   int ngroups = 1;
-  bool dense_too_big = false;
   for (int k = 0; k < nk && sp.mode == MODE_GROUPS; k++) {
     radix[k] = std::max<int>(1, (int)p->key_vals[k].size());
-    if ((int64_t)ngroups * radix[k] > (1 << 16)) { dense_too_big = true; break; }
     ngroups *= radix[k];
-  }
-  if (dense_too_big) {
-    // too many key combinations for the dense table: switch this plan to the hash-table variant (same tables, same
-    // slots) and replay what this execution has launched so far
-    CodegenOptions opt;
-    opt.force_hash = 1;
-    PlanSpec hspec;
-    KernelEntry hk;
-    sd_plan_desc dv = sp.desc_view();
-    int rc = resolve_kernel(dv, opt, p->device, &hk, &hspec);
-    if (rc) return rc;
-    std::vector<sd_plan::Launch> earlier(p->launch_log.begin(), p->launch_log.end() - (replay ? 0 : 1));
-    p->spec = hspec;
-    p->kernel = hk;
-    p->force_hash = true;
-    for (int v = 0; v < 4; v++) p->variant_state[v] = 0;
-    p->active = nullptr;
-    p->last_kernel = nullptr;
-    p->last_smem = (size_t)-1;
-    p->result_init = false;
-    p->hash_init = false;
-    SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
-    for (auto& l : earlier) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
-    return launch_scan(p, d_batches, d_prefix, nbatches, total_chunks, needs_slow, nullptr, batch_base);
   }
   const size_t ne = (size_t)ngroups * ns;
   // Where the dense group table lives (decided per launch from its size):
@@ -811,8 +857,30 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.chunk_rows = p->chunk_rows;
   args.fresh = fresh;
   memcpy(args.radix, radix, sizeof(radix));
+  if (p->litpool_dirty) {   // STRING literal bytes -> device (once per set of literal values)
+    std::vector<uint8_t> pool;
+    p->lit_packed.assign(p->lits.size(), 0);
+    for (size_t i = 0; i < p->lits.size(); i++) {
+      if (p->lits[i].type != SD_STRING) continue;
+      p->lit_packed[i] = (int64_t)(((uint64_t)pool.size() << 32) | (uint32_t)p->lits[i].slen);
+      pool.insert(pool.end(), p->lits[i].s, p->lits[i].s + p->lits[i].slen);
+    }
+    if (!pool.empty()) {
+      if (pool.size() > p->litpool_cap) {
+        if (p->d_litpool) cudaFree(p->d_litpool);
+        p->litpool_cap = pool.size() * 2 + 256;
+        SD_CUDA(cudaMalloc(&p->d_litpool, p->litpool_cap));
+      }
+      uint8_t* h = p->pinned.alloc(pool.size());
+      if (!h) return SD_ERR_CUDA;
+      memcpy(h, pool.data(), pool.size());
+      SD_CUDA(cudaMemcpyAsync(p->d_litpool, h, pool.size(), cudaMemcpyHostToDevice, p->stream));
+    }
+    p->litpool_dirty = false;
+  }
+  args.lit_pool = p->d_litpool;
   for (size_t i = 0; i < p->lits.size(); i++) {
-    args.lits.i[i] = p->lits[i].i;
+    args.lits.i[i] = p->lits[i].type == SD_STRING ? p->lit_packed[i] : p->lits[i].i;
     args.lits.d[i] = p->lits[i].d;
     if (p->lits[i].is_null) args.lits.nullmask |= 1ull << i;
   }
@@ -838,6 +906,13 @@ int flush_pending(sd_plan* p) {
   // the scan is ordered after the copies and the expansions with events
   int rc = build_scan(p, list, p->scratch, p->priv ? p->priv->copy_stream : p->stream, &bs);
   if (rc) return rc;
+  if (bs.needs_hash && p->spec.mode == MODE_GROUPS) {   // a key column came as raw strings: dense ids do not exist for it
+    rc = switch_to_hash(p);
+    if (rc) return rc;
+    bs = BuiltScan();
+    rc = build_scan(p, list, p->scratch, p->priv ? p->priv->copy_stream : p->stream, &bs);
+    if (rc) return rc;
+  }
   if (p->priv) {
     if (!p->priv->copies_done) SD_CUDA(cudaEventCreateWithFlags(&p->priv->copies_done, cudaEventDisableTiming));
     SD_CUDA(cudaEventRecord(p->priv->copies_done, p->priv->copy_stream));
@@ -974,6 +1049,13 @@ int finish_hash(sd_plan* p) {
   }
   SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
   SD_CUDA(cudaStreamSynchronize(p->stream));
+  // STRING keys are held by reference (address of the [len][bytes] record in a resident buffer): fetch their bytes
+  std::vector<std::vector<std::string>> key_strings((size_t)nk);
+  for (int k = 0; k < nk && count; k++) {
+    if (sp.exprs[sp.keys[k]].type != SD_STRING) continue;
+    rc = fetch_string_records(p->stream, d_keys + k, (int64_t)count, nk, key_strings[(size_t)k]);
+    if (rc) { cudaFree(d_keys); cudaFree(d_knull); cudaFree(d_vals); cudaFree(d_cursor); return rc; }
+  }
   cudaFree(d_keys); cudaFree(d_knull); cudaFree(d_vals); cudaFree(d_cursor);
   if (p->have_timing) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms; }
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
@@ -988,7 +1070,7 @@ int finish_hash(sd_plan* p) {
       HVal v;
       const int64_t code = hk[(size_t)g * nk + k];
       if ((hn[g] >> k) & 1u) v.isnull = true;
-      else if (types[k] == SD_STRING) v.s = p->key_vals[k][(size_t)code];
+      else if (types[k] == SD_STRING) v.s = key_strings[(size_t)k][g];
       else if (type_is_fp(types[k])) memcpy(&v.d, &code, 8);
       else { v.i = code; v.w = code; }
       vals.push_back(v);
@@ -1034,6 +1116,29 @@ int finish_project(sd_plan* p) {
     types.push_back(field_type(e.type, e.type == SD_DECIMAL ? decimal_ps(sp, sp.proj[j]) : 0));
     if (e.type == SD_STRING) str_col[j] = e.a;
   }
+  // strings of raw (variable-width) batches are projected by reference: record = position in the batch's body
+  std::vector<int64_t> raw_ptrs;
+  for (unsigned long long i = 0; i < count && !str_col.empty(); i++) {
+    const uint64_t* r = &recs[(size_t)i * (size_t)(rec / 8)];
+    const uint32_t bidx = (uint32_t)(r[0] & 0xffffffffu), pnull = (uint32_t)(r[0] >> 32);
+    if (bidx >= p->exec_batches.size()) return set_error(SD_ERR_CUDA, "corrupt projection record (batch %u)", bidx);
+    const StoredBatch& sb = *p->exec_batches[bidx];
+    for (int j = 0; j < np; j++) {
+      if (str_col[j] < 0 || ((pnull >> j) & 1u)) continue;
+      const StoredCol& sc = sb.cols[sb.positional ? str_col[j] : sp.cols[str_col[j]].table_ordinal];
+      if (sc.raw_str) raw_ptrs.push_back((int64_t)(uintptr_t)(sc.dev.dict + (uint32_t)r[1 + j]));
+    }
+  }
+  std::vector<std::string> raw_strings;
+  if (!raw_ptrs.empty()) {
+    int64_t* d_ptrs = nullptr;
+    SD_CUDA(cudaMalloc(&d_ptrs, raw_ptrs.size() * 8));
+    cudaError_t ce = cudaMemcpyAsync(d_ptrs, raw_ptrs.data(), raw_ptrs.size() * 8, cudaMemcpyHostToDevice, p->stream);
+    rc = ce == cudaSuccess ? fetch_string_records(p->stream, d_ptrs, (int64_t)raw_ptrs.size(), 1, raw_strings) : set_error(SD_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(ce));
+    cudaFree(d_ptrs);
+    if (rc) return rc;
+  }
+  size_t next_raw = 0;
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
   out.reserve((size_t)count * (size_t)(16 + 8 * np));
@@ -1051,6 +1156,7 @@ int finish_project(sd_plan* p) {
       if (types[j] == SD_STRING) {
         const int c = str_col[j];
         const StoredCol& sc = sb.cols[sb.positional ? c : sp.cols[c].table_ordinal];
+        if (sc.raw_str) { v.s = raw_strings[next_raw++]; continue; }
         const int64_t code = (int64_t)raw;
         if (code < 0 || code >= (int64_t)sc.dict_strings.size() || code == sc.dev.dict_n) { if (code == sc.dev.dict_n) v.isnull = true; else return set_error(SD_ERR_CUDA, "dictionary code %lld out of range", (long long)code); }
         else v.s = sc.dict_strings[(size_t)code];
@@ -1148,6 +1254,7 @@ int sd_plan_set_literals(sd_plan* p, const sd_literal* vals, int32_t n) {
     p->lits[i].slen = (int32_t)p->lit_strs[i].size();
   }
   p->lits_set = true;
+  p->litpool_dirty = true;
   return 0;
 }
 
@@ -1241,6 +1348,14 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
     BuiltScan bs;
     rc = build_scan(p, list, p->cache_arena, p->stream, &bs);
     if (rc) return rc;
+    if (bs.needs_hash && p->spec.mode == MODE_GROUPS) {
+      rc = switch_to_hash(p);
+      if (rc) return rc;
+      p->cache_arena.reset();
+      bs = BuiltScan();
+      rc = build_scan(p, list, p->cache_arena, p->stream, &bs);
+      if (rc) return rc;
+    }
     c.store = s; c.version = s->version; c.buckets = buckets; c.lit_key = lk;
     c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
     c.rows = bs.rows; c.algo_bytes = bs.algo_bytes; c.seen = seen; c.skipped = skipped;
@@ -1382,6 +1497,7 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->d_out_count) cudaFree(p->d_out_count);
   if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);
+  if (p->d_litpool) cudaFree(p->d_litpool);
   if (p->priv) sd_store_destroy(p->priv);
   delete p;
 }

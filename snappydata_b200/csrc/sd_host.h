@@ -52,10 +52,16 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out);
 int hash_table_init(cudaStream_t stream, const HashTable& t, uint32_t capacity, int nslot, const uint64_t* d_ident);
 int hash_table_compact(cudaStream_t stream, const HashTable& t, uint32_t capacity, int nk, int nslot, int64_t* out_keys,
                        uint32_t* out_knull, uint64_t* out_vals, uint32_t* d_cursor);
+// strings held by reference -> host: d_recs[i * stride] = device address of a [len:int32][bytes] record (0: none)
+int fetch_string_records(cudaStream_t stream, const int64_t* d_recs, int64_t n, int64_t stride, std::vector<std::string>& out);
 
 // ---- on-device LZ4 (sd_lz4.cu) ---------------------------------------------------------------------------
 struct Lz4Job { const uint8_t* src; uint8_t* dst; int64_t src_len; int64_t dst_len; };
 int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t want);
+// host Snappy (raw format) decoder: returns the uncompressed length or -1 (sd_lz4.cu)
+int64_t snappy_decode(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_cap);
+// a stored buffer [-codecId][uncompressedLen][payload] (CompressionUtils.scala:53-61) -> its uncompressed bytes, on the host
+int decompress_envelope_host(const uint8_t* buf, int64_t len, std::vector<uint8_t>& out);
 int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error);
 
 // ---- NCCL behind sd_comm (sd_nccl.cpp; dlopen'ed) --------------------------------------------------------
@@ -107,6 +113,9 @@ struct StoredCol {
   int64_t body_off = 0;                   // offset of the first value / index
   DevCol dev;                             // device view (delta pointers filled per plan)
   std::vector<std::string> dict_strings;  // STRING dictionary (or distinct RLE run strings)
+  std::vector<int64_t> dict_rec_off;      // per dict_strings entry: offset of its [len][bytes] record in the buffer (-1: none)
+  std::vector<int64_t> dict_rec_ptr;      // per unified code: device address of the record (0: NULL placeholder) -- string keys by reference
+  bool raw_str = false;                   // Uncompressed variable-width STRING body (dev.enc == ENC_STR_RAW)
   bool has_nulls = false;
   StoredDelta delta[2];
   DevDelta* dev_delta[2] = {nullptr, nullptr};   // DevDelta structs resident on the device

@@ -106,17 +106,55 @@ __device__ __forceinline__ void slot_atomic(int op, uint64_t* p, uint64_t v) {
   }
 }
 
+// ---- variable-width strings by their bytes: records are [len:int32 LE][bytes], unaligned (enc/Uncompressed.scala:116-161;
+//      the same layout as a string dictionary entry, enc/DictionaryEncoding.scala:452-518).  Strings compare as unsigned
+//      bytes, shorter first on a common prefix (UTF8String.compareTo) -----------------------------
+__device__ __forceinline__ int rec_len(const uint8_t* rec) {
+  return (int)((uint32_t)rec[0] | ((uint32_t)rec[1] << 8) | ((uint32_t)rec[2] << 16) | ((uint32_t)rec[3] << 24));
+}
+__device__ __noinline__ int str_cmp_rec(const uint8_t* rec, const uint8_t* lit, int llen) {
+  const int n = rec_len(rec);
+  const uint8_t* s = rec + 4;
+  const int m = n < llen ? n : llen;
+  for (int i = 0; i < m; i++) { const int d = (int)s[i] - (int)lit[i]; if (d) return d; }
+  return n - llen;
+}
+__device__ __noinline__ bool str_starts_rec(const uint8_t* rec, const uint8_t* lit, int llen) {
+  if (rec_len(rec) < llen) return false;
+  const uint8_t* s = rec + 4;
+  for (int i = 0; i < llen; i++) if (s[i] != lit[i]) return false;
+  return true;
+}
+__device__ __noinline__ bool str_eq_recs(const uint8_t* a, const uint8_t* b) {
+  if (a == b) return true;
+  const int n = rec_len(a);
+  if (n != rec_len(b)) return false;
+  for (int i = 0; i < n; i++) if (a[4 + i] != b[4 + i]) return false;
+  return true;
+}
+__device__ __noinline__ uint64_t str_hash_rec(const uint8_t* rec) {   // FNV-1a over the bytes
+  const int n = rec_len(rec);
+  uint64_t h = 1469598103934665603ull;
+  for (int i = 0; i < n; i++) { h ^= rec[4 + i]; h *= 1099511628211ull; }
+  return h ^ (uint64_t)n;
+}
+
 // ---- MODE_HASH: find-or-insert of a key tuple, then atomic slot updates ---------------------------------
 __device__ __forceinline__ uint64_t hash_mix64(uint64_t h, uint64_t v) {
   h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
   h *= 0xff51afd7ed558ccdull;
   return h ^ (h >> 33);
 }
-template <int NK>
+// STRMASK bit k: key k is a STRING held by reference (kc[k] = device address of its [len][bytes] record, 0 when NULL):
+// hashed and compared by its bytes
+template <int NK, uint32_t STRMASK>
 __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const int64_t* kc, uint32_t knull) {
   uint64_t h = 0x2545f4914f6cdd1dull ^ knull;
 #pragma unroll
-  for (int k = 0; k < NK; k++) h = hash_mix64(h, (uint64_t)kc[k]);
+  for (int k = 0; k < NK; k++) {
+    if ((STRMASK >> k) & 1u) h = hash_mix64(h, kc[k] ? str_hash_rec(reinterpret_cast<const uint8_t*>(kc[k])) : 0ull);
+    else h = hash_mix64(h, (uint64_t)kc[k]);
+  }
   uint32_t pos = (uint32_t)h & t.mask;
   for (uint32_t probe = 0; probe < t.max_probe; probe++, pos = (pos + 1) & t.mask) {
     uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);
@@ -136,7 +174,11 @@ __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const
     __threadfence();
     bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
 #pragma unroll
-    for (int k = 0; k < NK; k++) same = same && *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]) == kc[k];
+    for (int k = 0; k < NK; k++) {
+      const int64_t have = *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]);
+      if ((STRMASK >> k) & 1u) same = same && (have == kc[k] || (have && kc[k] && str_eq_recs(reinterpret_cast<const uint8_t*>(have), reinterpret_cast<const uint8_t*>(kc[k]))));
+      else same = same && have == kc[k];
+    }
     if (same) return pos;
   }
   atomicExch(t.overflow, 1u);
@@ -175,8 +217,8 @@ __device__ __forceinline__ typename KindT<KIND>::T decode_value(const uint8_t* d
     if (KIND == K_BOOL) return (T)(data[k] == 1);
     return ld_at<T>(data, k);
   }
-  if (enc == ENC_DICTIONARY || enc == ENC_BIG_DICTIONARY) {
-    int idx = enc == ENC_DICTIONARY ? (int)ld_at<int16_t>(data, k) : ld_at<int32_t>(data, k);
+  if (enc == ENC_DICTIONARY || enc == ENC_BIG_DICTIONARY || enc == ENC_STR_RAW) {
+    int idx = enc == ENC_DICTIONARY ? (int)ld_at<int16_t>(data, k) : ld_at<int32_t>(data, k);   // ENC_STR_RAW: record position
     if (KIND == K_CODE) return (T)idx;
     return ld_at<T>(dict, idx);
   }
@@ -714,7 +756,16 @@ struct RowCtx {
   //   kpack[t] : key maps of <= 8 codes packed one byte per code (no memory access per row), else ~0
   const uint8_t* tbl[MAX_TABLES];
   uint64_t kpack[MAX_TABLES];
+  const uint8_t* litpool;           // STRING literal bytes of this execution
+  const uint8_t* strbase[64];       // per STRING scan column: body of an ENC_STR_RAW batch (refs are positions into it), else nullptr
   __device__ __forceinline__ const uint8_t* table(int t) const { return tbl[t]; }
+  __device__ __forceinline__ const uint8_t* lit_bytes(int slot) const { return litpool + (uint32_t)((uint64_t)L->i[slot] >> 32); }
+  __device__ __forceinline__ int lit_len(int slot) const { return (int)((uint64_t)L->i[slot] & 0xffffffffull); }
+  // record of a STRING value held by reference: raw batch -> body + position; dictionary batch -> entry address from the
+  // per-batch key-pointer table t (int64 per code)
+  __device__ __forceinline__ int64_t str_ref(int c, int t, int code) const {
+    return strbase[c] ? (int64_t)(uintptr_t)(strbase[c] + (uint32_t)code) : reinterpret_cast<const int64_t*>(tbl[t])[code];
+  }
   __device__ __forceinline__ int key_id(int t, int code) const {
     const uint64_t kp = kpack[t];
     return kp != ~0ull ? (int)((kp >> (code * 8)) & 0xffull) : reinterpret_cast<const int32_t*>(tbl[t])[code];
@@ -728,6 +779,13 @@ __device__ __forceinline__ void load_tables(RowCtx& ctx, const uint8_t* aux) {
 #pragma unroll
     for (int t = 0; t < NT; t++) { ctx.tbl[t] = aux + __ldg(&off[t]); ctx.kpack[t] = __ldg(&kp[t]); }
   }
+}
+
+// per chunk: which STRING columns of this batch are raw (ENC_STR_RAW)
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void load_strbase(RowCtx& ctx, const DevBatch<PLAN::NC>& b, Seq<Cs...>) {
+  int dummy[] = {0, (PLAN::kind(Cs) == K_CODE ? (ctx.strbase[Cs] = (b.cols[Cs].enc == ENC_STR_RAW ? b.cols[Cs].dict : nullptr), 0) : 0)...};
+  (void)dummy;
 }
 
 // bit c set: K_CODE column c of this batch uses int16 dictionary indexes (else int32)
@@ -828,6 +886,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   RowCtx ctx;
   ctx.L = &args.lits;
   ctx.radix = args.radix;
+  ctx.litpool = args.lit_pool;
 
   // ---- persistent loop over (batch, chunk) work items, static round-robin -------------------------
   for (int item = blockIdx.x; item < args.total_chunks; item += gridDim.x) {
@@ -843,6 +902,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
     // else reaching it is a host-side bug: stop loudly instead of aggregating garbage
     if (!PLAN::SLOW_PATHS && !fast) __trap();
     load_tables<PLAN::NTABLES>(ctx, b.aux);
+    if (PLAN::ANY_STRING) load_strbase<PLAN>(ctx, b, ColSeq());
     const SD_CMASK(PLAN) c16 = code16_mask<PLAN>(b, ColSeq());
     uint32_t c_scanned = 0, c_passed = 0;
     const int tile0 = chunk * CHUNK_TILES;
@@ -954,7 +1014,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
             int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
             uint32_t knull = 0;
             PLAN::keys(row, ctx, kc, knull);
-            const int64_t e = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1)>(args.hash, kc, knull);
+            const int64_t e = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), PLAN::STRKEYMASK>(args.hash, kc, knull);
             if (e >= 0) {
               uint64_t* t = args.hash.vals + (size_t)e * NSLOT;
 #pragma unroll

@@ -41,6 +41,66 @@ int64_t lz4_decode_prefix(const uint8_t* src, int64_t src_len, uint8_t* dst, int
   return o;
 }
 
+// ---- host: Snappy raw format (the reference's other codec, CompressionCodecId.SNAPPY_ID = 2, CompressionUtils.scala:125-168).
+// preamble = uncompressed length as a varint; elements: tag & 3 = 0 literal (len-1 in the upper 6 bits, 60..63 = that
+// many + 1 - 60 extra length bytes), 1 copy (len 4..11, 11-bit offset), 2 copy (len 1..64, 16-bit offset), 3 copy (32-bit offset).
+int64_t snappy_decode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+  int64_t s = 0, ulen = 0;
+  int shift = 0;
+  for (;;) {
+    if (s >= n || shift > 35) return -1;
+    const uint8_t b = src[s++];
+    ulen |= (int64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+    shift += 7;
+  }
+  if (ulen > cap) return -1;
+  int64_t o = 0;
+  while (s < n) {
+    const uint8_t tag = src[s++];
+    int64_t len, off;
+    switch (tag & 3) {
+      case 0: {
+        len = (tag >> 2) + 1;
+        if (len > 60) {
+          const int extra = (int)len - 60;
+          if (s + extra > n) return -1;
+          len = 0;
+          for (int i = 0; i < extra; i++) len |= (int64_t)src[s + i] << (8 * i);
+          len += 1;
+          s += extra;
+        }
+        if (s + len > n || o + len > ulen) return -1;
+        memcpy(dst + o, src + s, (size_t)len);
+        s += len; o += len;
+        continue;
+      }
+      case 1: if (s + 1 > n) return -1; len = 4 + ((tag >> 2) & 7); off = ((int64_t)(tag >> 5) << 8) | src[s]; s += 1; break;
+      case 2: if (s + 2 > n) return -1; len = (tag >> 2) + 1; off = src[s] | ((int64_t)src[s + 1] << 8); s += 2; break;
+      default: if (s + 4 > n) return -1; len = (tag >> 2) + 1; off = src[s] | ((int64_t)src[s + 1] << 8) | ((int64_t)src[s + 2] << 16) | ((int64_t)src[s + 3] << 24); s += 4; break;
+    }
+    if (off == 0 || off > o || o + len > ulen) return -1;
+    for (int64_t i = 0; i < len; i++, o++) dst[o] = dst[o - off];
+  }
+  return o == ulen ? o : -1;
+}
+
+int decompress_envelope_host(const uint8_t* buf, int64_t len, std::vector<uint8_t>& out) {
+  if (len < 8) return set_error(SD_ERR_INVALID, "compressed buffer shorter than its envelope");
+  int32_t codec, ulen;
+  memcpy(&codec, buf, 4); memcpy(&ulen, buf + 4, 4);
+  codec = -codec;
+  if (ulen < 0) return set_error(SD_ERR_INVALID, "compressed buffer: bad uncompressed length %d", ulen);
+  out.assign((size_t)ulen + 16, 0);
+  int64_t got = -1;
+  if (codec == 1) got = lz4_decode_prefix(buf + 8, len - 8, out.data(), ulen);
+  else if (codec == 2) got = snappy_decode(buf + 8, len - 8, out.data(), ulen);
+  else return set_error(SD_ERR_UNSUPPORTED, "compressed buffer with unknown codec id %d (LZ4 = 1, Snappy = 2)", codec);
+  if (got != ulen) return set_error(SD_ERR_INVALID, "corrupt %s payload (%lld of %d bytes)", codec == 1 ? "LZ4" : "Snappy", (long long)got, ulen);
+  out.resize((size_t)ulen);
+  return 0;
+}
+
 // ---- device: one warp per buffer, 32 sequences at a time -------------------------------------------------
 // A column buffer is ONE LZ4 block (the reference compresses the whole value, CompressionUtils.scala:102-110), so
 // the unit of independent work is the buffer and the time of a launch is the serial chain of its longest buffer.
@@ -488,6 +548,17 @@ extern "C" int sdx_lz4_expand(int32_t device, const void* const* blocks, const i
 #undef LZX
   cleanup();
   if (err) return set_error(SD_ERR_INVALID, "sdx_lz4_expand: the device decoder rejected a block");
+  return 0;
+}
+
+// test hook: host decompression of a stored envelope (LZ4 or Snappy), as used for deltas, delete masks, Snappy columns
+extern "C" int sdx_decompress_envelope(const void* buf, int64_t len, void* out, int64_t cap, int64_t* out_len) {
+  std::vector<uint8_t> v;
+  int rc = sd::decompress_envelope_host(reinterpret_cast<const uint8_t*>(buf), len, v);
+  if (rc) return rc;
+  if (out_len) *out_len = (int64_t)v.size();
+  if ((int64_t)v.size() > cap) return sd::set_error(SD_ERR_OVERFLOW, "output needs %zu bytes", v.size());
+  if (!v.empty()) memcpy(out, v.data(), v.size());
   return 0;
 }
 

@@ -144,7 +144,8 @@ static int upload_bytes(sd_store* s, const uint8_t* src, size_t n, size_t align,
 }
 
 // Parse [numElements][dictionary] at p; returns bytes consumed or -1.
-static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, int* n_out, std::vector<std::string>* strings) {
+static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, int* n_out, std::vector<std::string>* strings,
+                                std::vector<int64_t>* rec_off = nullptr, const uint8_t* buf0 = nullptr) {
   if (p + 4 > end) return -1;
   const int n = rd_i32(p);
   if (n < 0) return -1;
@@ -157,6 +158,7 @@ static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, 
       const int l = rd_i32(q);
       if (l < 0 || q + 4 + l > end) return -1;
       strings->emplace_back(reinterpret_cast<const char*>(q + 4), (size_t)l);
+      if (rec_off) rec_off->push_back(q - buf0);
       q += 4 + l;
     }
   } else if (type == SD_INT || type == SD_DATE) {
@@ -176,9 +178,17 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
   const uint8_t* payload = nullptr;
   int64_t payload_len = 0;
   std::vector<uint8_t> prefix;
+  std::vector<uint8_t> host_full;   // whole buffer decompressed on the host (Snappy; LZ4 of encodings that need a host walk)
+  if (rd_i32(buf) < 0 && -rd_i32(buf) != 1) {
+    // Snappy (the reference's non-default codec): decompressed on the host like the reference's iterator does
+    // (ColumnBatchIterator.scala:102-113), then handled as an uncompressed buffer
+    int rc0 = decompress_envelope_host(buf, len, host_full);
+    if (rc0) return rc0;
+    buf = host_full.data();
+    len = (int64_t)host_full.size();
+    if (len < 8) return set_error(SD_ERR_INVALID, "column buffer shorter than its 8-byte header");
+  }
   if (rd_i32(buf) < 0) {
-    const int codec = -rd_i32(buf);
-    if (codec != 1) return set_error(SD_ERR_UNSUPPORTED, "compressed column buffer with codec %d (only LZ4 = 1 is decoded on the device)", codec);
     const int64_t ulen = rd_i32(buf + 4);
     if (ulen < 8) return set_error(SD_ERR_INVALID, "compressed column buffer: bad uncompressed length %lld", (long long)ulen);
     payload = buf + 8;
@@ -192,8 +202,9 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
       const int tid = rd_i32(prefix.data());
       const int nb = want >= 8 ? rd_i32(prefix.data() + 4) : 0;
       if (tid < 0 || tid > ENC_BOOLEAN_BITSET || nb < 0 || (nb & 7) || 8 + (int64_t)nb > ulen) return set_error(SD_ERR_INVALID, "corrupt header in LZ4 column buffer");
-      if (tid == ENC_RUN_LENGTH) return set_error(SD_ERR_UNSUPPORTED, "LZ4-compressed RunLength column (needs a host pass over every run)");
       int64_t need = 8 + nb;
+      // encodings whose layout needs a host walk over every value (run lengths, variable-width strings): decode it all here
+      if (tid == ENC_RUN_LENGTH || (tid == ENC_UNCOMPRESSED && type == SD_STRING)) need = ulen;
       if (tid == ENC_DICTIONARY || tid == ENC_BIG_DICTIONARY) {
         need += 4;
         if (want >= need) {
@@ -220,6 +231,7 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
     }
     buf = prefix.data();
     len = ulen;
+    if (want >= ulen) payload = nullptr;   // fully decoded on the host: uploaded as plain bytes, nothing left for the device decoder
   }
   const int type_id = rd_i32(buf);
   if (type_id > ENC_BOOLEAN_BITSET) return set_error(SD_ERR_INVALID, "unknown encoding typeId %d", type_id);
@@ -259,15 +271,31 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
   int64_t body = 8 + null_bytes;
   int64_t dict_bytes = 0;
   const int w = fixed_width_of(type);
-  std::vector<int32_t> run_ends, run_codes;
+  std::vector<int32_t> run_ends, run_codes, str_pos;
   switch (type_id) {
     case ENC_UNCOMPRESSED:
-      if (type == SD_STRING) { c.unsupported = "Uncompressed variable-width STRING column (needs an offsets pass; not in the GPU path yet)"; break; }
+      if (type == SD_STRING) {
+        // variable width: back-to-back [len:int32][bytes]; the reference reads it with a sequential cursor
+        // (enc/Uncompressed.scala:116-161).  One host walk per buffer gives every stored value's record position, which
+        // the kernel then loads like a 4-byte column; the bytes themselves stay where they are.
+        const uint8_t* q = buf + body;
+        str_pos.reserve((size_t)nn);
+        for (int64_t k = 0; k < nn; k++) {
+          if (q + 4 > end) return set_error(SD_ERR_INVALID, "uncompressed STRING column truncated at value %lld", (long long)k);
+          const int32_t l = rd_i32(q);
+          if (l < 0 || q + 4 + l > end) return set_error(SD_ERR_INVALID, "uncompressed STRING column: bad length %d at value %lld", l, (long long)k);
+          if (q - (buf + body) > INT32_MAX) return set_error(SD_ERR_UNSUPPORTED, "uncompressed STRING body beyond 2 GB");
+          str_pos.push_back((int32_t)(q - (buf + body)));
+          q += 4 + l;
+        }
+        c.raw_str = true;
+        break;
+      }
       if (body + nn * w > len) return set_error(SD_ERR_INVALID, "uncompressed column truncated: need %lld bytes, have %lld", (long long)(body + nn * w), (long long)len);
       break;
     case ENC_DICTIONARY: case ENC_BIG_DICTIONARY: {
       int n = 0;
-      int64_t used = parse_dictionary(buf + body, end, type, &n, &c.dict_strings);
+      int64_t used = parse_dictionary(buf + body, end, type, &n, &c.dict_strings, &c.dict_rec_off, buf);
       if (used == -2) return set_error(SD_ERR_INVALID, "DictionaryDecoder not supported for sd_type %d", type);
       if (used < 0) return set_error(SD_ERR_INVALID, "truncated dictionary");
       dict_bytes = used;
@@ -297,7 +325,7 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
           std::string sv(reinterpret_cast<const char*>(q + 4), (size_t)l);
           auto it = seen.find(sv);
           int code;
-          if (it == seen.end()) { code = (int)c.dict_strings.size(); seen.emplace(sv, code); c.dict_strings.push_back(sv); } else code = it->second;
+          if (it == seen.end()) { code = (int)c.dict_strings.size(); seen.emplace(sv, code); c.dict_strings.push_back(sv); c.dict_rec_off.push_back(q - buf); } else code = it->second;
           run_codes.push_back(code);
           covered += rd_i32(q + 4 + l);
           q += 8 + l;
@@ -332,6 +360,16 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
     if (rc) return rc;
   }
   c.dev.data = c.dev_base + body;
+  if (c.raw_str) {   // the kernel's view: positions as the column's data, the body as its "dictionary"
+    const int32_t* dp = nullptr;
+    str_pos.resize(str_pos.size() + 40, 0);   // tail padding: vector loads may overrun a partial pair
+    rc = upload_vec(s, str_pos, 128, &dp);     // (pageable source: staged before the call returns)
+    if (rc) return rc;
+    c.dev.dict = c.dev_base + body;
+    c.dev.data = reinterpret_cast<const uint8_t*>(dp);
+    c.dev.enc = ENC_STR_RAW;
+    c.dev.dict_n = 0;
+  }
   if ((type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY) && type != SD_STRING) {
     const int ew = (type == SD_INT || type == SD_DATE) ? 4 : 8;
     c.dev.dict = c.dev_base + body - (int64_t)ew * c.dev.dict_n;   // ew-aligned because `body` is 128-aligned
@@ -355,8 +393,13 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
     }
   }
   const int kind = kind_of_type(type);
-  c.fast = !c.has_nulls && ((kind == K_CODE && (type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY)) ||
+  c.fast = !c.has_nulls && ((kind == K_CODE && (type_id == ENC_DICTIONARY || type_id == ENC_BIG_DICTIONARY || c.raw_str)) ||
                             (kind != K_CODE && type_id == ENC_UNCOMPRESSED));
+  // string values by reference (hash-table keys): device address of every dictionary entry's record
+  if (type == SD_STRING && !c.raw_str) {
+    c.dict_rec_ptr.assign(c.dict_strings.size(), 0);
+    for (size_t k = 0; k < c.dict_strings.size() && k < c.dict_rec_off.size(); k++) c.dict_rec_ptr[k] = (int64_t)(uintptr_t)(c.dev_base + c.dict_rec_off[k]);
+  }
   return 0;
 }
 
@@ -364,9 +407,16 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
 // (enc/ColumnDeltaEncoder.scala:300-331; decoder init enc/ColumnDeltaDecoder.scala:47-61)
 static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, StoredCol& col, int depth) {
   StoredDelta& d = col.delta[depth];
+  std::vector<uint8_t> plain;
+  if (len >= 8 && rd_i32(buf) < 0) {   // stored compressed (a depth-1 delta of ~1.3k doubles passes the 2048-byte threshold): small, host-side
+    int rc0 = decompress_envelope_host(buf, len, plain);
+    if (rc0) return rc0;
+    buf = plain.data();
+    len = (int64_t)plain.size();
+  }
   if (len < 16) return set_error(SD_ERR_INVALID, "delta buffer too short");
   const int type_id = rd_i32(buf);
-  if (type_id < 0) return set_error(SD_ERR_UNSUPPORTED, "compressed delta buffer");
+  if (type_id < 0) return set_error(SD_ERR_INVALID, "doubly compressed delta buffer");
   const int null_bytes = rd_i32(buf + 4);
   if (null_bytes < 0 || (null_bytes & 7) || 16 + (int64_t)null_bytes > len) return set_error(SD_ERR_INVALID, "bad delta null bitset size");
   const uint8_t* cpos = buf + 8 + null_bytes;
@@ -537,10 +587,18 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
     c.dev.delta1 = c.dev_delta[1];
   }
   if (b->delete_buf) {   // [0][numBaseRows][numDeletes][positions]; the decoder walks to the buffer end
-    if (b->delete_len < 12) return set_error(SD_ERR_INVALID, "delete buffer too short");
-    const int n = (int)((b->delete_len - 12) / 4);
+    const uint8_t* db = reinterpret_cast<const uint8_t*>(b->delete_buf);
+    int64_t dlen = b->delete_len;
+    std::vector<uint8_t> plain;
+    if (dlen >= 8 && rd_i32(db) < 0) {   // stored compressed
+      int rc0 = decompress_envelope_host(db, dlen, plain);
+      if (rc0) return rc0;
+      db = plain.data(); dlen = (int64_t)plain.size();
+    }
+    if (dlen < 12) return set_error(SD_ERR_INVALID, "delete buffer too short");
+    const int n = (int)((dlen - 12) / 4);
     uint8_t* p = nullptr;
-    int rc = upload_bytes(s, reinterpret_cast<const uint8_t*>(b->delete_buf) + 12, 4 * (size_t)n, 16, 0, &p);
+    int rc = upload_bytes(s, db + 12, 4 * (size_t)n, 16, 0, &p);
     if (rc) return rc;
     sb->dev_deletes = reinterpret_cast<int32_t*>(p);
     sb->num_deletes = n;

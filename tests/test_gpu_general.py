@@ -220,17 +220,20 @@ def test_row_buffer_rows_join_the_same_aggregate(gpu_api, batches):
 def test_errors_not_fallbacks(gpu_api):
     """A buffer the GPU path cannot scan is an error, never a CPU fallback."""
     from snappydata_b200.column_format import encode_uncompressed, compress_lz4
+    # (Uncompressed variable-width STRING columns used to be refused here: they are scanned now, tests/test_gpu_strings.py)
+    # a corrupt variable-width body is an error
     b = PlanBuilder()
     s = b.col(T.STRING, 0, False)
     b.filter(s.eq(b.lit(T.STRING)))
     b.count()
-    desc = b.build()
-    gp = capi.Plan(gpu_api, desc).set_literals([b"x"])
-    bad = ColumnBatch(num_rows=3, columns=[encode_uncompressed([b"a", b"b", b"c"], T.STRING)])
+    gp = capi.Plan(gpu_api, b.build()).set_literals([b"x"])
+    good = encode_uncompressed([b"a", b"b", b"c"], T.STRING)
+    bad = ColumnBatch(num_rows=3, columns=[good[:-1] + b"\x7f"[:0]])   # last value truncated by one byte
+    bad.columns[0] = good[:-1]
     with pytest.raises(capi.SdError) as e:
         gp.submit(bad)
         gp.finish()
-    assert e.value.code == capi.SD_ERR_UNSUPPORTED
+    assert e.value.code == capi.SD_ERR_INVALID
     # NOT NULL column carrying a null bitset is rejected like NotNullDecoder does
     b = PlanBuilder()
     x = b.col(T.INT, 0, False)
@@ -240,10 +243,14 @@ def test_errors_not_fallbacks(gpu_api):
     with pytest.raises(capi.SdError) as e:
         gp.submit(bad)
     assert e.value.code == capi.SD_ERR_INVALID
-    # a Snappy-compressed envelope (codec 2) is refused; LZ4 (codec 1) is decoded on the device (test_lz4_*)
+    # a corrupt Snappy envelope (codec 2) is an error (valid ones are decoded: tests/test_gpu_strings.py); unknown codecs are refused
     snappy_env = (-2).to_bytes(4, "little", signed=True) + (20000).to_bytes(4, "little") + b"\0" * 100
     with pytest.raises(capi.SdError) as e:
         gp.submit(ColumnBatch(num_rows=5000, columns=[snappy_env]))
+    assert e.value.code == capi.SD_ERR_INVALID
+    codec3 = (-3).to_bytes(4, "little", signed=True) + (20000).to_bytes(4, "little") + b"\0" * 100
+    with pytest.raises(capi.SdError) as e:
+        gp.submit(ColumnBatch(num_rows=5000, columns=[codec3]))
     assert e.value.code == capi.SD_ERR_UNSUPPORTED
 
 

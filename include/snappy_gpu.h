@@ -169,6 +169,11 @@ int sd_device_count(int* out);
 const char* sd_last_error(void);               /* thread-local, valid until the next failing call   */
 const char* sd_version(void);
 
+/* page-locked host memory for a binding's staging area (the JNI shim copies heap byte[]s into it, so that no Java array
+ * is pinned while CUDA work is queued and host->device copies out of it are real asynchronous DMA) */
+int sd_host_alloc(int64_t bytes, void** out);
+void sd_host_free(void* p);
+
 /* ---- plan (one per Spark task / partition; ColumnTableScan.doProduce + SnappyHashAggregateExec
  *      doProduce/doConsume fused, core/.../ColumnTableScan.scala:186-672,
  *      core/.../aggregate/SnappyHashAggregateExec.scala:240-263) --------------------------------- */

@@ -1,7 +1,9 @@
 /*
  * JVM binding of libsnappygpu.so (see include/snappy_gpu.h and jvm/native/snappy_gpu_jni.c).
- * NOT COMPILED in this repository's container (no JDK/Scala toolchain); written against
- * SnappyData 1.3.0 / snappy-spark 2.1.1.9 class names as they appear in /root/reference.
+ * NOT COMPILED in this repository's container (no JDK/Scala toolchain); written against SnappyData 1.3.0 /
+ * snappy-spark 2.1.1.9 class names as they appear in /root/reference.  The natives follow the only native precedent of
+ * the reference, org.apache.spark.unsafe.Native (aqp/src/main/cpp/io/snappydata/DataOptimizations.c:26-68): raw
+ * addresses and sizes, primitive returns; a non-zero sd_status becomes RuntimeException(sd_last_error()).
  */
 package io.snappydata.gpu
 
@@ -15,12 +17,17 @@ object SnappyGpuNative {
   @native def init(device: Int): Int
   @native def planCreate(planDescAddr: Long): Long
   @native def planSetLiterals(plan: Long, literalsAddr: Long, n: Int): Unit
+  /** per column either a native address (direct ByteBuffer) or a heap byte[] + offset (copied by the shim into its
+    * page-locked staging area: no array is pinned while CUDA work is queued) */
   @native def batchSubmit(plan: Long, numRows: Int, nCols: Int,
-      colAddrs: Array[Long], colLens: Array[Long], heapCols: Array[Array[Byte]],
-      delta0Addrs: Array[Long], delta0Lens: Array[Long], delta1Addrs: Array[Long], delta1Lens: Array[Long],
-      deleteAddr: Long, deleteLen: Long, statsAddr: Long, statsLen: Long, statsNCols: Int,
+      colAddrs: Array[Long], colLens: Array[Long], heapCols: Array[Array[Byte]], heapOffsets: Array[Int],
+      delta0Addrs: Array[Long], delta0Lens: Array[Long], delta0Heap: Array[Array[Byte]], delta0Offsets: Array[Int],
+      delta1Addrs: Array[Long], delta1Lens: Array[Long], delta1Heap: Array[Array[Byte]], delta1Offsets: Array[Int],
+      deleteAddr: Long, deleteLen: Long, deleteHeap: Array[Byte], deleteOffset: Int,
+      statsAddr: Long, statsLen: Long, statsHeap: Array[Byte], statsOffset: Int, statsNCols: Int,
       bucketId: Int, batchId: Long): Unit
   @native def rowsSubmit(plan: Long, rowsAddr: Long, len: Long, nrows: Int): Unit
+  /** bytes written to outAddr; -needed when cap is too small (the execution is complete, call again) */
   @native def planFinish(plan: Long, outAddr: Long, cap: Long): Long
   @native def planReset(plan: Long): Unit
   @native def planMetrics(plan: Long, out: Array[Long]): Unit

@@ -624,6 +624,13 @@ extern "C" {
 
 const char* sd_last_error(void) { return sd::last_error_cstr(); }
 
+int sd_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return sd::set_error(SD_ERR_INVALID, "sd_host_alloc: bad arguments");
+  SD_CUDA(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+  return 0;
+}
+void sd_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store** out) {
   if (!out || ncols < 0 || (ncols > 0 && !schema)) return sd::set_error(SD_ERR_INVALID, "sd_store_create: bad arguments");
   int ndev = 0;

@@ -210,6 +210,17 @@ struct Gen {
         const int ps = decimal_ps(p, i), pr = ps >> 8, sc = ps & 0xff;
         if (pr < 1 || pr > 18 || sc > pr) return fail(SD_ERR_INVALID, "DECIMAL expression needs 1 <= precision <= 18 and scale <= precision (sd_expr.c / sd_column)");
       }
+      if (e.op == SD_OP_CAST) {   // refused casts are refused at plan creation, whether or not the node ends up in generated code
+        const int from = p.exprs[e.a].type, to = e.type;
+        const bool tf = from == SD_DATE || from == SD_TIMESTAMP, tt = to == SD_DATE || to == SD_TIMESTAMP;
+        if (from == SD_STRING || to == SD_STRING) return fail(SD_ERR_UNSUPPORTED, "casts involving STRING");
+        if ((tf || tt) && from != to) return fail(SD_ERR_UNSUPPORTED, "casts involving DATE / TIMESTAMP (time-zone dependent in Spark)");
+        if (from == SD_DECIMAL && !(type_is_fp(to) || to == SD_DECIMAL)) return fail(SD_ERR_UNSUPPORTED, "this cast from DECIMAL");
+        if (to == SD_DECIMAL && !(from == SD_BYTE || from == SD_SHORT || from == SD_INT || from == SD_LONG || from == SD_DECIMAL))
+          return fail(SD_ERR_UNSUPPORTED, "this cast to DECIMAL");
+        if (from == SD_DECIMAL && to == SD_DECIMAL && (decimal_ps(p, i) & 0xff) < (decimal_ps(p, e.a) & 0xff))
+          return fail(SD_ERR_UNSUPPORTED, "DECIMAL cast that reduces the scale (needs HALF_UP rounding)");
+      }
     }
     auto chk = [&](int n) { return n >= 0 && n < ne; };
     if (p.filter >= 0 && (!chk(p.filter) || p.exprs[p.filter].type != SD_BOOLEAN)) return fail(SD_ERR_INVALID, "filter must be a BOOLEAN expression");

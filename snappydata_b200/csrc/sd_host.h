@@ -159,12 +159,14 @@ struct sd_store {
   int64_t lz4_buffers = 0, lz4_in_bytes = 0, lz4_out_bytes = 0;
   // expansions are queued on a few streams of their own so that the launches of successive flushes (each one as
   // long as its longest buffer) overlap each other and the copies that follow
-  static constexpr int LZ4_STREAMS = 4;
-  cudaStream_t lz4_streams[LZ4_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t lz4_done[LZ4_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
-  bool lz4_used[LZ4_STREAMS] = {false, false, false, false};
+  static constexpr int LZ4_STREAMS = 12;   // enough launches in flight to keep ~2800 buffers resident with 256 MB flushes
+  cudaStream_t lz4_streams[LZ4_STREAMS] = {};
+  cudaEvent_t lz4_done[LZ4_STREAMS] = {};
+  bool lz4_used[LZ4_STREAMS] = {};
   cudaEvent_t lz4_copied = nullptr;
   int lz4_next = 0;
+  // compressed payloads of one batch that lie (almost) back to back in host memory travel as ONE copy
+  const uint8_t* span_h0 = nullptr; uint8_t* span_d0 = nullptr; size_t span_len = 0;
   sd::PinnedArena lz4_jobs_host;   // page-locked copies of the job lists (a pageable source would stall the caller per flush)
 };
 

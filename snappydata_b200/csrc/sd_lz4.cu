@@ -244,13 +244,16 @@ __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Jo
     if (lane == 0) atomicExch(error_flag, 1u);
     return;
   }
-  const uint8_t* __restrict__ src = j.src;
+  // input positions are "shifted" like the output's: src = j.src rounded down to 16 bytes, so that the 16-byte staging
+  // loads are aligned wherever the payload lies (payloads copied as one span keep their host alignment)
+  const uint32_t sofs = (uint32_t)(reinterpret_cast<uintptr_t>(j.src) & 15);
+  const uint8_t* __restrict__ src = j.src - sofs;
   const uint32_t wofs = (uint32_t)(reinterpret_cast<uintptr_t>(j.dst) & 15);
   uint8_t* dst_al = j.dst - wofs;
-  const uint32_t n_src = (uint32_t)j.src_len, end = (uint32_t)j.dst_len + wofs;
-  uint32_t s = 0, o = wofs, flushed = wofs;
+  const uint32_t n_src = (uint32_t)j.src_len + sofs, end = (uint32_t)j.dst_len + wofs;
+  uint32_t s = sofs, o = wofs, flushed = wofs;
   uint32_t in_hi = 0;   // the input ring holds src[.., in_hi) (multiple of 16), byte p in slot p & CFG::IM
-  const bool src_aligned = (reinterpret_cast<uintptr_t>(j.src) & 15) == 0;
+  const bool src_aligned = true;
   bool bad = false, finished = false;
 
   while (!finished && !bad) {
@@ -400,12 +403,27 @@ __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Jo
       const uint32_t msrc = my_mdst - my_off;
       const uint32_t dep_end = msrc + (my_ml < my_off ? my_ml : my_off);   // exclusive end of the bytes the match needs from others
       const bool near = group_end - msrc <= (uint32_t)CFG::WIN;              // its source is still in the ring after this group's writes
+      // Which lanes of this group must have copied their match before mine may run?  Match regions are ordered by lane, so
+      // the ones my source range [msrc, dep_end) overlaps are a contiguous run of lower lanes: two 5-step binary searches
+      // over the lanes' (start, end) with shuffles.  Literals are all in place already.  A match then waits only for the
+      // depth of its own dependency chain (typically 1-3 rounds), not for every earlier lane (it used to be a wavefront).
+      const uint32_t my_mend = my_mdst + my_ml;
+      uint32_t lo_a = 0, hi_a = lane, lo_b = 0, hi_b = lane;
+#pragma unroll
+      for (int st = 0; st < 5; st++) {
+        const uint32_t mid_a = (lo_a + hi_a) >> 1, mid_b = (lo_b + hi_b) >> 1;
+        const uint32_t e = __shfl_sync(FULL, my_mend, (int)(mid_a & 31u));
+        const uint32_t b2 = __shfl_sync(FULL, my_mdst, (int)(mid_b & 31u));
+        if (lo_a < hi_a) { if (e > msrc) hi_a = mid_a; else lo_a = mid_a + 1; }       // first lane whose match ends beyond msrc
+        if (lo_b < hi_b) { if (b2 >= dep_end) hi_b = mid_b; else lo_b = mid_b + 1; }   // first lane whose match starts at / after dep_end
+      }
+      const uint32_t below_b = lo_b >= 32u ? FULL : ((1u << lo_b) - 1u);
+      const uint32_t below_a = lo_a >= 32u ? FULL : ((1u << lo_a) - 1u);
+      const uint32_t need = below_b & ~below_a;
       for (;;) {
         const unsigned mask = __ballot_sync(FULL, pending);
         if (!mask) break;
-        const int k = __ffs(mask) - 1;
-        const uint32_t ready_below = __shfl_sync(FULL, my_mdst, k);   // every byte below it is final
-        if (pending && (lane == k || dep_end <= ready_below)) {
+        if (pending && (need & mask) == 0u) {   // the lowest pending lane always qualifies: its needs are lower lanes
           lz_lane_match<CFG>(win, dst_al, my_mdst, msrc, my_ml, my_off, near);
           pending = false;
         }
@@ -480,8 +498,10 @@ int lz4_launch_shape(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsig
 }
 
 int lz4_launch(cudaStream_t stream, const Lz4Job* d_jobs, int njobs, unsigned int* d_error) {
-  static const bool dense = getenv("SD_TUNE_LZ4_DENSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
-  static const bool wparse = getenv("SD_TUNE_LZ4_PARSE") != nullptr && atoi(getenv("SD_TUNE_LZ4_PARSE")) > 0;
+  // defaults (profiles/r02_lz4.txt): the dense shape (1 warp + ~11 KB of shared memory per CTA: ~19 buffers resident per SM)
+  // with the window parse: 127 GB/s of expanded output at 6000 buffers vs 45 GB/s for the round-1 default
+  static const bool dense = getenv("SD_TUNE_LZ4_DENSE") == nullptr || atoi(getenv("SD_TUNE_LZ4_DENSE")) > 0;
+  static const bool wparse = getenv("SD_TUNE_LZ4_PARSE") == nullptr || atoi(getenv("SD_TUNE_LZ4_PARSE")) > 0;
   return lz4_launch_shape(stream, d_jobs, njobs, d_error, dense, wparse);
 }
 

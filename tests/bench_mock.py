@@ -74,6 +74,7 @@ spec = importlib.util.spec_from_file_location("bench", __import__("os").path.joi
 # C.byref(ln) -> our fake lib reads ._obj
 b.QueryRun.cpu_baseline = lambda self, s: ({"value": 1.0, "unit": "rows/s", "cores": 1, "kind": "port", "sample": "mock"}, None)
 b.QueryRun.parity_check = lambda self, rows, threads: {"ok": True, "rows": self.e2e_rows, "groups": 0, "max_rel_err": 0.0, "counts_exact": True}
+b.QueryRun.prepare_pageable_copy = lambda self, n: (setattr(self, 'marshalled_pg', self.marshalled[:n]), setattr(self, 'pageable_rows', sum(m.c.num_rows for m in self.marshalled[:n])), setattr(self, 'pg_plan', self.e2e_plan))
 b.QueryRun.prepare_compressed_copy = lambda self, threads=32: (setattr(self, 'marshalled_lz4', self.marshalled), setattr(self, 'lz4_h2d_bytes', 1), setattr(self, 'lz4_compressed_buffers', 0))
 import os
 os.environ["BENCH_NO_CLOCKS"] = "1"

@@ -55,7 +55,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="q1", choices=["q1", "q6"])
+    ap.add_argument("--workload", default="q1", choices=["q1", "q6", "c4", "c5"],
+                    help="q1 (default; Q6 SF-10, C4 and C5 are measured in the same run under also / also_c4 / also_c5), q6, or one of "
+                         "BASELINE.json's other configs alone: c4 = wide-table filter + projection, c5 = hybrid scan under concurrent ingest")
+    ap.add_argument("--no-extras", action="store_true", help="skip also_c4 / also_c5 in the default run")
     ap.add_argument("--rows", type=int, default=0, help="override total table rows (default SF-100 for q1, SF-10 for q6)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -614,6 +617,27 @@ def main():
             return box[0]
         comm = capi.Comm(api, rank, world, local_rank, bcast)
 
+    if args.workload in ("c4", "c5"):   # BASELINE.json configs[3] / [4] alone
+        from snappydata_b200 import workloads
+        peak, peak_src = measured_peak_gbs()
+        if args.workload == "c4":
+            r = workloads.run_c4(api, torch, dist, rank, world, local_rank, args.steps, args.warmup, peak)
+        else:
+            assert world == 1, "C5 is a 1-GPU configuration (BASELINE.json configs[4])"
+            r = workloads.run_c5(api, torch, local_rank, args.steps, args.warmup, peak)
+        if rank == 0:
+            line = {"metric": "rows/sec, " + r["workload"], "value": r["value"], "unit": "rows/s", "n_gpus": world, "steps": r["steps"],
+                    "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "i32/f64/u8", "data": "synthetic", "config": {"workload": r["workload"]}, "gpu_launches": r["steps"]}
+            line.update({k: v for k, v in r.items() if k not in line})
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if not r["parity_check"]["ok"]:
+            sys.exit("parity_check failed (see the JSON line)")
+        return
+
     q1 = args.workload == "q1"
     total = args.rows or (SF100_ROWS if q1 else SF10_ROWS)
     main_run = QueryRun(api, torch, dist, q1, total, rank, world, local_rank, args.scaling, comm)
@@ -747,6 +771,19 @@ def main():
             other.prepare_host_copy()
             other.step_e2e()
             out["also"]["parity_check"] = run_parity(other, "q1 sf100" if oq1 else "q6 sf10", ofinal)
+    if not args.no_also and not args.no_extras and q1 and not args.rows:
+        # BASELINE.json's other two configurations in the same run, each with its own roofline and parity assertion
+        from snappydata_b200 import workloads
+        try:
+            del other
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        out["also_c4"] = workloads.run_c4(api, torch, dist, rank, world, local_rank, args.steps, args.warmup, peak)
+        parity_failed = parity_failed or not out["also_c4"]["parity_check"]["ok"]
+        if world == 1:
+            out["also_c5"] = workloads.run_c5(api, torch, local_rank, args.steps, args.warmup, peak)
+            parity_failed = parity_failed or not out["also_c5"]["parity_check"]["ok"]
     if comm is not None:
         out["exchange"] = dict(comm.info(), kind="sd_plan_exchange: ncclAllGather of partial rows by value inside libsnappygpu.so + merge on every rank")
     if rank == 0:

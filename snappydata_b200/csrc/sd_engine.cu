@@ -1319,10 +1319,20 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   SD_CUDA(cudaSetDevice(p->device));
   int rc = flush_pending(p);
   if (rc) return rc;
-  rc = store_flush_lz4(s);
-  if (rc) return rc;
-  rc = store_lz4_check(s);   // resident stores: expansions happen once, before the first scan
-  if (rc) return rc;
+  // snapshot under the store's lock: the batches present NOW are what this execution scans (ingest may continue meanwhile;
+  // the reference's scan likewise sees the batches of its snapshot, ColumnFormatIterator over the bucket's entries)
+  std::vector<const StoredBatch*> snapshot;
+  int64_t snap_version;
+  {
+    std::lock_guard<std::mutex> lock(s->mu);
+    rc = store_flush_lz4(s);
+    if (rc) return rc;
+    rc = store_lz4_check(s);   // resident stores: expansions happen once, before the first scan
+    if (rc) return rc;
+    snapshot.reserve(s->batches.size());
+    for (auto& sbp : s->batches) snapshot.push_back(sbp.get());
+    snap_version = s->version;
+  }
   for (auto& c : p->spec.cols) {
     if (c.table_ordinal < 0 || c.table_ordinal >= (int)s->schema.size()) return set_error(SD_ERR_INVALID, "plan column ordinal %d outside the store schema", c.table_ordinal);
     if (s->schema[c.table_ordinal].type != c.type || s->schema[c.table_ordinal].nullable != c.nullable)
@@ -1332,13 +1342,13 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   std::vector<int32_t> buckets(bucket_ids, bucket_ids + (bucket_ids ? nbuckets : 0));
   const std::string lk = literal_key(p);
   sd_plan::ScanCache& c = p->cache;
-  if (!(c.valid && c.store == s && c.version == s->version && c.buckets == buckets && c.lit_key == lk)) {
+  if (!(c.valid && c.store == s && c.version == snap_version && c.buckets == buckets && c.lit_key == lk)) {
     // (re)build: stats skipping + descriptors + tables, kept on the device for repeated executions
     c.valid = false;
     p->cache_arena.reset();
     std::vector<const StoredBatch*> list;
     int64_t seen = 0, skipped = 0;
-    for (auto& sbp : s->batches) {
+    for (const StoredBatch* sbp : snapshot) {
       const StoredBatch& sb = *sbp;
       if (!buckets.empty() && std::find(buckets.begin(), buckets.end(), sb.bucket_id) == buckets.end()) continue;
       seen++;
@@ -1356,7 +1366,7 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
       rc = build_scan(p, list, p->cache_arena, p->stream, &bs);
       if (rc) return rc;
     }
-    c.store = s; c.version = s->version; c.buckets = buckets; c.lit_key = lk;
+    c.store = s; c.version = snap_version; c.buckets = buckets; c.lit_key = lk;
     c.d_batches = bs.d_batches; c.d_prefix = bs.d_prefix; c.nbatches = bs.nbatches; c.total_chunks = bs.total_chunks;
     c.rows = bs.rows; c.algo_bytes = bs.algo_bytes; c.seen = seen; c.skipped = skipped;
     c.updated_cols = bs.updated_cols; c.deleted_batches = bs.deleted_batches; c.needs_slow = bs.needs_slow;

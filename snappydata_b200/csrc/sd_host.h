@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -138,6 +139,10 @@ struct StoredBatch {
 }  // namespace sd
 
 struct sd_store {
+  // ingest (sd_store_put_batch) may run concurrently with scans: `mu` guards batches / arena / version / the LZ4 queues.  A scan
+  // works on the SNAPSHOT of batch pointers it takes under the lock when it starts (batches are never removed or moved
+  // while the store lives; a batch becomes visible only after its bytes have reached the device).
+  std::mutex mu;
   int device = 0;
   std::vector<sd_column> schema;
   sd::Arena arena;

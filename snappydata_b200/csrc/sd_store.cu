@@ -526,6 +526,7 @@ int store_lz4_check(sd_store* s) {
 
 int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
   if (!b || b->num_rows < 0) return set_error(SD_ERR_INVALID, "bad batch");
+  std::lock_guard<std::mutex> lock(s->mu);
   cudaSetDevice(s->device);
   std::unique_ptr<StoredBatch> sb(new StoredBatch());
   sb->num_rows = b->num_rows; sb->bucket_id = b->bucket_id; sb->batch_id = b->batch_id;
@@ -692,8 +693,8 @@ int sd_store_put_batch(sd_store* s, const sd_batch* b) {
   return sd::store_put(s, b, nullptr);
 }
 
-int sd_store_num_batches(sd_store* s, int64_t* out) { *out = (int64_t)s->batches.size(); return 0; }
-int sd_store_bytes(sd_store* s, int64_t* out) { *out = (int64_t)s->arena.used; return 0; }
+int sd_store_num_batches(sd_store* s, int64_t* out) { std::lock_guard<std::mutex> lock(s->mu); *out = (int64_t)s->batches.size(); return 0; }
+int sd_store_bytes(sd_store* s, int64_t* out) { std::lock_guard<std::mutex> lock(s->mu); *out = (int64_t)s->arena.used; return 0; }
 
 void sd_store_destroy(sd_store* s) {
   if (!s) return;
@@ -710,7 +711,9 @@ void sd_store_destroy(sd_store* s) {
 }
 
 int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id, int64_t* batch_id) {
-  if (!s || batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
+  if (!s) return sd::set_error(SD_ERR_INVALID, "null store");
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
   const sd::StoredBatch& b = *s->batches[batch_index];
   if (num_rows) *num_rows = b.num_rows;
   if (bucket_id) *bucket_id = b.bucket_id;
@@ -719,7 +722,9 @@ int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, in
 }
 
 int sdx_store_get_buffer(sd_store* s, int64_t batch_index, int32_t table_col, void* out, int64_t cap, int64_t* out_len) {
-  if (!s || batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
+  if (!s) return sd::set_error(SD_ERR_INVALID, "null store");
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (batch_index < 0 || batch_index >= (int64_t)s->batches.size()) return sd::set_error(SD_ERR_INVALID, "batch index out of range");
   const sd::StoredBatch& b = *s->batches[batch_index];
   if (table_col < 0 || table_col >= (int)b.cols.size() || !b.cols[table_col].present || !b.cols[table_col].dev_base)
     return sd::set_error(SD_ERR_INVALID, "column %d not resident", table_col);

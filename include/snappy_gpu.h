@@ -217,6 +217,22 @@ int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store
 /* upload one batch; b->col_bufs is indexed by TABLE column here (ncols = table width; NULL entries
  * for columns never scanned); delta arrays likewise */
 int sd_store_put_batch(sd_store* s, const sd_batch* b);
+/* ---- ingest: ColumnBatch creation ON THE DEVICE.  Raw column values of one batch (what the reference's
+ *      generated insert loop feeds its ColumnEncoders row by row, core/.../columnar/ColumnInsertExec.scala:326-822) are copied to
+ *      the device once and encoded there into the reference's column buffers -- Uncompressed / Dictionary (first-seen
+ *      order, int16 -> int32 indexes at 32767 entries) / BooleanBitSet with trimmed null words, the default encoder choice
+ *      of enc/ColumnEncoding.scala:837-844 -- plus the stats row (lower / upper bound, null count per column;
+ *      ColumnInsertExec.scala:848-921).  The batch is resident and scannable when the call returns; its bytes are the ones
+ *      snappydata_b200/column_format.py writes for the same values (sdx_store_get_buffer / sdx_store_get_stats read them
+ *      back).  cols[c] describes TABLE column c (values == NULL: not materialised). ---------------------------------- */
+typedef struct sd_raw_column {
+  const void* values;        /* num_rows values: BOOLEAN / BYTE 1 byte, SHORT 2, INT / DATE / FLOAT 4, LONG / TIMESTAMP / DOUBLE /
+                                DECIMAL (unscaled) 8; STRING: int32 offsets[num_rows + 1] into str_bytes                  */
+  const uint8_t* str_bytes;  /* STRING: the values' bytes back to back                                                */
+  const uint8_t* nulls;      /* optional, 1 byte per row, non-zero = NULL; must be NULL for a NOT NULL column          */
+} sd_raw_column;
+int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw_column* cols, int32_t ncols,
+                          int32_t bucket_id, int64_t batch_id);
 int sd_store_num_batches(sd_store* s, int64_t* out);
 int sd_store_bytes(sd_store* s, int64_t* out);
 /* scan every resident batch of the given buckets (NULL/0 = all) with plan p: stats-row skipping on
@@ -282,6 +298,8 @@ int64_t sdx_lz4_decode_prefix(const void* src, int64_t src_len, void* dst, int64
 /* host decompression of a stored envelope [-codecId][uncompressedLen][payload] (LZ4 = 1, Snappy = 2), as the engine
  * applies it to update deltas, delete masks and Snappy column buffers (test hook; no CUDA call) */
 int sdx_decompress_envelope(const void* buf, int64_t len, void* out, int64_t cap, int64_t* out_len);
+/* stats row (UnsafeRow) of a resident batch */
+int sdx_store_get_stats(sd_store* s, int64_t batch_index, void* out, int64_t cap, int64_t* out_len);
 int sdx_store_batch_info(sd_store* s, int64_t batch_index, int32_t* num_rows, int32_t* bucket_id,
                          int64_t* batch_id);
 /* the batch-skipping decision (ColumnTableScan.scala:820-963) of a plan's filter for one stats row: *pass = 0 when the

@@ -74,6 +74,10 @@ class sd_literal(C.Structure):
                 ("s", C.c_char_p), ("slen", C.c_int32), ("pad_", C.c_int32)]
 
 
+class sd_raw_column(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("str_bytes", C.c_void_p), ("nulls", C.c_void_p)]
+
+
 class sd_batch(C.Structure):
     _fields_ = [("num_rows", C.c_int32), ("ncols", C.c_int32),
                 ("col_bufs", C.POINTER(C.c_void_p)), ("col_lens", C.POINTER(C.c_int64)),
@@ -200,6 +204,7 @@ class Api:
         self.plan_kernel_name = fn("plan_kernel_name", C.c_char_p, vp, required=False)
         self.store_create = fn("store_create", C.c_int, C.c_int, i32, C.POINTER(sd_column), C.POINTER(vp), required=False)
         self.store_put_batch = fn("store_put_batch", C.c_int, vp, C.POINTER(sd_batch), required=False)
+        self.store_encode_batch = fn("store_encode_batch", C.c_int, vp, i32, C.POINTER(sd_raw_column), i32, i32, i64, required=False)
         self.store_num_batches = fn("store_num_batches", C.c_int, vp, C.POINTER(i64), required=False)
         self.store_bytes = fn("store_bytes", C.c_int, vp, C.POINTER(i64), required=False)
         self.plan_scan_store = fn("plan_scan_store", C.c_int, vp, vp, C.POINTER(i32), i32, required=False)
@@ -539,6 +544,41 @@ class Store:
     def put(self, batch: ColumnBatch):
         mb = MarshalledBatch(batch, None)
         self.api.check(self.api.store_put_batch(self.h, C.byref(mb.c)))
+
+    def encode_batch(self, num_rows: int, raw: Dict[int, tuple], bucket_id: int = 0, batch_id: int = 0):
+        """Ingest: raw column values -> encoded ColumnBatch ON THE DEVICE (sd_store_encode_batch).
+        raw[table_col] = (values, nulls) with values a numpy array of the column's type (STRING: a sequence of bytes),
+        nulls a bool array or None."""
+        arr = (sd_raw_column * max(1, len(self.schema)))()
+        keep = []
+        for c, (vals, nulls) in raw.items():
+            t = self.schema[c][0]
+            if t == SqlType.STRING:
+                bs = [bytes(v) if v is not None else b"" for v in vals]
+                offs = np.zeros(len(bs) + 1, dtype=np.int32)
+                np.cumsum([len(b) for b in bs], out=offs[1:])
+                blob = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
+                keep += [offs, blob]
+                arr[c].values, arr[c].str_bytes = offs.ctypes.data, blob.ctypes.data
+            else:
+                from .column_format import np_dtype
+                v = np.ascontiguousarray(np.asarray(vals).astype(bool).astype("u1") if t == SqlType.BOOLEAN else np.asarray(vals).astype(np_dtype(t)))
+                keep.append(v)
+                arr[c].values = v.ctypes.data
+            if nulls is not None:
+                nb = np.ascontiguousarray(np.asarray(nulls).astype("u1"))
+                keep.append(nb)
+                arr[c].nulls = nb.ctypes.data
+        self.api.check(self.api.store_encode_batch(self.h, num_rows, arr, len(self.schema), bucket_id, batch_id))
+
+    def get_stats(self, batch_index: int) -> bytes:
+        f = self.api.lib.sdx_store_get_stats
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        ln = C.c_int64()
+        buf = C.create_string_buffer(1 << 16)
+        self.api.check(f(self.h, batch_index, buf, len(buf), C.byref(ln)))
+        return buf.raw[: ln.value]
 
     def num_batches(self) -> int:
         out = C.c_int64()

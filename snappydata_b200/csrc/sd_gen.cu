@@ -134,6 +134,7 @@ extern "C" int sdx_store_gen_lineitem(sd_store* s, int64_t first_row, int64_t nr
       if (s->schema[kOrdinal[k]].type != kType[k] || s->schema[kOrdinal[k]].nullable)
         return set_error(SD_ERR_INVALID, "store schema column %d does not match lineitem", kOrdinal[k]);
   if (nrows == 0) return 0;
+  std::lock_guard<std::mutex> lock(s->mu);
   SD_CUDA(cudaSetDevice(s->device));
   const int nb = (int)((nrows + rows_per_batch - 1) / rows_per_batch);
   std::vector<uint64_t> firsts(nb);
@@ -193,6 +194,7 @@ extern "C" int sdx_store_gen_lineitem(sd_store* s, int64_t first_row, int64_t nr
           code[v] = (int8_t)nd++;
           const char* str = k == 4 ? rf_str[v] : ls_str[v];
           const int32_t one = 1;
+          c.dict_rec_off.push_back(pl);
           memcpy(pre + pl, &one, 4); pre[pl + 4] = (uint8_t)str[0]; pl += 5;
           c.dict_strings.push_back(std::string(str, 1));
         }
@@ -214,6 +216,7 @@ extern "C" int sdx_store_gen_lineitem(sd_store* s, int64_t first_row, int64_t nr
       c.dev_base = s->arena.alloc((size_t)len + 160, 128, (size_t)body);
       if (!c.dev_base) return SD_ERR_CUDA;
       c.dev.data = c.dev_base + body;
+      for (size_t e = 0; e < c.dict_rec_off.size(); e++) c.dict_rec_ptr.push_back((int64_t)(uintptr_t)(c.dev_base + c.dict_rec_off[e]));
       c.fast = true;
       g.col[k] = c.dev_base;
       g.body_off[k] = body;

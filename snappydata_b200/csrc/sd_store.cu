@@ -171,8 +171,13 @@ static int64_t parse_dictionary(const uint8_t* p, const uint8_t* end, int type, 
   return q - p;
 }
 
-static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type, int nullable, int num_rows, StoredCol& c) {
+// device_fill_total >= 0: `buf` holds only the buffer's prefix (header, null words, dictionary) and a kernel of the caller
+// writes the whole buffer (device_fill_total bytes) at the device address this function reserves (sd_encode.cu)
+static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type, int nullable, int num_rows, StoredCol& c,
+                         int64_t device_fill_total = -1) {
   if (len < 8) return set_error(SD_ERR_INVALID, "column buffer shorter than its 8-byte header");
+  const bool device_fill = device_fill_total >= 0;
+  if (device_fill) len = device_fill_total;
   // ---- compressed envelope [-codecId][uncompressedLen][payload] (CompressionUtils.scala:53-61): only the
   //      compressed bytes go to the device; the host decodes just the leading bytes it must parse -------
   const uint8_t* payload = nullptr;
@@ -361,6 +366,9 @@ static int upload_column(sd_store* s, const uint8_t* buf, int64_t len, int type,
     }
     s->pending_lz4.push_back(Lz4Job{d_src, c.dev_base, payload_len, len});
     s->lz4_buffers++; s->lz4_in_bytes += payload_len; s->lz4_out_bytes += len;
+  } else if (device_fill) {
+    c.dev_base = s->arena.alloc((size_t)len + 160, 128, (size_t)body);
+    if (!c.dev_base) return SD_ERR_CUDA;
   } else {
     rc = upload_bytes(s, buf, (size_t)len, 128, (size_t)body, &c.dev_base);
     if (rc) return rc;
@@ -467,6 +475,12 @@ static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, 
   if (rc) return rc;
   d.dev.data = p;
   return 0;
+}
+
+int store_register_encoded(sd_store* s, const uint8_t* prefix, int64_t prefix_len, int64_t total_len, int type, int nullable,
+                           int num_rows, StoredCol& c) {
+  if (total_len < prefix_len) return set_error(SD_ERR_INVALID, "encoded column shorter than its prefix");
+  return upload_column(s, prefix, prefix_len, type, nullable, num_rows, c, total_len);
 }
 
 int store_flush_lz4(sd_store* s) {

@@ -10,7 +10,8 @@ C4  wide table, 128 columns c0..c127 cycling (INT, DOUBLE, dictionary STRING of 
     distinct batch ids (the scan reads all of them from HBM: 100 M rows x 39.1 B is far beyond the 126 MB L2).
 C5  hybrid scan: TPC-H Q6 over SF-10 lineitem where every batch carries update deltas (0.5 % of the rows in l_discount and
     l_quantity: <= 100 positions at depth 0, the rest at depth 1, a few in both), a delete mask (0.5 %), plus row-buffer
-    rows; an INGEST THREAD appends new batches (sd_store_put_batch) while the timed queries run.  Every query scans the
+    rows; an INGEST THREAD appends new batches while the timed queries run -- encoded on the device from raw values
+    (sd_store_encode_batch, the N2 path).  Every query scans the
     snapshot of batches present when it started; its result must equal the oracle's over exactly that snapshot.
 """
 from __future__ import annotations
@@ -178,7 +179,9 @@ def run_c5(api, torch, device, steps, warmup, peak, total_rows=59_986_052, inges
         bufs = [None] * 16
         for c in cols:
             bufs[c] = gen.get_buffer(i, c)
-        batches.append(_decorate_hybrid(ColumnBatch(num_rows=nrows, columns=bufs, batch_id=bid, bucket_id=bucket), r))
+        cb = ColumnBatch(num_rows=nrows, columns=bufs, batch_id=bid, bucket_id=bucket)
+        # batches of the base table carry deltas and deletes; freshly ingested ones (i >= nb_base) do not
+        batches.append(_decorate_hybrid(cb, r) if i < nb_base else cb)
     gen.close()
     nrb = 10_000
     rows = b""
@@ -222,12 +225,17 @@ def run_c5(api, torch, device, steps, warmup, peak, total_rows=59_986_052, inges
     stop = threading.Event()
     ingested = [0]
 
-    def ingest():   # appends batches while queries run (ctypes releases the GIL during the call)
-        for mb in marshalled[nb_base:]:
+    # raw values of the batches to ingest (all four Q6 columns are NOT NULL and Uncompressed: the body IS the value array)
+    dts = {P.L_SHIPDATE: "<i4", P.L_DISCOUNT: "<f8", P.L_QUANTITY: "<f8", P.L_EXTENDEDPRICE: "<f8"}
+    raws = [{c: (np.frombuffer(b.columns[c], dtype=dts[c], offset=8), None) for c in cols} for b in batches[nb_base:]]
+
+    def ingest():   # new batches are ENCODED ON THE DEVICE from raw values (sd_store_encode_batch) while queries run
+        for b, raw in zip(batches[nb_base:], raws):   # (ctypes releases the GIL during the call)
             if stop.is_set():
                 break
-            rc = api.store_put_batch(store.h, C.byref(mb.c))
-            if rc:
+            try:
+                store.encode_batch(b.num_rows, raw, b.bucket_id, b.batch_id)
+            except Exception:
                 break
             ingested[0] += 1
             time.sleep(0.0005)

@@ -379,6 +379,7 @@ class Plan:
         scan, the NCCL exchange when `comm` is given, partial rows (merged over the ranks with `comm`)."""
         if getattr(self, "_out_buf", None) is None:
             self._out_buf = C.create_string_buffer(1 << 14)
+        if getattr(self, "_out_len", None) is None:
             self._out_len, self._out_rows = C.c_int64(), C.c_int64()
         rc = self.api.plan_execute_store(self.h, store.h, None, 0, lit_array, nlits, comm.h if comm is not None else None,
                                          self._out_buf, len(self._out_buf), C.byref(self._out_len), C.byref(self._out_rows))

@@ -740,6 +740,12 @@ int analyze_plan(const sd_plan_desc* d, PlanSpec& out, std::string& err, const C
     if (o.rpt == 2 || o.rpt == 4 || o.rpt == 8) out.rpt = o.rpt;
     if (o.min_ctas >= 1) out.min_ctas = o.min_ctas;
     if (o.stages >= 0) out.stages = o.stages > 0 ? 1 : 0;
+    // a stage of the ring holds THREADS * RPT rows of every scan column (+ 128 bytes of alignment slack each): very wide
+    // plans first halve the tile, then give the ring up for direct vector loads (the ring needs >= 2 stages in ~200 KB)
+    auto stage_bytes = [&](int rpt) { return (size_t)THREADS * rpt * row_bytes + (size_t)128 * out.kinds.size(); };
+    const size_t ring_budget = size_t(200) << 10;
+    if (out.stages && 2 * stage_bytes(out.rpt) + (size_t)tile_smem_bytes((int)out.kinds.size(), out.rpt) > ring_budget && out.rpt > 2) out.rpt = 2;
+    if (out.stages && 2 * stage_bytes(out.rpt) + (size_t)tile_smem_bytes((int)out.kinds.size(), out.rpt) > ring_budget) out.stages = 0;
     if (out.stages == 0) out.reg_groups = 0;   // the register tables are reduced through the ring's memory
   }
   if (!projection) { rc = g.build_slots(); if (rc) return rc; }

@@ -601,8 +601,10 @@ static int build_buffer_schema(oracle_plan* p) {
     const sd_agg* a = &p->aggs[i];
     int ct = a->expr >= 0 ? p->exprs[a->expr].type : SD_LONG;
     int cn = a->expr >= 0 ? p->expr_nullable[a->expr] : 0;
-    if (a->expr >= 0 && (ct == SD_STRING) && a->fn != SD_AGG_COUNT)
-      return fail(SD_ERR_UNSUPPORTED, "aggregate over STRING input not supported");
+    if (a->expr >= 0 && (ct == SD_STRING) && a->fn != SD_AGG_COUNT && a->fn != SD_AGG_MIN && a->fn != SD_AGG_MAX)
+      return fail(SD_ERR_UNSUPPORTED, "aggregates over STRING: only MIN / MAX / COUNT");
+    if (a->expr >= 0 && ct == SD_STRING && (a->fn == SD_AGG_MIN || a->fn == SD_AGG_MAX) && p->exprs[a->expr].op != SD_OP_COL)
+      return fail(SD_ERR_UNSUPPORTED, "aggregates over STRING: only MIN / MAX / COUNT of a STRING column");
     int cps = ct == SD_DECIMAL ? dec_ps(p, a->expr) : 0;
     /* Sum / Average over DECIMAL(p,s): sumDataType = DecimalType.bounded(p + 10, s) (Spark 2.1.1 Sum.scala / Average.scala) */
     int sum_ps = (imin(38, (cps >> 8) + 10) << 8) | (cps & 0xff);
@@ -665,10 +667,19 @@ static void update_buffers(const oracle_plan* p, val* b, const val* cols) {
       case SD_AGG_MIN: case SD_AGG_MAX:
         if (!v.isnull) {
           v.w = v.i;
-          if (b[k].isnull) { b[k] = v; }
-          else {
-            int c = cmp_val(&v, &b[k], t);
-            if ((a->fn == SD_AGG_MIN && c < 0) || (a->fn == SD_AGG_MAX && c > 0)) b[k] = v;
+          int take = b[k].isnull;
+          if (!take) {
+            int c = cmp_val(&v, &b[k], t);     /* UTF8String.compareTo for strings: unsigned bytes, then length */
+            take = (a->fn == SD_AGG_MIN && c < 0) || (a->fn == SD_AGG_MAX && c > 0);
+          }
+          if (take) {
+            if (t == SD_STRING) {               /* the buffer owns its bytes (the batch's memory goes away) */
+              uint8_t* own = (uint8_t*)malloc(v.slen > 0 ? v.slen : 1);
+              memcpy(own, v.s, v.slen);
+              if (!b[k].isnull) free((void*)b[k].s);
+              v.s = own;
+            }
+            b[k] = v;
           }
         }
         k++; break;

@@ -290,8 +290,23 @@ struct Gen {
       const int in_null = a.expr >= 0 ? static_nullable(a.expr) : 0;
       m.in_type = it;
       if (a.fn != SD_AGG_COUNT_STAR && a.expr < 0) return fail(SD_ERR_INVALID, "aggregate without input expression");
-      if (a.expr >= 0 && it == SD_STRING && a.fn != SD_AGG_COUNT)
-        return fail(SD_ERR_UNSUPPORTED, "aggregate over a STRING input is not supported by the GPU path");
+      if (a.expr >= 0 && it == SD_STRING && a.fn != SD_AGG_COUNT) {
+        // MIN / MAX over a STRING column: the slot holds the address of the winning value's record (compared by bytes)
+        if (!(a.fn == SD_AGG_MIN || a.fn == SD_AGG_MAX) || p.exprs[a.expr].op != SD_OP_COL)
+          return fail(SD_ERR_UNSUPPORTED, "aggregates over STRING: only MIN / MAX / COUNT of a STRING column");
+        m.buf_type = SD_STRING;
+        m.value_slot2 = -1;
+        const int col = p.exprs[a.expr].a;
+        int t = -1;
+        for (size_t ti = 0; ti < p.tables.size(); ti++) if (p.tables[ti].kind == TABLE_KEYPTR && p.tables[ti].col == col && p.tables[ti].key < 0) t = (int)ti;
+        if (t < 0) { p.tables.push_back(TableSpec{TABLE_KEYPTR, col, -1, -1}); t = (int)p.tables.size() - 1; }
+        m.value_slot = add_slot(a.fn == SD_AGG_MIN ? SLOT_MIN_STR : SLOT_MAX_STR, a.expr, GATE_STRREF);
+        p.slots[m.value_slot].table = t;
+        m.buf_nullable = keyed ? in_null : 1;
+        if (m.buf_nullable) m.count_slot = count_slot_for(a.expr);
+        p.agg_map.push_back(m);
+        continue;
+      }
       m.value_slot2 = -1;
       if (it == SD_DECIMAL) {
         m.in_ps = decimal_ps(p, a.expr);
@@ -610,6 +625,10 @@ struct Gen {
       slt << "    sv[" << s << "] = ";
       if (x.gate == GATE_ONE) slt << "1ull;\n";
       else if (x.gate == GATE_NONNULL_COUNT) slt << NL << " ? 0ull : 1ull;\n";
+      else if (x.gate == GATE_STRREF) {
+        const int col = p.exprs[x.node].a;
+        slt << NL << " ? 0ull : (uint64_t)ctx.str_ref(" << col << ", " << x.table << ", r.c" << col << ");\n";
+      }
       else if (x.gate == GATE_VALUE_HI32) slt << NL << " ? 0ull : (uint64_t)((int64_t)" << V << " >> 32);\n";
       else if (x.gate == GATE_VALUE_LO32) slt << NL << " ? 0ull : ((uint64_t)(int64_t)" << V << " & 0xffffffffull);\n";
       else {

@@ -24,12 +24,14 @@ struct TableSpec {
 
 // GATE_VALUE_HI32 / GATE_VALUE_LO32: the two halves of a wide (128-bit) integer sum: v = (v >> 32) * 2^32 + (v & 0xffffffff);
 // each half is summed in its own int64 slot (exact for < 2^31 rows per execution), recombined on the host
-enum SlotGate { GATE_VALUE = 0, GATE_NONNULL_COUNT = 1, GATE_ONE = 2, GATE_VALUE_HI32 = 3, GATE_VALUE_LO32 = 4 };
+// GATE_STRREF: the value is a STRING column held by reference (address of its record; SlotSpec.table = its TABLE_KEYPTR table)
+enum SlotGate { GATE_VALUE = 0, GATE_NONNULL_COUNT = 1, GATE_ONE = 2, GATE_VALUE_HI32 = 3, GATE_VALUE_LO32 = 4, GATE_STRREF = 5 };
 
 struct SlotSpec {
   int op;     // SLOT_*
   int node;   // input expression (-1: none)
   int gate;   // SlotGate
+  int table = -1;   // GATE_STRREF: index of the column's TABLE_KEYPTR table
 };
 
 // how an aggregate's buffer fields map to slots

@@ -144,7 +144,11 @@ struct HashTable {
 enum : int32_t { TABLE_PRIVATE = 0, TABLE_SHARED_ATOMIC = 1, TABLE_GLOBAL_ATOMIC = 2, TABLE_REGS = 3 };
 
 // accumulator slot operations; every slot is 8 bytes
-enum : int32_t { SLOT_ADD_F64 = 0, SLOT_ADD_I64 = 1, SLOT_MIN_I64 = 2, SLOT_MAX_I64 = 3, SLOT_MIN_F64 = 4, SLOT_MAX_F64 = 5 };
+// SLOT_MIN_STR / SLOT_MAX_STR: the slot holds the device address of the winning value's [len][bytes] record (0: no value yet);
+// values compare as unsigned bytes (MIN / MAX over STRING: the aggregate buffer is not fixed-width, which is what sends the
+// reference down its ObjectHashSet path, SnappyHashAggregateExec.scala:82-94)
+enum : int32_t { SLOT_ADD_F64 = 0, SLOT_ADD_I64 = 1, SLOT_MIN_I64 = 2, SLOT_MAX_I64 = 3, SLOT_MIN_F64 = 4, SLOT_MAX_F64 = 5,
+                 SLOT_MIN_STR = 6, SLOT_MAX_STR = 7 };
 
 struct ScanArgs {
   const void* batches;            // DevBatch<NC>[nbatches]

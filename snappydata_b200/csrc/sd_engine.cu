@@ -977,12 +977,40 @@ int resolve_kernel(const sd_plan_desc& desc, const CodegenOptions& opt, int devi
   return 0;
 }
 
+// MIN / MAX over STRING: slots hold device addresses of [len][bytes] records -> their bytes, for every group at once
+typedef std::unordered_map<uint64_t, std::string> StrMap;
+int fetch_agg_strings(sd_plan* p, const uint64_t* slots, size_t ngroups, StrMap& out) {
+  const PlanSpec& sp = p->spec;
+  const size_t ns = sp.slots.size();
+  std::vector<int64_t> ptrs;
+  for (auto& m : sp.agg_map) {
+    if (m.buf_type != SD_STRING) continue;
+    for (size_t g = 0; g < ngroups; g++) { const uint64_t a = slots[g * ns + m.value_slot]; if (a && !out.count(a)) { out.emplace(a, std::string()); ptrs.push_back((int64_t)a); } }
+  }
+  if (ptrs.empty()) return 0;
+  int64_t* d_ptrs = nullptr;
+  SD_CUDA(cudaMalloc(&d_ptrs, ptrs.size() * 8));
+  std::vector<std::string> strs;
+  cudaError_t ce = cudaMemcpyAsync(d_ptrs, ptrs.data(), ptrs.size() * 8, cudaMemcpyHostToDevice, p->stream);
+  int rc = ce == cudaSuccess ? fetch_string_records(p->stream, d_ptrs, (int64_t)ptrs.size(), 1, strs) : set_error(SD_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(ce));
+  cudaFree(d_ptrs);
+  if (rc) return rc;
+  for (size_t i = 0; i < ptrs.size(); i++) out[(uint64_t)ptrs[i]] = strs[i];
+  return 0;
+}
+
 // partial-row fields of one group from its slot values (shared by the dense and the hash paths)
-void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>& vals) {
+void append_agg_fields(const PlanSpec& sp, const uint64_t* sv, std::vector<HVal>& vals, const StrMap* strs = nullptr) {
   for (auto& m : sp.agg_map) {
     HVal v;
     const uint64_t raw = sv[m.value_slot];
     const int64_t cnt = m.count_slot >= 0 ? (int64_t)sv[m.count_slot] : 1;
+    if (m.buf_type == SD_STRING) {
+      if ((m.buf_nullable && cnt == 0) || raw == 0 || !strs) v.isnull = true;
+      else { auto it = strs->find(raw); if (it == strs->end()) v.isnull = true; else v.s = it->second; }
+      vals.push_back(v);
+      continue;
+    }
     if (m.value_slot2 >= 0) {   // DECIMAL SUM / AVG: high and low halves summed separately (sd_codegen.cpp build_slots)
       v.w = (i128)(int64_t)sv[m.value_slot] * ((i128)1 << 32) + (i128)(int64_t)sv[m.value_slot2];
       v.i = (int64_t)v.w;
@@ -1062,6 +1090,9 @@ int finish_hash(sd_plan* p) {
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
   const std::vector<int> types = partial_field_types(sp);
+  StrMap agg_strs;
+  rc = fetch_agg_strings(p, hv.data(), count, agg_strs);
+  if (rc) return rc;
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
   for (uint32_t g = 0; g < count; g++) {
@@ -1075,7 +1106,7 @@ int finish_hash(sd_plan* p) {
       else { v.i = code; v.w = code; }
       vals.push_back(v);
     }
-    append_agg_fields(sp, &hv[(size_t)g * ns], vals);
+    append_agg_fields(sp, &hv[(size_t)g * ns], vals, &agg_strs);
     emit_unsafe_row(out, types, vals);
   }
   p->finished_nrows = count;
@@ -1403,6 +1434,12 @@ static int finish_dense(sd_plan* p) {
   p->metrics[11] = (int64_t)counters[0];
   // partial rows: UnsafeRow(group keys ++ aggregate buffers) (SnappyHashAggregateExec.scala:1148-1178)
   const std::vector<int> types = partial_field_types(sp);
+  StrMap agg_strs;
+  {
+    std::vector<uint64_t> copy(h, h + ne);   // (the pinned mirror is reused by the fetch's own read-backs)
+    rc = fetch_agg_strings(p, copy.data(), (size_t)p->ngroups, agg_strs);
+    if (rc) return rc;
+  }
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
   int64_t nrows = 0;
@@ -1418,7 +1455,7 @@ static int finish_dense(sd_plan* p) {
       if (idx[k] == p->key_null_id[k]) v.isnull = true; else v.s = p->key_vals[k][idx[k]];
       vals.push_back(v);
     }
-    append_agg_fields(sp, sv, vals);
+    append_agg_fields(sp, sv, vals, &agg_strs);
     emit_unsafe_row(out, types, vals);
     nrows++;
   }

@@ -63,49 +63,6 @@ __device__ __forceinline__ int tv_and(int a, int b) { return (a == 0 || b == 0) 
 __device__ __forceinline__ int tv_or(int a, int b) { return (a == 1 || b == 1) ? 1 : ((a == 2 || b == 2) ? 2 : 0); }
 __device__ __forceinline__ int tv_not(int a) { return a == 2 ? 2 : 1 - a; }
 
-// ---- slot (accumulator) algebra: every op is a commutative monoid over 8-byte words ------------
-__device__ __forceinline__ uint64_t f2u(double d) { return (uint64_t)__double_as_longlong(d); }
-__device__ __forceinline__ double u2f(uint64_t u) { return __longlong_as_double((long long)u); }
-
-__host__ __device__ constexpr uint64_t slot_identity(int op) {
-  return op == SLOT_ADD_F64 ? 0ull
-       : op == SLOT_ADD_I64 ? 0ull
-       : op == SLOT_MIN_I64 ? 0x7fffffffffffffffull
-       : op == SLOT_MAX_I64 ? 0x8000000000000000ull
-       : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull   /* NaN: the greatest element of the order */
-       : 0xfff0000000000000ull;                        /* SLOT_MAX_F64: -inf */
-}
-__device__ __forceinline__ uint64_t slot_combine(int op, uint64_t a, uint64_t b) {
-  switch (op) {
-    case SLOT_ADD_F64: return f2u(u2f(a) + u2f(b));
-    case SLOT_ADD_I64: return a + b;
-    case SLOT_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
-    case SLOT_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
-    case SLOT_MIN_F64: return f_lt(u2f(b), u2f(a)) ? b : a;
-    default: return f_gt(u2f(b), u2f(a)) ? b : a;
-  }
-}
-
-// atomic version (shared or global address): used when the group table is shared by many threads
-__device__ __forceinline__ void slot_atomic(int op, uint64_t* p, uint64_t v) {
-  switch (op) {
-    case SLOT_ADD_F64: if (v != 0ull) atomicAdd(reinterpret_cast<double*>(p), u2f(v)); break;   // x + (+0.0) == x for every running sum
-    case SLOT_ADD_I64: if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); break;
-    case SLOT_MIN_I64: atomicMin(reinterpret_cast<long long*>(p), (long long)v); break;
-    case SLOT_MAX_I64: atomicMax(reinterpret_cast<long long*>(p), (long long)v); break;
-    default: {   // NaN-aware double min / max: CAS loop
-      unsigned long long* a = reinterpret_cast<unsigned long long*>(p);
-      unsigned long long old = *a, assumed;
-      do {
-        assumed = old;
-        const unsigned long long want = slot_combine(op, assumed, v);
-        if (want == assumed) break;
-        old = atomicCAS(a, assumed, want);
-      } while (old != assumed);
-    }
-  }
-}
-
 // ---- variable-width strings by their bytes: records are [len:int32 LE][bytes], unaligned (enc/Uncompressed.scala:116-161;
 //      the same layout as a string dictionary entry, enc/DictionaryEncoding.scala:452-518).  Strings compare as unsigned
 //      bytes, shorter first on a common prefix (UTF8String.compareTo) -----------------------------
@@ -132,11 +89,65 @@ __device__ __noinline__ bool str_eq_recs(const uint8_t* a, const uint8_t* b) {
   for (int i = 0; i < n; i++) if (a[4 + i] != b[4 + i]) return false;
   return true;
 }
+__device__ __noinline__ int str_cmp_recs(const uint8_t* a, const uint8_t* b) {   // UTF8String.compareTo on two records
+  const int na = rec_len(a), nb = rec_len(b), m = na < nb ? na : nb;
+  for (int i = 0; i < m; i++) { const int d = (int)a[4 + i] - (int)b[4 + i]; if (d) return d; }
+  return na - nb;
+}
 __device__ __noinline__ uint64_t str_hash_rec(const uint8_t* rec) {   // FNV-1a over the bytes
   const int n = rec_len(rec);
   uint64_t h = 1469598103934665603ull;
   for (int i = 0; i < n; i++) { h ^= rec[4 + i]; h *= 1099511628211ull; }
   return h ^ (uint64_t)n;
+}
+
+// ---- slot (accumulator) algebra: every op is a commutative monoid over 8-byte words ------------
+__device__ __forceinline__ uint64_t f2u(double d) { return (uint64_t)__double_as_longlong(d); }
+__device__ __forceinline__ double u2f(uint64_t u) { return __longlong_as_double((long long)u); }
+
+__host__ __device__ constexpr uint64_t slot_identity(int op) {
+  return op == SLOT_ADD_F64 ? 0ull
+       : op == SLOT_ADD_I64 ? 0ull
+       : op == SLOT_MIN_I64 ? 0x7fffffffffffffffull
+       : op == SLOT_MAX_I64 ? 0x8000000000000000ull
+       : op == SLOT_MIN_F64 ? 0x7ff8000000000000ull   /* NaN: the greatest element of the order */
+       : op == SLOT_MAX_F64 ? 0xfff0000000000000ull   /* -inf */
+       : 0ull;                                         /* SLOT_MIN_STR / SLOT_MAX_STR: no record yet */
+}
+__device__ __forceinline__ uint64_t slot_combine(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case SLOT_ADD_F64: return f2u(u2f(a) + u2f(b));
+    case SLOT_ADD_I64: return a + b;
+    case SLOT_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
+    case SLOT_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
+    case SLOT_MIN_F64: return f_lt(u2f(b), u2f(a)) ? b : a;
+    case SLOT_MAX_F64: return f_gt(u2f(b), u2f(a)) ? b : a;
+    default: {   // SLOT_MIN_STR / SLOT_MAX_STR: addresses of [len][bytes] records, 0 = none
+      if (a == 0ull || b == 0ull || a == b) return a ? a : b;
+      const int c = str_cmp_recs(reinterpret_cast<const uint8_t*>(b), reinterpret_cast<const uint8_t*>(a));
+      return (op == SLOT_MIN_STR ? c < 0 : c > 0) ? b : a;
+    }
+  }
+}
+
+// atomic version (shared or global address): used when the group table is shared by many threads
+__device__ __forceinline__ void slot_atomic(int op, uint64_t* p, uint64_t v) {
+  switch (op) {
+    case SLOT_ADD_F64: if (v != 0ull) atomicAdd(reinterpret_cast<double*>(p), u2f(v)); break;   // x + (+0.0) == x for every running sum
+    case SLOT_ADD_I64: if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); break;
+    case SLOT_MIN_I64: atomicMin(reinterpret_cast<long long*>(p), (long long)v); break;
+    case SLOT_MAX_I64: atomicMax(reinterpret_cast<long long*>(p), (long long)v); break;
+    default: {   // NaN-aware double min / max: CAS loop
+      unsigned long long* a = reinterpret_cast<unsigned long long*>(p);
+      unsigned long long old = *a, assumed;
+      do {
+        assumed = old;
+        const unsigned long long want = slot_combine(op, assumed, v);
+        if (want == assumed) break;
+        old = atomicCAS(a, assumed, want);
+      } while (old != assumed);
+    }
+  }
 }
 
 // ---- MODE_HASH: find-or-insert of a key tuple, then atomic slot updates ---------------------------------

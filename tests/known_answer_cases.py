@@ -296,7 +296,37 @@ def case_sha_null_key_bit_masking_1_to_32_key_columns(_run):
         assert found_null
 
 
+def case_min_max_of_strings(_run):
+    """MIN / MAX over a STRING column (the aggregate buffer is not fixed-width: the reference's ObjectHashSet path,
+    SnappyHashAggregateExec.scala:82-94): 300 rows i, s = 's%03d' % i (NULL when i % 7 == 0), key = i % 4: per key the smallest /
+    largest surviving i; one batch dictionary-encoded, one with the strings as an Uncompressed variable-width body."""
+    n = 300
+    i = np.arange(n)
+    s = np.array([b"s%03d" % x for x in i], dtype=object)
+    nulls = {"s": (i % 7) == 0}
+    schema = [("k", T.INT, False), ("s", T.STRING, True)]
+    half = n // 2
+    batches = [build_batch(half, schema, {"k": (i[:half] % 4).astype(np.int32), "s": s[:half]}, {"s": nulls["s"][:half]}, batch_id=0),
+               build_batch(n - half, schema, {"k": (i[half:] % 4).astype(np.int32), "s": s[half:]}, {"s": nulls["s"][half:]}, batch_id=1,
+                           encoders={"s": "uncompressed"})]
+    b = PlanBuilder()
+    k, sc = b.col(T.INT, 0, False), b.col(T.STRING, 1, True)
+    b.group_by(k)
+    b.min(sc).max(sc).count(sc)
+    rows, _ = _run(b.build(), [], batches)
+    assert len(rows) == 4
+    for key, mn, mx, cnt in rows:
+        alive = [x for x in range(n) if x % 4 == key and x % 7 != 0]
+        assert (mn, mx, cnt) == (b"s%03d" % min(alive), b"s%03d" % max(alive), len(alive))
+    b = PlanBuilder()   # no key; and a filter that leaves nothing: NULL results
+    k, sc = b.col(T.INT, 0, False), b.col(T.STRING, 1, True)
+    b.filter(k > b.lit(T.INT))
+    b.min(sc).max(sc)
+    assert _run(b.build(), [-1], batches)[0] == [[b"s001", b"s299"]]
+    assert _run(b.build(), [99], batches)[0] == [[None, None]]
+
+
 CASES = [case_sha_one_nullable_string_key_closed_form, case_sha_two_nullable_string_keys_closed_form,
          case_delta_stats_point_filters_after_updates, case_basic_delete_and_update_counts,
          case_sha_sum_of_every_numeric_type_per_string_key, case_sha_decimal_sum_and_avg_per_string_key, case_casts_follow_spark,
-         case_sha_null_key_bit_masking_1_to_32_key_columns]
+         case_sha_null_key_bit_masking_1_to_32_key_columns, case_min_max_of_strings]

@@ -137,6 +137,29 @@ def test_projection_of_raw_strings(gpu_api, mixed):
     assert_rowsets_match(got, want, 4)
 
 
+def test_min_max_over_string_columns(gpu_api, mixed):
+    """MIN / MAX(STRING): slot = address of the winning record, compared by bytes; dense table, hash table and no-key plans,
+    dictionary and raw batches mixed."""
+    b = PlanBuilder()
+    c = cols(b)
+    b.group_by(c["t"])                       # dictionary keys -> dense table until the raw batch switches it to the hash table
+    b.min(c["s"]).max(c["s"]).count(c["s"]).sum(c["v"])
+    both(gpu_api, b.build(), [], mixed, 1)
+    both(gpu_api, b.build(), [], [mixed[2]], 1)          # dictionary batches only: stays a dense table
+    b = PlanBuilder()
+    c = cols(b)
+    b.group_by(c["v"])                       # integer key -> hash table
+    b.min(c["t"]).max(c["s"])
+    both(gpu_api, b.build(), [], mixed, 1)
+    b = PlanBuilder()
+    c = cols(b)
+    b.filter(c["d"] > b.lit(T.DOUBLE))
+    b.min(c["s"]).max(c["s"]).min(c["t"]).max(c["t"]).count()
+    both(gpu_api, b.build(), [5.0], mixed, 0)
+    both(gpu_api, b.build(), [1e9], mixed, 0)            # nothing passes: NULL results
+    both(gpu_api, b.build(), [5.0], mixed, 0, store=True)
+
+
 def _recompress(batch, fn):
     c = copy.copy(batch)
     c.columns = [None if x is None else fn(x) for x in batch.columns]

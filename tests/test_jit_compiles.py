@@ -42,6 +42,12 @@ def _plans():
     b.group_by(sk)
     b.sum(dc).avg(dc).min(dc).sum(dc.cast(T.DOUBLE)).sum(ic.cast(T.DECIMAL, 9, 2)).sum(dc.cast(T.DECIMAL, 15, 7))
     out["decimal"] = b.build()
+    b = PlanBuilder()   # raw-string predicates (byte compares), string keys by reference in the hash table, MIN / MAX(STRING)
+    s1, s2, v = b.col(T.STRING, 0, True), b.col(T.STRING, 1, False), b.col(T.INT, 2, False)
+    b.filter((s1 >= b.lit(T.STRING)) & s2.startswith(b.lit(T.STRING)) | s1.isin(2))
+    b.group_by(s2, v)
+    b.min(s1).max(s1).count()
+    out["strings"] = b.build()
     return out
 
 
@@ -78,7 +84,7 @@ def _compile(source, name):
     return dt
 
 
-@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable", "decimal"])
+@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable", "decimal", "strings"])
 def test_every_kernel_variant_compiles_for_sm_100a(label):
     desc = _plans()[label]
     seen = set()

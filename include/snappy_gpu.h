@@ -233,6 +233,12 @@ typedef struct sd_raw_column {
 } sd_raw_column;
 int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw_column* cols, int32_t ncols,
                           int32_t bucket_id, int64_t batch_id);
+/* ColumnDeltaEncoder.merge (enc/ColumnDeltaEncoder.scala:348-556), host only: the new update delta of a column merged with what
+ * the table holds -- another delta (existing_is_delta = 1: union of positions, the new one wins on equal positions, result is a
+ * delta) or the full column of num_rows rows (existing_is_delta = 0: the delta folded into the column, result is a column
+ * buffer) -- re-encoded with the type's default encoder.  Either input may be a compressed envelope. */
+int sd_delta_merge(const sd_column* column, const void* new_delta, int64_t new_len, const void* existing, int64_t existing_len,
+                   int32_t existing_is_delta, int32_t num_rows, void* out, int64_t cap, int64_t* out_len);
 int sd_store_num_batches(sd_store* s, int64_t* out);
 int sd_store_bytes(sd_store* s, int64_t* out);
 /* scan every resident batch of the given buckets (NULL/0 = all) with plan p: stats-row skipping on

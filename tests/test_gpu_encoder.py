@@ -38,7 +38,7 @@ def table(n, seed, distinct_strings=12):
     return data, nulls
 
 
-@pytest.mark.parametrize("n,seed,nd", [(5000, 1, 12), (1, 2, 3), (64, 3, 5), (2049, 4, 12), (70000, 5, 40000)])
+@pytest.mark.parametrize("n,seed,nd", [(5000, 1, 12), (1, 2, 3), (64, 3, 5), (2049, 4, 12), (70000, 5, 60000)])
 def test_device_encoder_is_byte_identical_to_the_fixture_writer(gpu_api, n, seed, nd):
     data, nulls = table(n, seed, nd)
     want = build_batch(n, SCHEMA, data, nulls, batch_id=7, bucket_id=3)

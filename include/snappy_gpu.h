@@ -173,6 +173,11 @@ const char* sd_version(void);
  * is pinned while CUDA work is queued and host->device copies out of it are real asynchronous DMA) */
 int sd_host_alloc(int64_t bytes, void** out);
 void sd_host_free(void* p);
+/* page-lock memory the caller already owns and keeps for a long time (the region's off-heap column buffers): copies out of
+ * it become asynchronous DMA at link speed instead of the driver's staged pageable copies (bench.py: e2e_pageable_unretained
+ * is ~4x below the pinned legs) */
+int sd_host_register(void* p, int64_t bytes);
+int sd_host_unregister(void* p);
 
 /* ---- plan (one per Spark task / partition; ColumnTableScan.doProduce + SnappyHashAggregateExec
  *      doProduce/doConsume fused, core/.../ColumnTableScan.scala:186-672,

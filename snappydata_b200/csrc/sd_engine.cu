@@ -1169,32 +1169,72 @@ int finish_project(sd_plan* p) {
     cudaFree(d_ptrs);
     if (rc) return rc;
   }
+  // records -> UnsafeRows, written in place (no per-row value objects: C4 emits ~1 M rows per execution)
   size_t next_raw = 0;
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
-  out.reserve((size_t)count * (size_t)(16 + 8 * np));
-  std::vector<HVal> vals((size_t)np);
+  const int64_t bits = ((np + 63) / 64) * 8, fixed = bits + 8 * (int64_t)np;
+  // pass 1: sizes (strings are the only variable part)
+  size_t total = 0;
+  {
+    size_t nr = 0;
+    for (unsigned long long i = 0; i < count; i++) {
+      const uint64_t* r = &recs[(size_t)i * (size_t)(rec / 8)];
+      const uint32_t bidx = (uint32_t)(r[0] & 0xffffffffu), pnull = (uint32_t)(r[0] >> 32);
+      const StoredBatch& sb = *p->exec_batches[bidx];
+      int64_t var = 0;
+      for (int j = 0; j < np; j++) {
+        if (str_col[j] < 0 || ((pnull >> j) & 1u)) continue;
+        const StoredCol& sc = sb.cols[sb.positional ? str_col[j] : sp.cols[str_col[j]].table_ordinal];
+        if (sc.raw_str) { var += ((int64_t)raw_strings[nr++].size() + 7) & ~int64_t(7); continue; }
+        const int64_t code = (int64_t)r[1 + j];
+        if (code == sc.dev.dict_n && code >= 0) continue;   // NULL code
+        if (code < 0 || code >= (int64_t)sc.dict_strings.size()) return set_error(SD_ERR_CUDA, "dictionary code %lld out of range", (long long)code);
+        var += ((int64_t)sc.dict_strings[(size_t)code].size() + 7) & ~int64_t(7);
+      }
+      total += (size_t)(8 + fixed + var);
+    }
+  }
+  out.assign(total, 0);
+  uint8_t* w = out.data();
   for (unsigned long long i = 0; i < count; i++) {
     const uint64_t* r = &recs[(size_t)i * (size_t)(rec / 8)];
     const uint32_t bidx = (uint32_t)(r[0] & 0xffffffffu), pnull = (uint32_t)(r[0] >> 32);
-    if (bidx >= p->exec_batches.size()) return set_error(SD_ERR_CUDA, "corrupt projection record (batch %u)", bidx);
     const StoredBatch& sb = *p->exec_batches[bidx];
+    uint8_t* row = w + 8;
+    int64_t voff = fixed;
     for (int j = 0; j < np; j++) {
-      HVal& v = vals[(size_t)j];
-      v = HVal();
-      if ((pnull >> j) & 1u) { v.isnull = true; continue; }
+      uint8_t* slot = row + bits + 8 * (int64_t)j;
+      if ((pnull >> j) & 1u) { row[j >> 3] |= (uint8_t)(1u << (j & 7)); continue; }
       const uint64_t raw = r[1 + j];
-      if (types[j] == SD_STRING) {
-        const int c = str_col[j];
-        const StoredCol& sc = sb.cols[sb.positional ? c : sp.cols[c].table_ordinal];
-        if (sc.raw_str) { v.s = raw_strings[next_raw++]; continue; }
-        const int64_t code = (int64_t)raw;
-        if (code < 0 || code >= (int64_t)sc.dict_strings.size() || code == sc.dev.dict_n) { if (code == sc.dev.dict_n) v.isnull = true; else return set_error(SD_ERR_CUDA, "dictionary code %lld out of range", (long long)code); }
-        else v.s = sc.dict_strings[(size_t)code];
-      } else if (type_is_fp(types[j])) memcpy(&v.d, &raw, 8);
-      else { v.i = (int64_t)raw; v.w = v.i; }
+      const int t = ft_base(types[j]);
+      if (t == SD_STRING) {
+        const StoredCol& sc = sb.cols[sb.positional ? str_col[j] : sp.cols[str_col[j]].table_ordinal];
+        const std::string* sv;
+        if (sc.raw_str) sv = &raw_strings[next_raw++];
+        else {
+          const int64_t code = (int64_t)raw;
+          if (code == sc.dev.dict_n) { row[j >> 3] |= (uint8_t)(1u << (j & 7)); continue; }
+          sv = &sc.dict_strings[(size_t)code];
+        }
+        const int64_t ol = (voff << 32) | (int64_t)sv->size();
+        memcpy(slot, &ol, 8);
+        memcpy(row + voff, sv->data(), sv->size());
+        voff += ((int64_t)sv->size() + 7) & ~int64_t(7);
+        continue;
+      }
+      switch (t) {
+        case SD_BOOLEAN: slot[0] = raw != 0; break;
+        case SD_BYTE: memcpy(slot, &raw, 1); break;
+        case SD_SHORT: memcpy(slot, &raw, 2); break;
+        case SD_INT: case SD_DATE: memcpy(slot, &raw, 4); break;
+        case SD_FLOAT: { double d; memcpy(&d, &raw, 8); const float f = (float)d; memcpy(slot, &f, 4); break; }
+        default: memcpy(slot, &raw, 8); break;   // LONG, TIMESTAMP, DOUBLE (its bits), DECIMAL(p <= 18)
+      }
     }
-    emit_unsafe_row(out, types, vals);
+    const int64_t sz = voff;
+    memcpy(w, &sz, 8);
+    w += 8 + sz;
   }
   p->finished_nrows = (int64_t)count;
   return 0;

@@ -700,17 +700,31 @@ __device__ __forceinline__ void load_col_staged_nulls(const DevCol& col, SD_CMAS
   const int64_t first = tile_start - n0;
   const uint8_t* base = stage + stage_col_off<PLAN>(C) + ((first * w) & 15);
   regs.nullmask = 0;
+  // nulls before each 64-row word of the tile, computed BY EVERY WARP FOR ITSELF with shuffles (no shared memory, no CTA
+  // barrier: warp-0-only preparation with two barriers per tile kept this path at a quarter of the roofline).  The rows of
+  // a thread lie in word (u * THREADS / 32 + warp) for its row pair u, so a warp needs RPT / 2 of the tile's prefixes.
+  constexpr int TW = TileSmem<PLAN>::TILE_WORDS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w0 = (int)(tile_start >> 6);
+  uint64_t my_word = 0;
+  if (lane < TW && w0 + lane < col.nwords) my_word = col.nulls[w0 + lane];
+  int incl = __popcll(my_word);
+  const int pc = incl;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  const int excl = incl - pc;
 #pragma unroll
   for (int r = 0; r < PLAN::RPT; r++) {
     const int li = row_in_tile(r);
     const int64_t i = tile_start + li;
+    const int wi = (r >> 1) * (THREADS / 32) + warp;                      // == li >> 6
+    const uint64_t word = __shfl_sync(0xffffffffu, my_word, wi);
+    const int before = __shfl_sync(0xffffffffu, excl, wi);
     T v = (T)0;
     bool isnull = false;
     if (i < num_rows) {
-      const int wd = (int)(i >> 6);
-      const uint64_t word = wd < col.nwords ? col.nulls[wd] : 0ull;
       isnull = (word >> (i & 63)) & 1ull;
-      const int64_t k = i - (n0 + sm.wprefix[C][li >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull)));
+      const int64_t k = i - (n0 + before + __popcll(word & ((1ull << (i & 63)) - 1ull)));
       if (!isnull) {
         const uint8_t* p = base + (k - first) * w;
         if (K == K_CODE) v = (T)(w == 2 ? (int)*reinterpret_cast<const int16_t*>(p) : *reinterpret_cast<const int32_t*>(p));
@@ -929,12 +943,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 
       if (fast) {
         if (PLAN::STAGES > 0) {
-          if (with_nulls) {   // per-word null prefix of the tile (warp 0), visible to everyone before the loads
-            consumer_sync();
-            prep_all_general<PLAN>(b, tile_start, sm, ColSeq());
-            consumer_sync();
-          }
-          mbar_wait(&full_bar[c_stage], c_phase);
+          mbar_wait(&full_bar[c_stage], c_phase);   // (the NULL-aware loads derive their word prefixes per warp: no barrier here)
           if (with_nulls) load_all_staged_nulls<PLAN>(b, c16, tile_start, sm, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           else load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           __syncwarp();

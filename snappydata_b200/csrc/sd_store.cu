@@ -675,6 +675,16 @@ int sd_host_alloc(int64_t bytes, void** out) {
   return 0;
 }
 void sd_host_free(void* p) { if (p) cudaFreeHost(p); }
+int sd_host_register(void* p, int64_t bytes) {
+  if (!p || bytes <= 0) return sd::set_error(SD_ERR_INVALID, "sd_host_register: bad arguments");
+  SD_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int sd_host_unregister(void* p) {
+  if (!p) return sd::set_error(SD_ERR_INVALID, "sd_host_unregister: null");
+  SD_CUDA(cudaHostUnregister(p));
+  return 0;
+}
 
 int sd_store_create(int device, int32_t ncols, const sd_column* schema, sd_store** out) {
   if (!out || ncols < 0 || (ncols > 0 && !schema)) return sd::set_error(SD_ERR_INVALID, "sd_store_create: bad arguments");

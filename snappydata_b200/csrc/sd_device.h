@@ -52,7 +52,8 @@ constexpr int MAX_STAGES = 12;
 
 // bytes of TileSmem<PLAN> for a plan with nc scan columns (kept in sync with sd_kernels.cuh)
 constexpr int tile_smem_bytes(int nc, int rpt) {
-  return (THREADS * rpt / 32) * 4 + (nc > 0 ? nc : 1) * ((THREADS * rpt / 32) * 4 + (THREADS * rpt / 64) * 4 + 16) + 8;
+  return (THREADS * rpt / 32) * 4 + (nc > 0 ? nc : 1) * ((THREADS * rpt / 32) * 4 + (THREADS * rpt / 64) * 4 + 16) + 8 +
+         (THREADS / 32) * 4 + (nc > 0 ? nc : 1) * (THREADS / 32) * 2 * 4;   // per-warp cursors of the overlay path
 }
 
 constexpr int MAX_LITERALS = 64;

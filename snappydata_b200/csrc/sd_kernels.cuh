@@ -323,6 +323,10 @@ struct TileSmem {
   int32_t wprefix[PLAN::NC > 0 ? PLAN::NC : 1][TILE_WORDS];
   int32_t drange[PLAN::NC > 0 ? PLAN::NC : 1][4];   // per column: [lo, hi) of delta0 and delta1 positions inside the tile
   int32_t delrange[2];                               // [lo, hi) of the delete positions inside the tile
+  // overlay path: per-warp cursors into the sorted delete / delta positions (a warp's 64-row segments are visited in
+  // ascending order inside a chunk, so every list is walked once, linearly, by each warp on its own -- no CTA barrier)
+  int32_t wdel[THREADS / 32];
+  int32_t wcur[PLAN::NC > 0 ? PLAN::NC : 1][THREADS / 32][2];
 };
 
 // row r of a thread within tile: pair u = r/2 at tile + u*2*THREADS + 2*tid + (r&1)
@@ -404,6 +408,117 @@ __device__ __forceinline__ void load_col_general(const DevCol& col, int tile, in
     regs.v[r] = v;
     regs.nullmask |= (isnull ? 1u : 0u) << r;
   }
+}
+
+// value of entry j of an update delta (null bits index the relative entry, enc/ColumnDeltaDecoder.scala:77-83)
+template <int KIND>
+__device__ __noinline__ typename KindT<KIND>::T delta_value_at(const DevDelta* d, int j, int null_code, bool* out_null) {
+  typedef typename KindT<KIND>::T T;
+  int64_t k = j;
+  bool isnull = false;
+  if (d->nulls) {
+    const int w = j >> 6;
+    const uint64_t word = w < d->nwords ? d->nulls[w] : 0ull;
+    isnull = (word >> (j & 63)) & 1ull;
+    int before = __popcll(word & ((1ull << (j & 63)) - 1ull));
+    for (int x = 0; x < w && x < d->nwords; x++) before += __popcll(d->nulls[x]);
+    k = j - before;
+  }
+  *out_null = isnull;
+  if (!isnull) return decode_delta_value<KIND>(*d, k);
+  return KIND == K_CODE ? (T)null_code : (T)0;
+}
+
+// The entries of the ascending list `pos` that fall into the 64-row segment [a, a + 64), found by one warp on its own:
+// -> bit mask (bit = position - a) and, in *first, the list index of the lowest one; *cur is the warp's cursor into the
+// list (everything below it lies before this warp's previous segments) and is advanced past the segment.  One or two
+// coalesced 32-entry loads, ballots and warp OR-reductions; no shared memory, no barrier.
+__device__ __forceinline__ uint64_t warp_segment_mask(const int32_t* pos, int n, int32_t a, int& cur, int lane, int* first) {
+  for (;;) {   // skip what belongs to other warps' segments
+    const int idx = cur + lane;
+    const int32_t p = idx < n ? __ldg(pos + idx) : 0x7fffffff;
+    const int c = __popc(__ballot_sync(0xffffffffu, p < a));
+    cur += c;
+    if (c < 32) break;
+  }
+  *first = cur;
+  uint64_t mask = 0;
+  for (;;) {
+    const int idx = cur + lane;
+    const int32_t p = idx < n ? __ldg(pos + idx) : 0x7fffffff;
+    const bool in = p < a + 64;
+    const int bit = in ? (int)(p - a) : 0;
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (in && bit < 32) ? (1u << bit) : 0u);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (in && bit >= 32) ? (1u << (bit - 32)) : 0u);
+    mask |= (uint64_t)lo | ((uint64_t)hi << 32);
+    const int c = __popc(__ballot_sync(0xffffffffu, in));
+    cur += c;
+    if (c < 32) break;
+  }
+  return mask;
+}
+__device__ __noinline__ int warp_cursor_init(const int32_t* pos, int n, int32_t a) { return lower_bound_i32(pos, 0, n, a); }
+
+// overlay of one column, per warp: rows whose position is in the depth-0 delta take that value, else the depth-1 delta's
+// (enc/UpdatedColumnDecoder.scala:95-104)
+template <class PLAN, int C>
+__device__ __forceinline__ void warp_overlay_col(const DevCol& col, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, ColRegs<PLAN, C>& regs) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
+  constexpr int K = PLAN::kind(C);
+  const DevDelta *d0 = col.delta0, *d1 = col.delta1;
+  if (!(d0 || d1)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t a0 = (int32_t)tile_start + warp * 64;
+  int cur0 = 0, cur1 = 0;
+  if (first_tile) {
+    if (d0) cur0 = warp_cursor_init(d0->positions, d0->n, a0);
+    if (d1) cur1 = warp_cursor_init(d1->positions, d1->n, a0);
+  } else { cur0 = sm.wcur[C][warp][0]; cur1 = sm.wcur[C][warp][1]; }
+#pragma unroll
+  for (int u = 0; u < PLAN::RPT / 2; u++) {
+    const int32_t a = a0 + u * 2 * THREADS;
+    int f0 = 0, f1 = 0;
+    const uint64_t m0 = d0 ? warp_segment_mask(d0->positions, d0->n, a, cur0, lane, &f0) : 0ull;
+    const uint64_t m1 = d1 ? warp_segment_mask(d1->positions, d1->n, a, cur1, lane, &f1) : 0ull;
+    if ((m0 | m1) == 0ull) continue;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = 2 * u + h, bit = 2 * lane + h;
+      const uint64_t below = (1ull << bit) - 1ull;
+      bool isnull = false;
+      if ((m0 >> bit) & 1ull) {
+        regs.v[r] = delta_value_at<K>(d0, f0 + __popcll(m0 & below), col.dict_n, &isnull);
+        regs.nullmask = (regs.nullmask & ~(1u << r)) | ((isnull ? 1u : 0u) << r);
+      } else if ((m1 >> bit) & 1ull) {
+        regs.v[r] = delta_value_at<K>(d1, f1 + __popcll(m1 & below), col.dict_n, &isnull);
+        regs.nullmask = (regs.nullmask & ~(1u << r)) | ((isnull ? 1u : 0u) << r);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { sm.wcur[C][warp][0] = cur0; sm.wcur[C][warp][1] = cur1; }
+  __syncwarp();
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void warp_overlay_all(const DevBatch<PLAN::NC>& b, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm,
+                                                 AllCols<PLAN, Seq<Cs...>>& regs, uint32_t& live, Seq<Cs...>) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (b.deletes) {   // delete mask (enc/ColumnDeleteDecoder.scala:49-55)
+    const int32_t a0 = (int32_t)tile_start + warp * 64;
+    int cur = first_tile ? warp_cursor_init(b.deletes, b.num_deletes, a0) : sm.wdel[warp];
+#pragma unroll
+    for (int u = 0; u < PLAN::RPT / 2; u++) {
+      int f;
+      const uint64_t m = warp_segment_mask(b.deletes, b.num_deletes, a0 + u * 2 * THREADS, cur, lane, &f);
+      if ((m >> (2 * lane)) & 1ull) live &= ~(1u << (2 * u));
+      if ((m >> (2 * lane + 1)) & 1ull) live &= ~(1u << (2 * u + 1));
+    }
+    __syncwarp();
+    if (lane == 0) sm.wdel[warp] = cur;
+    __syncwarp();
+  }
+  int dummy[] = {0, (warp_overlay_col<PLAN, Cs>(b.cols[Cs], tile_start, first_tile, sm, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
+  (void)dummy;
 }
 
 // fast + overlay path: the base values were loaded by the staged vector path; rows whose bit is set in the tile's
@@ -953,9 +1068,11 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           load_all_fast<PLAN>(b, tile_start, regs, ColSeq());
         }
       }
-      if (PLAN::SLOW_PATHS && (!fast || overlay)) {
-        // per-row decode of the whole tile (!fast), or patch the staged tile's few updated rows (overlay); both
-        // drop the deleted rows
+      if (PLAN::SLOW_PATHS && fast && overlay) {
+        // staged tile + update deltas / delete mask: every warp patches its own rows from its own cursors (no CTA barrier)
+        warp_overlay_all<PLAN>(b, tile_start, tile == tile0, sm, regs, live, ColSeq());
+      } else if (PLAN::SLOW_PATHS && !fast) {
+        // per-row decode of the whole tile; drops the deleted rows
         consumer_sync();                       // previous tile's readers are done with sm
         clear_upd_bits<PLAN>(b, sm, ColSeq());
         if (tid < 32) find_all_ranges<PLAN>(b, tile_start, tile == tile0, sm, tid, ColSeq());
@@ -969,8 +1086,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           }
         }
         consumer_sync();
-        if (fast) overlay_all<PLAN>(b, tile_start, sm, regs, ColSeq());
-        else load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
+        load_all_general<PLAN>(b, tile, tile_start, sm, regs, ColSeq());
         if (b.deletes) {
 #pragma unroll
           for (int r = 0; r < RPT; r++) {

@@ -436,6 +436,16 @@ static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, 
   const uint8_t* cpos = buf + 8 + null_bytes;
   const int n = rd_i32(cpos + 4);
   if (n < 0 || 16 + (int64_t)null_bytes + 4 * (int64_t)n > len) return set_error(SD_ERR_INVALID, "delta positions truncated");
+  // the kernels index shared-memory bitmaps and delta values with these: they must be ascending ordinals of the base batch
+  {
+    const int nbase = rd_i32(cpos);
+    int32_t prev = -1;
+    for (int k = 0; k < n; k++) {
+      const int32_t pos = rd_i32(cpos + 8 + 4 * (int64_t)k);
+      if (pos <= prev || pos < 0 || (nbase > 0 && pos >= nbase)) return set_error(SD_ERR_INVALID, "delta positions must be ascending ordinals below %d (entry %d is %d)", nbase, k, pos);
+      prev = pos;
+    }
+  }
   int64_t data_off = ((8 + null_bytes + 8 + 4 * (int64_t)n + 7) >> 3) << 3;   // round to nearest word
   d = StoredDelta();
   d.present = true;
@@ -471,6 +481,16 @@ static int upload_delta(sd_store* s, const uint8_t* buf, int64_t len, int type, 
     if (type != SD_BOOLEAN) return set_error(SD_ERR_INVALID, "BooleanBitSet delta on a non-boolean column");
   } else return set_error(SD_ERR_UNSUPPORTED, "RunLength-encoded update delta");
   if (body > len) return set_error(SD_ERR_INVALID, "delta values truncated");
+  {   // the value bytes must cover the non-null entries
+    int64_t nulls = 0;
+    for (int wd = 0; wd < (null_bytes >> 3); wd++) nulls += __builtin_popcountll(rd_u64(buf + 8 + 8 * (int64_t)wd));
+    const int64_t nnv = n - nulls;
+    int64_t need = 0;
+    if (type_id == ENC_UNCOMPRESSED) need = nnv * fixed_width_of(type);
+    else if (type_id == ENC_BOOLEAN_BITSET) need = ((nnv + 63) / 64) * 8;
+    else need = nnv * (type_id == ENC_DICTIONARY ? 2 : 4);
+    if (nnv < 0 || body + need > len) return set_error(SD_ERR_INVALID, "delta values truncated: %lld entries need %lld bytes, %lld present", (long long)nnv, (long long)need, (long long)(len - body));
+  }
   rc = upload_bytes(s, buf + body, (size_t)(len - body), 16, 0, &p);
   if (rc) return rc;
   d.dev.data = p;
@@ -641,6 +661,14 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
     }
     if (dlen < 12) return set_error(SD_ERR_INVALID, "delete buffer too short");
     const int n = (int)((dlen - 12) / 4);
+    {   // ascending ordinals below num_rows (the kernels index tile bitmaps with them)
+      int32_t prev = -1;
+      for (int k = 0; k < n; k++) {
+        const int32_t pos = rd_i32(db + 12 + 4 * (int64_t)k);
+        if (pos <= prev || pos >= b->num_rows) return set_error(SD_ERR_INVALID, "delete positions must be ascending ordinals below %d (entry %d is %d)", b->num_rows, k, pos);
+        prev = pos;
+      }
+    }
     uint8_t* p = nullptr;
     int rc = upload_bytes(s, db + 12, 4 * (size_t)n, 16, 0, &p);
     if (rc) return rc;

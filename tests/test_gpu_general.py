@@ -243,6 +243,26 @@ def test_errors_not_fallbacks(gpu_api):
     with pytest.raises(capi.SdError) as e:
         gp.submit(bad)
     assert e.value.code == capi.SD_ERR_INVALID
+    # update-delta / delete positions index shared-memory bitmaps in the kernel: they are validated when the batch is uploaded
+    import struct
+    okcol = encode_uncompressed(np.arange(10, dtype=np.int32), T.INT)
+    bad_del = struct.pack("<iii", 0, 10, 2) + struct.pack("<ii", 7, 3)                     # descending
+    with pytest.raises(capi.SdError) as e:
+        gp.submit(ColumnBatch(num_rows=10, columns=[okcol], delete_mask=bad_del))
+    assert e.value.code == capi.SD_ERR_INVALID
+    bad_del = struct.pack("<iii", 0, 10, 1) + struct.pack("<i", 10)                        # beyond the batch
+    with pytest.raises(capi.SdError) as e:
+        gp.submit(ColumnBatch(num_rows=10, columns=[okcol], delete_mask=bad_del))
+    assert e.value.code == capi.SD_ERR_INVALID
+    good_delta = encode_delta(10, np.array([2, 5], dtype=np.int32), np.array([1, 2], dtype=np.int32), T.INT)
+    bad_delta = bytearray(good_delta)
+    bad_delta[16:24] = struct.pack("<ii", 5, 2)                                             # positions swapped
+    with pytest.raises(capi.SdError) as e:
+        gp.submit(ColumnBatch(num_rows=10, columns=[okcol], delta0={0: bytes(bad_delta)}))
+    assert e.value.code == capi.SD_ERR_INVALID
+    with pytest.raises(capi.SdError) as e:                                                  # values shorter than the entries
+        gp.submit(ColumnBatch(num_rows=10, columns=[okcol], delta0={0: good_delta[:-4]}))
+    assert e.value.code == capi.SD_ERR_INVALID
     # a corrupt Snappy envelope (codec 2) is an error (valid ones are decoded: tests/test_gpu_strings.py); unknown codecs are refused
     snappy_env = (-2).to_bytes(4, "little", signed=True) + (20000).to_bytes(4, "little") + b"\0" * 100
     with pytest.raises(capi.SdError) as e:

@@ -236,9 +236,16 @@ extern "C" int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw
   using namespace sd;
   if (!s || !cols || num_rows < 0) return set_error(SD_ERR_INVALID, "sd_store_encode_batch: bad arguments");
   if (ncols != (int)s->schema.size()) return set_error(SD_ERR_INVALID, "sd_store_encode_batch: %d columns, table schema has %zu", ncols, s->schema.size());
-  std::lock_guard<std::mutex> lock(s->mu);
+  // Scans of the store go on while a batch is being encoded: the store's lock is held only to lay the buffers out in the
+  // arena (phase 2) and to publish the finished batch; everything that touches the rows runs on the encoder's own stream.
+  std::lock_guard<std::mutex> enc_lock(s->enc_mu);
   SD_CUDA(cudaSetDevice(s->device));
-  cudaStream_t st = s->copy_stream;
+  if (!s->enc_stream) {
+    SD_CUDA(cudaStreamCreateWithFlags(&s->enc_stream, cudaStreamNonBlocking));
+    SD_CUDA(cudaEventCreateWithFlags(&s->enc_event, cudaEventDisableTiming));
+  }
+  cudaStream_t st = s->enc_stream;
+  int64_t h2d = 0;
   const int n = num_rows;
   Arena tmp;
   tmp.device = s->device;
@@ -247,7 +254,7 @@ extern "C" int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw
     uint8_t* d = tmp.alloc(bytes + 64, align);
     if (!d) return SD_ERR_CUDA;
     if (bytes) SD_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
-    s->h2d_bytes += (int64_t)bytes;
+    h2d += (int64_t)bytes;
     *out = d;
     return 0;
   };
@@ -332,6 +339,7 @@ extern "C" int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw
   sb->cols.resize(s->schema.size());
   std::vector<EncCol> enc(work.size());
   std::vector<ColStat> stats(s->schema.size());
+  std::unique_lock<std::mutex> store_lock(s->mu);   // phase 2: arena placement + the small side uploads of upload_column
   for (size_t k = 0; k < work.size(); k++) {
     Work& w = work[k];
     const int nn = n - w.fb[0];
@@ -398,6 +406,10 @@ extern "C" int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw
     cs.present = true; cs.type = w.type; cs.nulls = w.fb[0];
     if (w.type != SD_STRING) cs.has = nn > 0;
   }
+  // the side uploads (null words, prefixes of "nulls before") went over the store's copy stream: order the encoder after them
+  SD_CUDA(cudaEventRecord(s->enc_event, s->copy_stream));
+  SD_CUDA(cudaStreamWaitEvent(st, s->enc_event, 0));
+  store_lock.unlock();
   if (!work.empty()) {
     uint8_t* d_enc = tmp.alloc(enc.size() * sizeof(EncCol) + 64, 16);
     uint8_t* h_enc = s->enc_host.alloc(enc.size() * sizeof(EncCol));
@@ -417,8 +429,13 @@ extern "C" int sd_store_encode_batch(sd_store* s, int32_t num_rows, const sd_raw
   }
   sb->stats = stats_row_bytes(n, stats);
   sb->stats_ncols = (int32_t)s->schema.size();
-  s->batches.push_back(std::move(sb));
-  s->version++;
+  SD_CUDA(cudaStreamSynchronize(st));   // bodies written, side uploads done (ordered above): the batch may become visible
+  {
+    std::lock_guard<std::mutex> lock(s->mu);
+    s->batches.push_back(std::move(sb));
+    s->version++;
+    s->h2d_bytes += h2d;
+  }
   s->enc_host.reset();
   return 0;   // `tmp` (the raw values' staging) is released here; everything queued on the stream has completed
 }

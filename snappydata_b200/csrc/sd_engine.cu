@@ -5,7 +5,9 @@
 //   SnappyHashAggregateExec partial output      core/execution/aggregate/SnappyHashAggregateExec.scala:1148-1178
 //   CollectAggregateExec / final merge          core/execution/aggregate/CollectAggregateExec.scala:67-121
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -299,6 +301,10 @@ struct sd_plan {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  // one event pair per launch of an execution: aggTime = the SUM of the launches' device times (host work between two
+  // launches -- descriptor building, waiting for a store's lock -- is not kernel time)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
+  size_t ev_used = 0;
   // private store for sd_batch_submit / sd_rows_submit
   sd_store* priv = nullptr;
   // pending batches
@@ -344,6 +350,8 @@ struct sd_plan {
   // MODE_PROJECT output records + the batches of this execution (records carry a batch ordinal)
   uint8_t* d_out = nullptr;
   int64_t out_cap = 0;
+  uint64_t* h_recs = nullptr;     // page-locked read-back staging of the projection records
+  size_t h_recs_cap = 0;
   unsigned long long* d_out_count = nullptr;
   std::vector<const StoredBatch*> exec_batches;
   std::vector<uint8_t> finished_rows;   // rows of the last sd_plan_finish (re-served when the caller's buffer was too small)
@@ -642,11 +650,26 @@ int ensure_out(sd_plan* p, int64_t cap_records) {
   if (!p->d_out_count) { SD_CUDA(cudaMalloc(&p->d_out_count, 64)); SD_CUDA(cudaMemset(p->d_out_count, 0, 64)); }
   if (cap_records > p->out_cap) {
     if (p->d_out) cudaFree(p->d_out);
+  if (p->h_recs) cudaFreeHost(p->h_recs);
     p->d_out = nullptr;
     SD_CUDA(cudaMalloc(&p->d_out, (size_t)(cap_records * rec)));
     p->out_cap = cap_records;
   }
   return 0;
+}
+
+// device time of this execution's launches (sum over the per-launch event pairs; the span as a fallback)
+static void update_agg_time(sd_plan* p) {
+  if (!p->have_timing) return;
+  float total = 0;
+  bool ok = p->ev_used > 0 && p->ev_used == (size_t)p->metrics[7];
+  for (size_t i = 0; ok && i < p->ev_used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->ev_pairs[i].first, p->ev_pairs[i].second) != cudaSuccess) { ok = false; break; }
+    total += ms;
+  }
+  if (!ok) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) total = ms; else return; }
+  p->agg_ms = total;
 }
 
 // the kernel variant of the plan for this execution / launch
@@ -885,9 +908,18 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     if (p->lits[i].is_null) args.lits.nullmask |= 1ull << i;
   }
   void* kargs[] = {&args};
+  if (p->ev_used == p->ev_pairs.size() && p->ev_pairs.size() < 4096) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    SD_CUDA(cudaEventCreate(&a));
+    SD_CUDA(cudaEventCreate(&b));
+    p->ev_pairs.emplace_back(a, b);
+  }
+  const bool own_pair = p->ev_used < p->ev_pairs.size();
+  if (own_pair) SD_CUDA(cudaEventRecord(p->ev_pairs[p->ev_used].first, p->stream));
   if (!p->have_timing) SD_CUDA(cudaEventRecord(p->ev_start, p->stream));
   { int rc = kernel_launch(*k, grid, smem, p->stream, kargs); if (rc) return rc; }
   SD_CUDA(cudaEventRecord(p->ev_stop, p->stream));
+  if (own_pair) { SD_CUDA(cudaEventRecord(p->ev_pairs[p->ev_used].second, p->stream)); p->ev_used++; }
   p->have_timing = true;
   p->metrics[7]++;
   return 0;
@@ -1085,7 +1117,7 @@ int finish_hash(sd_plan* p) {
     if (rc) { cudaFree(d_keys); cudaFree(d_knull); cudaFree(d_vals); cudaFree(d_cursor); return rc; }
   }
   cudaFree(d_keys); cudaFree(d_knull); cudaFree(d_vals); cudaFree(d_cursor);
-  if (p->have_timing) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms; }
+  update_agg_time(p);
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
@@ -1131,12 +1163,23 @@ int finish_project(sd_plan* p) {
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
     for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
   }
-  std::vector<uint64_t> recs((size_t)count * (size_t)(rec / 8));
+  static const bool dbg = getenv("SD_DEBUG_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { if (dbg) fprintf(stderr, "[finish_project] %s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count()); };
+  // (page-locked staging for the records: a pageable destination makes the driver bounce the copy through its own buffers)
+  const size_t rec_bytes = (size_t)count * (size_t)rec;
+  if (rec_bytes > p->h_recs_cap) {
+    if (p->h_recs) cudaFreeHost(p->h_recs);
+    p->h_recs = nullptr; p->h_recs_cap = 0;
+    SD_CUDA(cudaMallocHost(&p->h_recs, rec_bytes + rec_bytes / 4 + 4096));
+    p->h_recs_cap = rec_bytes + rec_bytes / 4 + 4096;
+  }
+  const uint64_t* recs = p->h_recs;
   unsigned long long counters[2] = {0, 0};
-  if (count) SD_CUDA(cudaMemcpyAsync(recs.data(), p->d_out, (size_t)count * rec, cudaMemcpyDeviceToHost, p->stream));
+  if (count) SD_CUDA(cudaMemcpyAsync(p->h_recs, p->d_out, rec_bytes, cudaMemcpyDeviceToHost, p->stream));
   SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
   SD_CUDA(cudaStreamSynchronize(p->stream));
-  if (p->have_timing) { float ms = 0; if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms; }
+  update_agg_time(p);
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
@@ -1147,6 +1190,7 @@ int finish_project(sd_plan* p) {
     types.push_back(field_type(e.type, e.type == SD_DECIMAL ? decimal_ps(sp, sp.proj[j]) : 0));
     if (e.type == SD_STRING) str_col[j] = e.a;
   }
+  lap("records on the host");
   // strings of raw (variable-width) batches are projected by reference: record = position in the batch's body
   std::vector<int64_t> raw_ptrs;
   for (unsigned long long i = 0; i < count && !str_col.empty(); i++) {
@@ -1195,7 +1239,9 @@ int finish_project(sd_plan* p) {
       total += (size_t)(8 + fixed + var);
     }
   }
+  lap("sizes");
   out.assign(total, 0);
+  lap("zero fill");
   uint8_t* w = out.data();
   for (unsigned long long i = 0; i < count; i++) {
     const uint64_t* r = &recs[(size_t)i * (size_t)(rec / 8)];
@@ -1236,6 +1282,7 @@ int finish_project(sd_plan* p) {
     memcpy(w, &sz, 8);
     w += 8 + sz;
   }
+  lap("rows written");
   p->finished_nrows = (int64_t)count;
   return 0;
 }
@@ -1465,10 +1512,7 @@ static int finish_dense(sd_plan* p) {
   SD_CUDA(cudaStreamSynchronize(p->stream));
   const uint64_t* h = p->h_pinned + STATE_HDR;
   const unsigned long long counters[2] = {p->h_pinned[0], p->h_pinned[1]};
-  if (p->have_timing) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop) == cudaSuccess) p->agg_ms = ms;
-  }
+  update_agg_time(p);
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
@@ -1541,6 +1585,7 @@ int sd_plan_reset(sd_plan* p) {
   p->finished_nrows = -1;
   if (p->d_out_count) SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
   p->have_timing = false;
+  p->ev_used = 0;
   p->agg_ms = 0;
   SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
   memset(p->metrics, 0, sizeof(p->metrics));
@@ -1576,11 +1621,13 @@ void sd_plan_destroy(sd_plan* p) {
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
   if (p->ev_stop) cudaEventDestroy(p->ev_stop);
+  for (auto& e : p->ev_pairs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (p->d_state) cudaFree(p->d_state);
   if (p->h_pinned) cudaFreeHost(p->h_pinned);
   if (p->d_partials) cudaFree(p->d_partials);
   hash_free(p);
   if (p->d_out) cudaFree(p->d_out);
+  if (p->h_recs) cudaFreeHost(p->h_recs);
   if (p->d_out_count) cudaFree(p->d_out_count);
   if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);

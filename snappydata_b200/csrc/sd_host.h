@@ -173,7 +173,10 @@ struct sd_store {
   // compressed payloads of one batch that lie (almost) back to back in host memory travel as ONE copy
   const uint8_t* span_h0 = nullptr; uint8_t* span_d0 = nullptr; size_t span_len = 0;
   sd::PinnedArena lz4_jobs_host;
-  sd::PinnedArena enc_host;        // sd_encode.cu: prefixes / descriptors on their way to the device   // page-locked copies of the job lists (a pageable source would stall the caller per flush)
+  sd::PinnedArena enc_host;        // sd_encode.cu: prefixes / descriptors on their way to the device
+  std::mutex enc_mu;               // one encoder at a time per store; `mu` is taken only to lay the buffers out and to publish
+  cudaStream_t enc_stream = nullptr;
+  cudaEvent_t enc_event = nullptr;   // page-locked copies of the job lists (a pageable source would stall the caller per flush)
 };
 
 namespace sd {

@@ -759,6 +759,8 @@ void sd_store_destroy(sd_store* s) {
     if (s->lz4_done[k]) cudaEventDestroy(s->lz4_done[k]);
   }
   if (s->copies_done) cudaEventDestroy(s->copies_done);
+  if (s->enc_stream) cudaStreamDestroy(s->enc_stream);
+  if (s->enc_event) cudaEventDestroy(s->enc_event);
   delete s;
 }
 

@@ -221,6 +221,8 @@ class Api:
         self.plan_exchange = fn("plan_exchange", C.c_int, vp, vp, required=False)
         self.plan_execute_store = fn("plan_execute_store", C.c_int, vp, vp, C.POINTER(i32), i32, C.POINTER(sd_literal), i32, vp,
                                      vp, i64, C.POINTER(i64), C.POINTER(i64), required=False)
+        self.host_alloc = fn("host_alloc", C.c_int, i64, C.POINTER(vp), required=False)
+        self.host_free = fn("host_free", None, vp, required=False)
         self.plan_export_partials = fn("plan_export_partials", C.c_int, vp, vp, i64, required=False)
         self.plan_import_partials = fn("plan_import_partials", C.c_int, vp, vp, i64, required=False)
 
@@ -390,6 +392,35 @@ class Plan:
             self.api.check(rc)
         return C.string_at(self._out_buf, self._out_len.value)
 
+    def _pinned_out(self, need: int):
+        """Page-locked result buffer owned by this handle (sd_host_alloc): the projected rows of MODE_PROJECT arrive in it by one
+        device->host copy at link speed."""
+        if getattr(self, "_pin_cap", 0) < need:
+            if getattr(self, "_pin_ptr", None):
+                self.api.host_free(self._pin_ptr)
+                self._pin_ptr, self._pin_cap = None, 0
+            ptr = C.c_void_p()
+            cap = int(need) + int(need) // 4 + (1 << 16)
+            self.api.check(self.api.host_alloc(cap, C.byref(ptr)))
+            self._pin_ptr, self._pin_cap = ptr, cap
+        return self._pin_ptr, self._pin_cap
+
+    def execute_store_view(self, store: "Store", lit_array, nlits: int, comm: Optional["Comm"] = None) -> memoryview:
+        """execute_store_raw without the two host copies: the row stream lands in this handle's page-locked buffer and comes
+        back as a memoryview of it (valid until the next execution on this handle)."""
+        if getattr(self, "_out_len", None) is None:
+            self._out_len, self._out_rows = C.c_int64(), C.c_int64()
+        ptr, cap = self._pinned_out(1 << 20)
+        rc = self.api.plan_execute_store(self.h, store.h, None, 0, lit_array, nlits, comm.h if comm is not None else None,
+                                         ptr, cap, C.byref(self._out_len), C.byref(self._out_rows))
+        if rc == SD_ERR_OVERFLOW:   # the execution is complete; only the buffer was too small
+            ptr, cap = self._pinned_out(int(self._out_len.value) + 64)
+            rc = self.api.plan_finish(self.h, ptr, cap, C.byref(self._out_len), C.byref(self._out_rows))
+        if rc:
+            self.api.check(rc)
+        n = int(self._out_len.value)
+        return memoryview((C.c_char * max(n, 1)).from_address(ptr.value)).cast("B")[:n]
+
     def exchange(self, comm: "Comm"):
         self.api.check(self.api.plan_exchange(self.h, comm.h))
         return self
@@ -474,6 +505,9 @@ class Plan:
         if self.h:
             self.api.plan_destroy(self.h)
             self.h = None
+        if getattr(self, "_pin_ptr", None):
+            self.api.host_free(self._pin_ptr)
+            self._pin_ptr, self._pin_cap = None, 0
 
     def __del__(self):
         try:

@@ -352,6 +352,8 @@ struct sd_plan {
   int64_t out_cap = 0;
   uint64_t* h_recs = nullptr;     // page-locked read-back staging of the projection records
   size_t h_recs_cap = 0;
+  RowWriterBuffers roww;          // device row writer (sd_rows.cu): offsets, rows, string-source tables
+  int64_t dev_rows_len = -1;      // >= 0: the finished rows of this execution are roww.d_rows[0, dev_rows_len) (not finished_rows)
   unsigned long long* d_out_count = nullptr;
   std::vector<const StoredBatch*> exec_batches;
   std::vector<uint8_t> finished_rows;   // rows of the last sd_plan_finish (re-served when the caller's buffer was too small)
@@ -651,6 +653,7 @@ int ensure_out(sd_plan* p, int64_t cap_records) {
   if (cap_records > p->out_cap) {
     if (p->d_out) cudaFree(p->d_out);
   if (p->h_recs) cudaFreeHost(p->h_recs);
+  p->roww.release();
     p->d_out = nullptr;
     SD_CUDA(cudaMalloc(&p->d_out, (size_t)(cap_records * rec)));
     p->out_cap = cap_records;
@@ -753,6 +756,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     if (blist) p->exec_batches.insert(p->exec_batches.end(), blist->begin(), blist->end());
   }
   p->finished_nrows = -1;
+  p->dev_rows_len = -1;
   if (nbatches == 0 || total_chunks == 0) return 0;
   const PlanSpec& sp = p->spec;
   const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
@@ -806,6 +810,18 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     if (tile_smem + priv + min_ring <= budget1) { table_mode = TABLE_PRIVATE; table_bytes = priv; }
     else if (shared <= 64 * 1024 && tile_smem + shared + min_ring <= budget1) { table_mode = TABLE_SHARED_ATOMIC; table_bytes = shared; }
     else { table_mode = TABLE_GLOBAL_ATOMIC; table_bytes = 64; }
+  }
+  int hash_smem_cap = 0;
+  if (sp.mode == MODE_HASH && !getenv("SD_TUNE_NO_FRONT_TABLE")) {
+    // per-CTA shared-memory front table (sd_kernels.cuh: FrontTable): the largest power of two that leaves the ring >= 3 stages,
+    // with one CTA per SM so that the table gets most of the SM's shared memory
+    target_ctas = 1;
+    const size_t entry = 8 + 8 * (size_t)std::max(nk, 1) + 8 * (size_t)std::max(ns, 1);
+    const size_t ring_need = k->staged ? ring_fixed + 3 * k->stage_bytes + 256 : 0;
+    const size_t room = (size_t)p->smem_optin > tile_smem + ring_need + 1024 ? (size_t)p->smem_optin - tile_smem - ring_need - 1024 : 0;
+    size_t cap = 8192;
+    while (cap >= 256 && cap * entry + 16 > std::min<size_t>(room, size_t(144) << 10)) cap >>= 1;
+    if (cap >= 256) { hash_smem_cap = (int)cap; table_bytes = cap * entry + 16; }
   }
   const size_t budget = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
   size_t ring_off = (tile_smem + table_bytes + 127) & ~size_t(127);
@@ -879,6 +895,7 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.batch_base = batch_base;
   args.chunk_rows = p->chunk_rows;
   args.fresh = fresh;
+  args.hash_smem_cap = hash_smem_cap;
   memcpy(args.radix, radix, sizeof(radix));
   if (p->litpool_dirty) {   // STRING literal bytes -> device (once per set of literal values)
     std::vector<uint8_t> pool;
@@ -1146,6 +1163,103 @@ int finish_hash(sd_plan* p) {
 }
 
 // MODE_PROJECT: grow + replay when the record buffer was too small, then records -> UnsafeRows
+// The projected rows built by the GPU (sd_rows.cu).  *done = false: this execution needs the host writer below (more than 32
+// fields, or a projected STRING column whose dictionary has entries that exist only on the host: values brought by an update
+// delta).
+static int project_rows_on_device(sd_plan* p, unsigned long long count, bool* done) {
+  *done = false;
+  const bool off = getenv("SD_TUNE_HOST_ROWS") != nullptr;   // (tests compare the two writers byte for byte)
+  const PlanSpec& sp = p->spec;
+  const int np = (int)sp.proj.size();
+  if (off || np > ROW_MAX_FIELDS || count >= (1ull << 31) - 2) return 0;
+  uint8_t kinds[ROW_MAX_FIELDS];
+  std::vector<int> str_cols;
+  for (int j = 0; j < np; j++) {
+    const sd_expr& e = sp.exprs[sp.proj[j]];
+    switch (e.type) {
+      case SD_BOOLEAN: kinds[j] = ROW_KIND_BOOL; break;
+      case SD_BYTE: kinds[j] = ROW_KIND_1; break;
+      case SD_SHORT: kinds[j] = ROW_KIND_2; break;
+      case SD_INT: case SD_DATE: kinds[j] = ROW_KIND_4; break;
+      case SD_FLOAT: kinds[j] = ROW_KIND_FLOAT; break;
+      case SD_STRING: kinds[j] = ROW_KIND_STRING; str_cols.push_back(e.a); break;
+      default: kinds[j] = ROW_KIND_8; break;
+    }
+  }
+  RowWriterBuffers& b = p->roww;
+  const int ns = (int)str_cols.size(), nb = (int)p->exec_batches.size();
+  if (ns > 0) {
+    std::vector<const void*> key;
+    key.reserve((size_t)nb + 1);
+    key.push_back(reinterpret_cast<const void*>((uintptr_t)ns));
+    for (const StoredBatch* sb : p->exec_batches) key.push_back(reinterpret_cast<const void*>((uintptr_t)sb->uid));
+    if (key != b.src_key || !b.d_src) {
+      b.src_key.clear();
+      std::vector<RowStrSrc> src((size_t)nb * ns);
+      std::vector<int32_t> recoff;
+      std::vector<size_t> first((size_t)nb * ns, SIZE_MAX);
+      for (int bi = 0; bi < nb; bi++) {
+        const StoredBatch& sb = *p->exec_batches[bi];
+        for (int k = 0; k < ns; k++) {
+          const StoredCol& sc = sb.cols[sb.positional ? str_cols[k] : sp.cols[str_cols[k]].table_ordinal];
+          RowStrSrc& r = src[(size_t)bi * ns + k];
+          if (sc.raw_str) { r = RowStrSrc{sc.dev.dict, nullptr, -1, 0}; continue; }
+          if (sc.dict_rec_off.size() != sc.dict_strings.size() || !sc.dev_base) return 0;   // host-only dictionary entries
+          first[(size_t)bi * ns + k] = recoff.size();
+          for (int64_t o : sc.dict_rec_off) {
+            if (o < 0 || o > INT32_MAX) return 0;
+            recoff.push_back((int32_t)o);
+          }
+          r = RowStrSrc{sc.dev_base, nullptr, sc.dev.dict_n, (int32_t)sc.dict_strings.size()};
+        }
+      }
+      if (recoff.size() * 4 > b.recoff_cap) {
+        if (b.d_recoff) cudaFree(b.d_recoff);
+        b.d_recoff = nullptr; b.recoff_cap = 0;
+        SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.d_recoff), recoff.size() * 4 + 4096));
+        b.recoff_cap = recoff.size() * 4 + 4096;
+      }
+      if (src.size() * sizeof(RowStrSrc) > b.src_cap) {
+        if (b.d_src) cudaFree(b.d_src);
+        b.d_src = nullptr; b.src_cap = 0;
+        SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.d_src), src.size() * sizeof(RowStrSrc) + 4096));
+        b.src_cap = src.size() * sizeof(RowStrSrc) + 4096;
+      }
+      for (size_t i = 0; i < src.size(); i++) if (first[i] != SIZE_MAX) src[i].rec_off = b.d_recoff + first[i];
+      // (pageable sources: both copies are staged by the driver before the calls return)
+      if (!recoff.empty()) SD_CUDA(cudaMemcpyAsync(b.d_recoff, recoff.data(), recoff.size() * 4, cudaMemcpyHostToDevice, p->stream));
+      SD_CUDA(cudaMemcpyAsync(b.d_src, src.data(), src.size() * sizeof(RowStrSrc), cudaMemcpyHostToDevice, p->stream));
+      SD_CUDA(cudaStreamSynchronize(p->stream));
+      b.src_key.swap(key);
+    }
+  }
+  int64_t total = 0;
+  int rc = device_write_rows(p->stream, reinterpret_cast<const uint64_t*>(p->d_out), (int64_t)count, np, kinds, nb, b, &total);
+  if (rc) return rc;
+  unsigned long long counters[2] = {0, 0};
+  SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  update_agg_time(p);
+  p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
+  p->metrics[8] = (int64_t)counters[0];
+  p->metrics[11] = (int64_t)counters[0];
+  p->finished_rows.clear();
+  p->dev_rows_len = total;
+  p->finished_nrows = (int64_t)count;
+  *done = true;
+  return 0;
+}
+
+// rows of this execution on the host (callers that post-process them: the exchange, the partial merge)
+static int rows_to_host(sd_plan* p) {
+  if (p->dev_rows_len < 0) return 0;
+  p->finished_rows.resize((size_t)p->dev_rows_len);
+  if (p->dev_rows_len) SD_CUDA(cudaMemcpyAsync(p->finished_rows.data(), p->roww.d_rows, (size_t)p->dev_rows_len, cudaMemcpyDeviceToHost, p->stream));
+  SD_CUDA(cudaStreamSynchronize(p->stream));
+  p->dev_rows_len = -1;
+  return 0;
+}
+
 int finish_project(sd_plan* p) {
   const PlanSpec& sp = p->spec;
   const int np = (int)sp.proj.size();
@@ -1162,6 +1276,11 @@ int finish_project(sd_plan* p) {
     SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
     SD_CUDA(cudaMemsetAsync(p->d_counters, 0, 64, p->stream));
     for (auto& l : p->launch_log) { rc = launch_scan(p, l.d_batches, l.d_prefix, l.nbatches, l.total_chunks, l.needs_slow, nullptr, l.batch_base); if (rc) return rc; }
+  }
+  {
+    bool done = false;
+    rc = project_rows_on_device(p, count, &done);
+    if (rc || done) return rc;
   }
   static const bool dbg = getenv("SD_DEBUG_TIMING") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1565,6 +1684,14 @@ int sd_plan_finish(sd_plan* p, void* out_rows, int64_t cap, int64_t* out_len, in
   if (!p || !out_len) return set_error(SD_ERR_INVALID, "sd_plan_finish: null argument");
   int rc = collect_partial_rows(p);
   if (rc) return rc;
+  if (p->dev_rows_len >= 0) {   // projected rows written by the GPU: one copy, straight into the caller's buffer
+    *out_len = p->dev_rows_len;
+    if (out_nrows) *out_nrows = p->finished_nrows;
+    if (p->dev_rows_len > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %lld bytes", (long long)p->dev_rows_len);
+    if (p->dev_rows_len) SD_CUDA(cudaMemcpyAsync(out_rows, p->roww.d_rows, (size_t)p->dev_rows_len, cudaMemcpyDeviceToHost, p->stream));
+    SD_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+  }
   *out_len = (int64_t)p->finished_rows.size();
   if (out_nrows) *out_nrows = p->finished_nrows;
   if ((int64_t)p->finished_rows.size() > cap) return set_error(SD_ERR_OVERFLOW, "sd_plan_finish: output needs %zu bytes", p->finished_rows.size());
@@ -1583,6 +1710,7 @@ int sd_plan_reset(sd_plan* p) {
   p->launch_log.clear();
   p->exec_batches.clear();
   p->finished_nrows = -1;
+  p->dev_rows_len = -1;
   if (p->d_out_count) SD_CUDA(cudaMemsetAsync(p->d_out_count, 0, 8, p->stream));
   p->have_timing = false;
   p->ev_used = 0;
@@ -1661,6 +1789,7 @@ int sd_plan_import_partials(sd_plan* p, const void* dev_in, int64_t bytes) {
   if (!p || !dev_in) return set_error(SD_ERR_INVALID, "null argument");
   if (p->spec.mode == MODE_HASH || p->spec.mode == MODE_PROJECT) return set_error(SD_ERR_UNSUPPORTED, "dense partials exist only for no-key / dictionary-keyed plans");
   p->finished_nrows = -1;
+  p->dev_rows_len = -1;
   SD_CUDA(cudaSetDevice(p->device));
   const size_t want = (size_t)p->ngroups * p->spec.slots.size() * 8;
   if ((size_t)bytes != want) return set_error(SD_ERR_INVALID, "import expects %zu bytes", want);
@@ -1973,6 +2102,8 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   if (!p || !c) return set_error(SD_ERR_INVALID, "sd_plan_exchange: null argument");
   if (c->device != p->device) return set_error(SD_ERR_INVALID, "communicator lives on device %d, plan on %d", c->device, p->device);
   int rc = collect_partial_rows(p);
+  if (rc) return rc;
+  rc = rows_to_host(p);
   if (rc) return rc;
   const std::vector<uint8_t>& mine = p->finished_rows;
   for (;;) {

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <mutex>
@@ -55,6 +56,29 @@ int hash_table_compact(cudaStream_t stream, const HashTable& t, uint32_t capacit
                        uint32_t* out_knull, uint64_t* out_vals, uint32_t* d_cursor);
 // strings held by reference -> host: d_recs[i * stride] = device address of a [len:int32][bytes] record (0: none)
 int fetch_string_records(cudaStream_t stream, const int64_t* d_recs, int64_t n, int64_t stride, std::vector<std::string>& out);
+
+// ---- sd_rows.cu: projection records -> UnsafeRows on the device -------------------------------------------------------------
+constexpr int ROW_MAX_FIELDS = 32;   // one lane per field; the record's null bits are 32 wide
+enum { ROW_KIND_8 = 0, ROW_KIND_BOOL = 1, ROW_KIND_1 = 2, ROW_KIND_2 = 3, ROW_KIND_4 = 4, ROW_KIND_FLOAT = 5, ROW_KIND_STRING = 6 };
+// where the strings of one projected STRING column of one batch live on the device
+struct RowStrSrc {
+  const uint8_t* base;        // dictionary: the column's uploaded buffer; raw strings: its [len][bytes] body
+  const int32_t* rec_off;     // dictionary: offset of each code's [len][bytes] record from base; nullptr: raw (the value IS the offset)
+  int32_t null_code;          // dictionary code that stands for NULL (-1: none)
+  int32_t n;                  // dictionary entries
+};
+struct RowWriterBuffers {
+  int64_t* d_offs = nullptr; size_t offs_cap = 0;
+  void* d_tmp = nullptr; size_t tmp_cap = 0;
+  uint8_t* d_rows = nullptr; size_t rows_cap = 0;
+  int32_t* d_err = nullptr;
+  RowStrSrc* d_src = nullptr; size_t src_cap = 0;       // [batches of the execution][string fields]
+  int32_t* d_recoff = nullptr; size_t recoff_cap = 0;   // the rec_off tables, back to back
+  std::vector<const void*> src_key;                       // the batches d_src / d_recoff were built for
+  void release();
+};
+int device_write_rows(cudaStream_t st, const uint64_t* d_recs, int64_t count, int np, const uint8_t* kinds, int nbatches,
+                      RowWriterBuffers& b, int64_t* total_out);
 
 // ---- on-device LZ4 (sd_lz4.cu) ---------------------------------------------------------------------------
 struct Lz4Job { const uint8_t* src; uint8_t* dst; int64_t src_len; int64_t dst_len; };
@@ -123,7 +147,9 @@ struct StoredCol {
   bool fast = false;                      // vector fast path applies
 };
 
+inline uint64_t next_batch_uid() { static std::atomic<uint64_t> n{1}; return n.fetch_add(1, std::memory_order_relaxed); }
 struct StoredBatch {
+  uint64_t uid = next_batch_uid();        // never reused (an address can be): key of per-plan caches built from a batch
   int32_t num_rows = 0;
   int32_t bucket_id = 0;
   int64_t batch_id = 0;

@@ -196,6 +196,63 @@ __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const
   return -1;
 }
 
+// ---- MODE_HASH front table: a small open-addressing table per CTA in SHARED memory.  A group-by with few thousand groups
+// otherwise sends every row to the same few global-memory lines (probe + NSLOT atomics that bounce between SMs: 200 GB/s in
+// profiles/r02_modes_ncu.txt); here the rows of a CTA meet in its own shared memory and the CTA merges its table into the
+// global one once, at the end.  Layout: [state u32 x cap][knull u32 x cap][keys i64 x cap*NK][vals u64 x cap*NSLOT][count u32].
+// When the table is 3/4 full the CTA stops inserting into it (high-cardinality keys go straight to the global table).
+template <int NK, int NSLOT>
+struct FrontTable {
+  uint32_t* state; uint32_t* knull; int64_t* keys; uint64_t* vals; uint32_t* count; uint32_t cap;
+  __device__ __forceinline__ void bind(uint8_t* base, uint32_t c) {
+    cap = c;
+    state = reinterpret_cast<uint32_t*>(base);
+    knull = state + c;
+    keys = reinterpret_cast<int64_t*>(knull + c);
+    vals = reinterpret_cast<uint64_t*>(keys + (size_t)c * NK);
+    count = reinterpret_cast<uint32_t*>(vals + (size_t)c * NSLOT);
+  }
+  static __host__ __device__ constexpr size_t bytes(size_t c) { return c * (8 + 8 * (size_t)NK + 8 * (size_t)NSLOT) + 16; }
+};
+template <int NK, int NSLOT, uint32_t STRMASK>
+__device__ __forceinline__ int front_find_or_insert(const FrontTable<NK, NSLOT>& t, const int64_t* kc, uint32_t knull) {
+  uint64_t h = 0x2545f4914f6cdd1dull ^ knull;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    if ((STRMASK >> k) & 1u) h = hash_mix64(h, kc[k] ? str_hash_rec(reinterpret_cast<const uint8_t*>(kc[k])) : 0ull);
+    else h = hash_mix64(h, (uint64_t)kc[k]);
+  }
+  const uint32_t mask = t.cap - 1u;
+  uint32_t pos = (uint32_t)(h >> 20) & mask;   // (other bits than the global table's: no correlated clustering)
+  for (int probe = 0; probe < 16; probe++, pos = (pos + 1u) & mask) {
+    uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);
+    if (st == 0u) {
+      if (*reinterpret_cast<volatile uint32_t*>(t.count) >= t.cap - (t.cap >> 2)) return -1;   // 3/4 full: the caller goes global
+      st = atomicCAS(&t.state[pos], 0u, 1u);
+      if (st == 0u) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) t.keys[(size_t)pos * NK + k] = kc[k];
+        t.knull[pos] = knull;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&t.state[pos]) = 2u;
+        atomicAdd(t.count, 1u);
+        return (int)pos;
+      }
+    }
+    while (st == 1u) st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);   // writer (same CTA) in flight
+    __threadfence_block();
+    bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const int64_t have = *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]);
+      if ((STRMASK >> k) & 1u) same = same && (have == kc[k] || (have && kc[k] && str_eq_recs(reinterpret_cast<const uint8_t*>(have), reinterpret_cast<const uint8_t*>(kc[k]))));
+      else same = same && have == kc[k];
+    }
+    if (same) return (int)pos;
+  }
+  return -1;
+}
+
 // ---- loads ------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T ld_at(const uint8_t* base, int64_t k) {
   return *reinterpret_cast<const T*>(base + k * (int64_t)sizeof(T));
@@ -1012,6 +1069,16 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   } else if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
+  } else if (PLAN::MODE == MODE_HASH && args.hash_smem_cap > 0) {
+    FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
+    ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
+    for (uint32_t e = tid; e < ft.cap; e += THREADS) {
+      ft.state[e] = 0u;
+#pragma unroll
+      for (int s2 = 0; s2 < NSLOT; s2++) ft.vals[(size_t)e * NSLOT + s2] = slot_identity(PLAN::slot_op(s2));
+    }
+    if (tid == 0) *ft.count = 0u;
+    consumer_sync();
   } else if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
     // nothing per CTA: the table / output buffer is global
   } else if (args.table_mode == TABLE_PRIVATE) {
@@ -1150,6 +1217,17 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
             int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
             uint32_t knull = 0;
             PLAN::keys(row, ctx, kc, knull);
+            if (args.hash_smem_cap > 0) {   // the CTA's own shared-memory table first
+              FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
+              ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
+              const int fe = front_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1), PLAN::STRKEYMASK>(ft, kc, knull);
+              if (fe >= 0) {
+                uint64_t* t = ft.vals + (size_t)fe * NSLOT;
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) slot_atomic(PLAN::slot_op(s), t + s, sv[s]);
+                continue;
+              }
+            }
             const int64_t e = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), PLAN::STRKEYMASK>(args.hash, kc, knull);
             if (e >= 0) {
               uint64_t* t = args.hash.vals + (size_t)e * NSLOT;
@@ -1187,7 +1265,26 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
   const int lane = tid & 31, warp = tid >> 5;
-  if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
+  if (PLAN::MODE == MODE_HASH && args.hash_smem_cap > 0) {
+    // the CTA's front table -> the global table (one find-or-insert + NSLOT atomics per group this CTA has seen)
+    FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
+    ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
+    for (uint32_t e = tid; e < ft.cap; e += THREADS) {
+      if (ft.state[e] != 2u) continue;
+      int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
+#pragma unroll
+      for (int k = 0; k < (PLAN::NKEYS > 0 ? PLAN::NKEYS : 1); k++) kc[k] = ft.keys[(size_t)e * (PLAN::NKEYS > 0 ? PLAN::NKEYS : 1) + k];
+      const int64_t g = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), PLAN::STRKEYMASK>(args.hash, kc, ft.knull[e]);
+      if (g >= 0) {
+        uint64_t* t = args.hash.vals + (size_t)g * NSLOT;
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+          const uint64_t v = ft.vals[(size_t)e * NSLOT + s];
+          if (v != slot_identity(PLAN::slot_op(s))) slot_atomic(PLAN::slot_op(s), t + s, v);
+        }
+      }
+    }
+  } else if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
     // results live in the global hash table / the output record buffer
   } else if (PLAN::MODE == MODE_NOKEY) {
     uint64_t* scratch = table;   // [NSLOT][THREADS/32]

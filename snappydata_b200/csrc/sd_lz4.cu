@@ -202,56 +202,25 @@ __device__ __forceinline__ void lz_flush(const uint8_t* win, uint8_t* dst_al, ui
   flushed = lim;
 }
 
-// 8 bytes at any alignment out of a power-of-two byte ring (two aligned 64-bit loads and a funnel shift instead of eight
-// byte loads: the byte-wise copies were 46 % of the kernel's instructions, profiles/r02_lz4_ncu.txt)
-template <uint32_t MASK>
-__device__ __forceinline__ uint64_t ring_load8(const uint8_t* ring, uint32_t a) {
-  const uint32_t sh = (a & 7u) * 8u;
-  const uint64_t lo = *reinterpret_cast<const uint64_t*>(ring + (a & MASK & ~7u));
-  if (sh == 0u) return lo;
-  const uint64_t hi = *reinterpret_cast<const uint64_t*>(ring + ((a + 8u) & MASK & ~7u));
-  return (lo >> sh) | (hi << (64u - sh));
-}
-// the low `nbytes` (1..8) bytes of v to ring position d: one or two wide stores when d is aligned, byte stores otherwise
-template <uint32_t MASK>
-__device__ __forceinline__ void ring_store(uint8_t* ring, uint32_t d, uint64_t v, uint32_t nbytes) {
-  if (nbytes == 8u && (d & 7u) == 0u) { *reinterpret_cast<uint64_t*>(ring + (d & MASK)) = v; return; }
-  if (nbytes == 8u && (d & 3u) == 0u) {
-    *reinterpret_cast<uint32_t*>(ring + (d & MASK)) = (uint32_t)v;
-    *reinterpret_cast<uint32_t*>(ring + ((d + 4u) & MASK)) = (uint32_t)(v >> 32);
-    return;
-  }
-  for (uint32_t k = 0; k < nbytes; k++) ring[(d + k) & MASK] = (uint8_t)(v >> (8u * k));
-}
-
 // one lane copies its own match of <= LZ_MAX_ML bytes into the ring
 template <class CFG>
 __device__ __forceinline__ void lz_lane_match(uint8_t* win, const uint8_t* dst_al, uint32_t mdst, uint32_t msrc, uint32_t ml, uint32_t off, bool near) {
-  if (near && off >= 8u) {   // 8 source bytes never overlap the 8 bytes they produce
-    uint32_t q = 0;
-    for (; q + 8u <= ml; q += 8u) ring_store<CFG::M>(win, mdst + q, ring_load8<CFG::M>(win, msrc + q), 8u);
-    if (q < ml) ring_store<CFG::M>(win, mdst + q, ring_load8<CFG::M>(win, msrc + q), ml - q);
-    return;
-  }
-  if (near && (off == 1u || off == 2u || off == 4u)) {   // run of a 1 / 2 / 4-byte pattern (dictionary codes, repeated ints): the
-    uint64_t pat = ring_load8<CFG::M>(win, msrc);         // pattern's period divides 8, so every 8-byte chunk is the same word
-    if (off == 1u) pat = (pat & 0xffull) * 0x0101010101010101ull;
-    else if (off == 2u) { pat &= 0xffffull; pat |= pat << 16; pat |= pat << 32; }
-    else { pat &= 0xffffffffull; pat |= pat << 32; }
-    for (uint32_t q = 0; q < ml; q += 8u) ring_store<CFG::M>(win, mdst + q, pat, ml - q < 8u ? ml - q : 8u);
-    return;
-  }
   uint32_t q = 0;
-  if (off >= 8u) {   // source no longer in the ring: it was flushed long ago, read it back from HBM / L2
-    for (; q + 8u <= ml; q += 8u) {
+  if (off >= 8) {   // 8 source bytes never overlap the 8 bytes they produce: fetch them all, then store
+    for (; q + 8 <= ml; q += 8) {
       uint8_t t[8];
+      if (near) {
 #pragma unroll
-      for (int u = 0; u < 8; u++) t[u] = __ldcg(dst_al + msrc + q + u);
+        for (int u = 0; u < 8; u++) t[u] = win[(msrc + q + u) & CFG::M];
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(dst_al + msrc + q + u);
+      }
 #pragma unroll
       for (int u = 0; u < 8; u++) win[(mdst + q + u) & CFG::M] = t[u];
     }
   }
-  for (; q < ml; q++) {   // tail, or a match that overlaps its own output with an odd period: byte by byte, in order
+  for (; q < ml; q++) {   // tail, or a match that overlaps its own output (offset < 8): byte by byte, in order
     const uint8_t v = near ? win[(msrc + q) & CFG::M] : __ldcg(dst_al + msrc + q);
     win[(mdst + q) & CFG::M] = v;
   }
@@ -426,7 +395,7 @@ __global__ void __launch_bounds__(CFG::WARPS * 32) lz4_decode_kernel(const Lz4Jo
       const uint32_t group_end = o;
       if (lane < n) {
         const uint32_t p0 = my_mdst - my_lit;
-        if (my_staged) { for (uint32_t k = 0; k < my_lit; k += 8u) ring_store<CFG::M>(win, p0 + k, ring_load8<CFG::IM>(in, my_lit_src + k), my_lit - k < 8u ? my_lit - k : 8u); }
+        if (my_staged) { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & CFG::M] = in[(my_lit_src + k) & CFG::IM]; }
         else { for (uint32_t k = 0; k < my_lit; k++) win[(p0 + k) & CFG::M] = __ldg(src + my_lit_src + k); }
       }
       __syncwarp();

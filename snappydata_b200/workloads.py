@@ -105,7 +105,7 @@ def run_c4(api, torch, dist, rank, world, device, steps, warmup, peak):
     lit_arr = gp.literal_array(C4_LITS)
 
     def step():
-        raw = gp.execute_store_raw(store, lit_arr, len(C4_LITS), None)
+        raw = gp.execute_store_view(store, lit_arr, len(C4_LITS), None)   # rows in the handle's page-locked buffer
         return len(raw)
     for _ in range(warmup):
         step()
@@ -143,8 +143,8 @@ def run_c4(api, torch, dist, rank, world, device, steps, warmup, peak):
                          "note": "per rank; algorithmic bytes = column bodies + null words read (SURVEY.md 8d: ~39.1 B/row) + 72-byte output records written"},
             "parity_check": {"ok": bool(ok), "sample_rows_vs_oracle": len(want), "sample_equal": bool(rows_equal), "rows_out": out_rows,
                              "rows_out_expected": exp_rows, "checker": "oracle row-for-row on two batches; whole-shard row count against a numpy evaluation of the predicate"},
-            "note": f"10 M distinct rows generated in {gen_s:.1f} s on the host, each batch resident 10x under distinct ids; whole step includes the "
-                    "read-back of the projected records and their conversion to UnsafeRows on the host; c2 skewed so that 1 % is reachable"}
+            "note": f"10 M distinct rows generated in {gen_s:.1f} s on the host, each batch resident 10x under distinct ids; whole step includes writing the "
+                    "projected UnsafeRows on the device (sd_rows.cu) and their copy into a page-locked host buffer; c2 skewed so that 1 % is reachable"}
 
 
 # ---- C5 ------------------------------------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ class FakePlan:
     def finish_raw(self): return b""
     def literal_array(self, vals): return None
     def execute_store_raw(self, store, lit_array, nlits, comm=None): return b""
+    def execute_store_view(self, store, lit_array, nlits, comm=None): return memoryview(b"")
     def exchange(self, comm): return self
     def metrics(self): return {"kernelLaunches": 1, "aggTimeNs": 3_500_000, "algorithmicBytes": 24_000_000_000}
     def final_merge_raw(self, raw): return b""

@@ -408,6 +408,34 @@ def test_high_cardinality_group_by_grows_the_hash_table(gpu_api):
     assert_rowsets_match(gp.finish(), got, 1)
 
 
+@pytest.mark.parametrize("front", [True, False])
+@pytest.mark.parametrize("ngroups", [300, 7000])
+def test_hash_group_by_front_table_on_and_off(gpu_api, ngroups, front, monkeypatch):
+    """MODE_HASH with the per-CTA shared-memory front table (sd_kernels.cuh FrontTable) and without it: fewer groups than the
+    front table holds (every row meets in shared memory) and more (the table fills, later keys go to the global table and the
+    same key can live in both until the end-of-kernel merge).  Nullable key, every kind of slot."""
+    if front:
+        monkeypatch.delenv("SD_TUNE_NO_FRONT_TABLE", raising=False)
+    else:
+        monkeypatch.setenv("SD_TUNE_NO_FRONT_TABLE", "1")
+    r = np.random.default_rng(ngroups)
+    n = 150_000
+    schema = [("k", T.INT, True), ("k2", T.LONG, False), ("v", T.DOUBLE, True), ("w", T.INT, False)]
+    bs = []
+    for i in range(2):
+        kk = r.integers(0, ngroups, n).astype(np.int32)
+        v = r.normal(0, 5, n)
+        v[r.integers(0, n, 5)] = np.nan
+        data = {"k": kk, "k2": (kk % 3).astype(np.int64) - 1, "v": v, "w": r.integers(-50, 50, n).astype(np.int32)}
+        bs.append(build_batch(n, schema, data, {"k": r.random(n) < 0.02, "v": r.random(n) < 0.1}, batch_id=i))
+    b = PlanBuilder()
+    k, k2, v, w = b.col(T.INT, 0, True), b.col(T.LONG, 1, False), b.col(T.DOUBLE, 2, True), b.col(T.INT, 3, False)
+    b.group_by(k, k2)
+    b.count().sum(v).avg(w).min(v).max(v).min(w).max(w).count(v)
+    gp, _, got = both(gpu_api, b.build(), [], bs, 2)
+    assert len(got) >= ngroups
+
+
 # ---- MODE_PROJECT: filter + project, no aggregate (BASELINE.json configs[3], SURVEY.md 8d C4) -----------
 def _rowkey(r):
     return tuple((0, 0) if v is None else (1, v) if isinstance(v, bytes) else (2, float(v)) for v in r)
@@ -471,6 +499,57 @@ def test_projection_with_filter_wide_table(gpu_api):
     assert len(got) == len(want) > 4000
     assert got == want
     assert gp.metrics()["numOutputRows"] == len(want)
+
+
+def _split_rows(raw):
+    out, o = [], 0
+    while o < len(raw):
+        sz = int.from_bytes(raw[o:o + 8], "little")
+        out.append(bytes(raw[o:o + 8 + sz]))
+        o += 8 + sz
+    assert o == len(raw)
+    return sorted(out)
+
+
+def test_projected_rows_written_on_the_device_equal_the_host_writer(gpu_api, batches, monkeypatch):
+    """MODE_PROJECT rows are sized, laid out and written by the GPU (sd_rows.cu) and leave in one copy.  Every field width
+    (BOOLEAN, BYTE, SHORT, INT, DATE, FLOAT, DOUBLE, LONG, dictionary STRING), NULLs in the record's null bits and as dictionary
+    NULL codes: against the oracle row for row, and byte for byte against the engine's host-side writer (SD_TUNE_HOST_ROWS, the
+    path a plan with host-only dictionary entries still takes)."""
+    b = PlanBuilder()
+    c = cols(b)
+    b.filter(c["c0"].is_null() | (c["c0"] > b.lit(T.INT)))
+    b.project(*[c[name] for name, _, _ in SCHEMA])
+    desc = b.build()
+    raws = {}
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("SD_TUNE_HOST_ROWS", "1")
+        else:
+            monkeypatch.delenv("SD_TUNE_HOST_ROWS", raising=False)
+        gp = capi.Plan(gpu_api, desc).set_literals([-200])
+        for x in batches:
+            gp.submit(x)
+        raws[host] = gp.finish_raw()
+        assert gp.finish_raw() == raws[host]          # served again (a caller whose buffer was too small asks twice)
+    assert len(raws[False]) == len(raws[True]) > 100_000
+    assert _split_rows(raws[False]) == _split_rows(raws[True])
+    op = oracle.plan(desc).set_literals([-200])
+    for x in batches:
+        op.submit(x)
+    from snappydata_b200.column_format import parse_row_stream
+    got = sorted(parse_row_stream(raws[False], desc.partial_schema()), key=_rowkey)
+    want = sorted(op.finish(), key=_rowkey)
+    assert len(got) == len(want) and got == want
+    # nothing passes: an empty stream, not an error
+    b2 = PlanBuilder()
+    c2 = cols(b2)
+    b2.filter(c2["c0"] > b2.lit(T.INT))
+    b2.project(c2["c0"], c2["c3"])
+    gp = capi.Plan(gpu_api, b2.build()).set_literals([10**6])
+    for x in batches:
+        gp.submit(x)
+    assert gp.finish_raw() == b""
 
 
 def test_projection_output_larger_than_initial_buffer_is_replayed(gpu_api):

@@ -652,8 +652,6 @@ int ensure_out(sd_plan* p, int64_t cap_records) {
   if (!p->d_out_count) { SD_CUDA(cudaMalloc(&p->d_out_count, 64)); SD_CUDA(cudaMemset(p->d_out_count, 0, 64)); }
   if (cap_records > p->out_cap) {
     if (p->d_out) cudaFree(p->d_out);
-  if (p->h_recs) cudaFreeHost(p->h_recs);
-  p->roww.release();
     p->d_out = nullptr;
     SD_CUDA(cudaMalloc(&p->d_out, (size_t)(cap_records * rec)));
     p->out_cap = cap_records;
@@ -1618,10 +1616,37 @@ int sd_plan_scan_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32
   return launch_scan(p, c.d_batches, c.d_prefix, c.nbatches, c.total_chunks, c.needs_slow, &c.batches);
 }
 
+// dense / no-key state (the [ngroups][slots] table the kernel leaves) -> partial rows appended to `out`:
+// UnsafeRow(group keys ++ aggregate buffers) (SnappyHashAggregateExec.scala:1148-1178).  The key dictionaries are arguments
+// because the exchange's dense form carries ANOTHER rank's state and dictionaries (ids are private to a partition).
+static int64_t dense_rows_from_state(const PlanSpec& sp, const uint64_t* h, int ngroups, const int32_t* radix, const std::vector<int>& key_null_id,
+                                     const std::vector<std::vector<std::string>>& key_vals, const StrMap* agg_strs, std::vector<uint8_t>& out) {
+  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  const std::vector<int> types = partial_field_types(sp);
+  int64_t nrows = 0;
+  std::vector<HVal> vals;
+  for (int g = 0; g < ngroups; g++) {
+    const uint64_t* sv = &h[(size_t)g * ns];
+    if (nk > 0 && sv[sp.rows_slot] == 0) continue;   // group never seen
+    vals.clear();
+    int rem = g, idx[MAX_KEYS];
+    for (int k = nk - 1; k >= 0; k--) { idx[k] = rem % radix[k]; rem /= radix[k]; }
+    for (int k = 0; k < nk; k++) {
+      HVal v;
+      if (idx[k] == key_null_id[k]) v.isnull = true; else v.s = key_vals[k][idx[k]];
+      vals.push_back(v);
+    }
+    append_agg_fields(sp, sv, vals, agg_strs);
+    emit_unsafe_row(out, types, vals);
+    nrows++;
+  }
+  return nrows;
+}
+
 // partial rows of this execution's dense / no-key result -> p->finished_rows
 static int finish_dense(sd_plan* p) {
   const PlanSpec& sp = p->spec;
-  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  const int ns = (int)sp.slots.size();
   int rc = 0;
   if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
   const size_t ne = (size_t)p->ngroups * ns;
@@ -1635,8 +1660,6 @@ static int finish_dense(sd_plan* p) {
   p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
   p->metrics[8] = (int64_t)counters[0];
   p->metrics[11] = (int64_t)counters[0];
-  // partial rows: UnsafeRow(group keys ++ aggregate buffers) (SnappyHashAggregateExec.scala:1148-1178)
-  const std::vector<int> types = partial_field_types(sp);
   StrMap agg_strs;
   {
     std::vector<uint64_t> copy(h, h + ne);   // (the pinned mirror is reused by the fetch's own read-backs)
@@ -1645,33 +1668,21 @@ static int finish_dense(sd_plan* p) {
   }
   std::vector<uint8_t>& out = p->finished_rows;
   out.clear();
-  int64_t nrows = 0;
-  std::vector<HVal> vals;
-  for (int g = 0; g < p->ngroups; g++) {
-    const uint64_t* sv = &h[(size_t)g * ns];
-    if (nk > 0 && sv[sp.rows_slot] == 0) continue;   // group never seen
-    vals.clear();
-    int rem = g, idx[MAX_KEYS];
-    for (int k = nk - 1; k >= 0; k--) { idx[k] = rem % p->radix[k]; rem /= p->radix[k]; }
-    for (int k = 0; k < nk; k++) {
-      HVal v;
-      if (idx[k] == p->key_null_id[k]) v.isnull = true; else v.s = p->key_vals[k][idx[k]];
-      vals.push_back(v);
-    }
-    append_agg_fields(sp, sv, vals, &agg_strs);
-    emit_unsafe_row(out, types, vals);
-    nrows++;
-  }
-  p->finished_nrows = nrows;
+  p->finished_nrows = dense_rows_from_state(sp, h, p->ngroups, p->radix, p->key_null_id, p->key_vals, &agg_strs, out);
   return 0;
 }
 
 // run what is pending and materialise this partition's partial rows in p->finished_rows (once per execution)
-static int collect_partial_rows(sd_plan* p) {
+static int launch_what_is_pending(sd_plan* p) {
   SD_CUDA(cudaSetDevice(p->device));
   int rc = flush_pending(p);
   if (rc) return rc;
   if (p->priv) { rc = store_lz4_check(p->priv); if (rc) return rc; }   // a corrupt compressed buffer fails the execution
+  return 0;
+}
+static int collect_partial_rows(sd_plan* p) {
+  int rc = launch_what_is_pending(p);
+  if (rc) return rc;
   if (p->finished_nrows >= 0) return 0;
   const int mode = p->spec.mode;
   rc = mode == MODE_HASH ? finish_hash(p) : mode == MODE_PROJECT ? finish_project(p) : finish_dense(p);
@@ -1756,6 +1767,7 @@ void sd_plan_destroy(sd_plan* p) {
   hash_free(p);
   if (p->d_out) cudaFree(p->d_out);
   if (p->h_recs) cudaFreeHost(p->h_recs);
+  p->roww.release();
   if (p->d_out_count) cudaFree(p->d_out_count);
   if (p->d_hash_ident) cudaFree(p->d_hash_ident);
   if (p->d_ticket) cudaFree(p->d_ticket);
@@ -2098,24 +2110,76 @@ int sd_comm_info(sd_comm* c, int64_t out[4]) {
   return 0;
 }
 
+// The exchange's blob of one rank: [magic u32][flags u32][len u64][payload].  flags bit 0: the payload did not fit the slot (only
+// the header travelled; every rank doubles the slot and repeats).  flags bit 1: DENSE form -- the payload is this rank's key
+// dictionaries followed by the raw [counters][ngroups x slots] state exactly as the kernel left it in HBM:
+//   [ngroups i32][nk i32][radix i32 x nk][null id i32 x nk] { [n u32] { [len u32][bytes] } x n } x nk  pad to 8  [state u64 x (8 + ngroups*ns)]
+// The sender queues header H2D + a device-to-device copy of the state + the all-gather behind its scan kernel and meets the
+// result with ONE synchronisation: no read-back of its own state, no row building, no second upload before the collective
+// (the by-value form below needs all three).  Receivers turn each rank's state into partial rows with that rank's dictionaries.
+static bool dense_exchange_eligible(const sd_plan* p) {
+  if (getenv("SD_TUNE_EXCHANGE_ROWS")) return false;
+  const PlanSpec& sp = p->spec;
+  if (sp.mode != MODE_NOKEY && sp.mode != MODE_GROUPS) return false;
+  if (p->finished_nrows >= 0) return false;   // rows already materialised by an earlier call
+  for (const auto& sl : sp.slots) if (sl.op == SLOT_MIN_STR || sl.op == SLOT_MAX_STR) return false;   // values live in this rank's HBM
+  return true;
+}
+
 int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   if (!p || !c) return set_error(SD_ERR_INVALID, "sd_plan_exchange: null argument");
   if (c->device != p->device) return set_error(SD_ERR_INVALID, "communicator lives on device %d, plan on %d", c->device, p->device);
-  int rc = collect_partial_rows(p);
+  int rc = launch_what_is_pending(p);
   if (rc) return rc;
-  rc = rows_to_host(p);
-  if (rc) return rc;
+  const PlanSpec& sp = p->spec;
+  const int ns = (int)sp.slots.size(), nk = (int)sp.keys.size();
+  const bool dense = dense_exchange_eligible(p);
+  std::vector<uint8_t> dense_hdr;
+  size_t state_bytes = 0;
+  if (dense) {
+    if (!p->result_init) { rc = init_result(p, 1); if (rc) return rc; p->ngroups = 1; }
+    const size_t ne = (size_t)p->ngroups * ns;
+    rc = ensure_result(p, ne);
+    if (rc) return rc;
+    state_bytes = (STATE_HDR + ne) * 8;
+    auto put32 = [&](uint32_t v) { const uint8_t* q = reinterpret_cast<const uint8_t*>(&v); dense_hdr.insert(dense_hdr.end(), q, q + 4); };
+    put32((uint32_t)p->ngroups); put32((uint32_t)nk);
+    for (int k = 0; k < nk; k++) put32((uint32_t)p->radix[k]);
+    for (int k = 0; k < nk; k++) put32((uint32_t)p->key_null_id[k]);
+    for (int k = 0; k < nk; k++) {
+      put32((uint32_t)p->key_vals[k].size());
+      for (const std::string& v : p->key_vals[k]) { put32((uint32_t)v.size()); dense_hdr.insert(dense_hdr.end(), v.begin(), v.end()); }
+    }
+    dense_hdr.resize((dense_hdr.size() + 7) & ~size_t(7), 0);
+  } else {
+    rc = collect_partial_rows(p);
+    if (rc) return rc;
+    rc = rows_to_host(p);
+    if (rc) return rc;
+  }
   const std::vector<uint8_t>& mine = p->finished_rows;
   for (;;) {
     rc = comm_buffers(c);
     if (rc) return rc;
-    const size_t room = c->cap - 16, n = mine.size(), sent = std::min(n, room);
-    const uint32_t hdr32[2] = {COMM_MAGIC, n > room ? 1u : 0u};
+    const size_t room = c->cap - 16, n = dense ? dense_hdr.size() + state_bytes : mine.size();
+    const bool fits = n <= room;
+    const uint32_t hdr32[2] = {COMM_MAGIC, (fits ? 0u : 1u) | (dense ? 2u : 0u)};
     const uint64_t len64 = n;
     memcpy(c->h_send, hdr32, 8);
     memcpy(c->h_send + 8, &len64, 8);
-    if (sent) memcpy(c->h_send + 16, mine.data(), sent);
-    SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16 + sent, cudaMemcpyHostToDevice, p->stream));
+    if (dense) {
+      if (fits) {
+        memcpy(c->h_send + 16, dense_hdr.data(), dense_hdr.size());
+        SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16 + dense_hdr.size(), cudaMemcpyHostToDevice, p->stream));
+        SD_CUDA(cudaMemcpyAsync(c->d_send + 16 + dense_hdr.size(), p->d_state, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
+      } else {
+        SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16, cudaMemcpyHostToDevice, p->stream));
+      }
+    } else {
+      const size_t sent = std::min(n, room);
+      if (sent) memcpy(c->h_send + 16, mine.data(), sent);
+      SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16 + sent, cudaMemcpyHostToDevice, p->stream));
+    }
     rc = comm_all_gather_bytes(c->nccl, c->d_send, c->d_recv, c->cap, p->stream);
     if (rc) return rc;
     SD_CUDA(cudaMemcpyAsync(c->h_recv, c->d_recv, c->cap * (size_t)c->world, cudaMemcpyDeviceToHost, p->stream));
@@ -2138,8 +2202,44 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   std::vector<uint8_t> all;
   for (int r = 0; r < c->world; r++) {
     const uint8_t* h = c->h_recv + (size_t)r * c->cap;
-    uint64_t l; memcpy(&l, h + 8, 8);
-    all.insert(all.end(), h + 16, h + 16 + l);
+    uint32_t flags; uint64_t l;
+    memcpy(&flags, h + 4, 4); memcpy(&l, h + 8, 8);
+    const uint8_t* q = h + 16;
+    const uint8_t* const end = q + l;
+    if (!(flags & 2u)) { all.insert(all.end(), q, end); continue; }
+    // dense form: that rank's dictionaries, then its state
+    auto get32 = [&](uint32_t* v) { if (q + 4 > end) return false; memcpy(v, q, 4); q += 4; return true; };
+    auto bad = [&]() { return set_error(SD_ERR_CUDA, "sd_plan_exchange: malformed dense blob from rank %d", r); };
+    uint32_t ng = 0, rnk = 0;
+    if (!get32(&ng) || !get32(&rnk) || (int)rnk != nk || ng == 0) return bad();
+    int32_t radix[MAX_KEYS] = {1, 1, 1, 1};
+    std::vector<int> null_id((size_t)nk, -1);
+    std::vector<std::vector<std::string>> vals((size_t)nk);
+    uint64_t prod = 1;
+    for (int k = 0; k < nk; k++) { uint32_t v; if (!get32(&v) || v == 0) return bad(); radix[k] = (int32_t)v; prod *= v; }
+    if (prod != ng) return bad();
+    for (int k = 0; k < nk; k++) { uint32_t v; if (!get32(&v)) return bad(); null_id[(size_t)k] = (int32_t)v; }
+    for (int k = 0; k < nk; k++) {
+      uint32_t nv; if (!get32(&nv)) return bad();
+      for (uint32_t i = 0; i < nv; i++) {
+        uint32_t sl; if (!get32(&sl) || q + sl > end) return bad();
+        vals[(size_t)k].emplace_back(reinterpret_cast<const char*>(q), sl); q += sl;
+      }
+      // (a radix may exceed the dictionary by the NULL id; an id beyond both never has rows)
+      if ((size_t)radix[k] > vals[(size_t)k].size()) vals[(size_t)k].resize((size_t)radix[k]);
+    }
+    q = h + 16 + (((size_t)(q - (h + 16)) + 7) & ~size_t(7));
+    if (q + (STATE_HDR + (size_t)ng * ns) * 8 != end) return bad();
+    std::vector<uint64_t> st((STATE_HDR + (size_t)ng * ns));
+    memcpy(st.data(), q, st.size() * 8);
+    const int64_t nr = dense_rows_from_state(sp, st.data() + STATE_HDR, (int)ng, radix, null_id, vals, nullptr, all);
+    if (r == c->rank) {   // this rank's own execution metrics come back with its blob
+      update_agg_time(p);
+      p->metrics[6] = (int64_t)(p->agg_ms * 1e6);
+      p->metrics[8] = (int64_t)st[0];
+      p->metrics[11] = (int64_t)st[0];
+      p->metrics[0] = nr;
+    }
   }
   std::vector<uint8_t> merged;
   int64_t nrows = 0;
@@ -2147,6 +2247,7 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   if (rc) return rc;
   p->finished_rows.swap(merged);
   p->finished_nrows = nrows;
+  p->dev_rows_len = -1;
   return 0;
 }
 

@@ -55,21 +55,35 @@ def by_flag_and_date():
     return b.build()
 
 
-for name, desc, lits, nk in (("q1", P.q1_plan(), P.Q1_LITERALS, 2), ("q6", P.q6_plan(), P.Q6_LITERALS, 0), ("by_date", by_date(), [], 1),
-                             ("by_flag_and_date", by_flag_and_date(), [10000], 2)):
-    gp = capi.Plan(api, desc).set_literals(lits)
-    for b in mine:
-        gp.submit(b)
-    gp.exchange(comm)
-    merged = gp.finish_raw()
-    got = gp.final_merge(merged)
+def form(which):
+    """which form this rank's blob takes in sd_plan_exchange: "dense" = dictionaries + raw device state (default for dense /
+    no-key plans), "rows" = partial rows by value, "mixed" = rank 0 dense, the others by value (receivers decode per blob)"""
+    if which == "rows" or (which == "mixed" and rank != 0):
+        os.environ["SD_TUNE_EXCHANGE_ROWS"] = "1"
+    else:
+        os.environ.pop("SD_TUNE_EXCHANGE_ROWS", None)
+
+
+for name, desc, lits, nk, forms in (("q1", P.q1_plan(), P.Q1_LITERALS, 2, ("dense", "rows", "mixed")), ("q6", P.q6_plan(), P.Q6_LITERALS, 0, ("dense", "rows")),
+                                    ("by_date", by_date(), [], 1, ("dense",)), ("by_flag_and_date", by_flag_and_date(), [10000], 2, ("dense",))):
     op = oracle.plan(desc).set_literals(lits)
     for b in table:
         op.submit(b)
     want = oracle.final_merge(desc, op.finish_raw())
-    assert_rowsets_match(got, want, nk)
-    if rank == 0:
-        print(name, "ok:", len(got), "groups", comm.info(), flush=True)
+    for which in forms:
+        form(which)
+        gp = capi.Plan(api, desc).set_literals(lits)
+        for b in mine:
+            gp.submit(b)
+        gp.exchange(comm)
+        merged = gp.finish_raw()
+        got = gp.final_merge(merged)
+        assert_rowsets_match(got, want, nk)
+        m = gp.metrics()
+        assert m["numOutputRows"] >= (1 if nk == 0 else 0) and m["aggTimeNs"] > 0
+        if rank == 0:
+            print(name, which, "ok:", len(got), "groups", comm.info(), flush=True)
+form("dense")
 assert comm.info()["regrows"] >= 1
 dist.barrier()
 dist.destroy_process_group()

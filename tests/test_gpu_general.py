@@ -538,8 +538,13 @@ def test_projected_rows_written_on_the_device_equal_the_host_writer(gpu_api, bat
     for x in batches:
         op.submit(x)
     from snappydata_b200.column_format import parse_row_stream
-    got = sorted(parse_row_stream(raws[False], desc.partial_schema()), key=_rowkey)
-    want = sorted(op.finish(), key=_rowkey)
+    import struct
+
+    def canon(r):   # bit-exact and NaN-safe: doubles by their bytes (c2 holds NaN, -0.0, inf)
+        return tuple((0, b"") if v is None else (1, struct.pack("<d", v)) if isinstance(v, float) else (2, v) if isinstance(v, bytes)
+                     else (3, struct.pack("<q", int(v))) for v in r)
+    got = sorted(canon(r) for r in parse_row_stream(raws[False], desc.partial_schema()))
+    want = sorted(canon(r) for r in op.finish())
     assert len(got) == len(want) and got == want
     # nothing passes: an empty stream, not an error
     b2 = PlanBuilder()

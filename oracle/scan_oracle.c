@@ -430,7 +430,7 @@ static int dec_ps(const oracle_plan* p, int node) {
 static val eval_node(const oracle_plan* p, const sd_expr* e, const val* cols) {
   val r; memset(&r, 0, sizeof(r));
   switch (e->op) {
-    case SD_OP_COL: return cols[e->a];
+    case SD_OP_COL: { val v = cols[e->a]; if (e->type == SD_DECIMAL) v.w = v.i; return v; }   /* decoders fill .i; DECIMAL consumers read .w */
     case SD_OP_LIT: {
       const sd_literal* l = &p->lits[e->a];
       r.isnull = l->is_null; r.i = l->i; r.d = l->d; r.s = (const uint8_t*)l->s; r.slen = l->slen;

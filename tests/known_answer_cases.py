@@ -327,7 +327,37 @@ def case_min_max_of_strings(_run):
     assert _run(b.build(), [99], batches)[0] == [[None, None]]
 
 
+def case_projection_returns_the_stored_values(_run):
+    """Filter + project with no aggregate (ColumnTableScan feeding the row consumer directly): every projected field is the
+    stored value -- DECIMAL(18,2) and a nullable DECIMAL(12,3) as their unscaled longs (UnsafeRow.setDecimal for precision <=
+    18), FLOAT, BOOLEAN, LONG, a dictionary STRING and an Uncompressed one -- checked against the INPUT arrays, not against
+    another engine."""
+    from snappydata_b200 import capi
+    n = 700
+    i = np.arange(n)
+    data = {"d": (i * 1234567 - 400_000_000).astype(np.int64), "e": ((i % 97) * 1001 - 5000).astype(np.int64), "l": (i * i - 1000).astype(np.int64),
+            "f": (i % 13).astype(np.float32) / 4, "b": (i % 3 == 0), "s": np.array([b"v%d" % (x % 11) for x in i], dtype=object),
+            "t": np.array([b"raw-%05d" % x for x in i], dtype=object)}
+    nulls = {"e": i % 5 == 0, "b": i % 7 == 0}
+    schema = [("d", T.DECIMAL, False), ("e", T.DECIMAL, True), ("l", T.LONG, False), ("f", T.FLOAT, False), ("b", T.BOOLEAN, True),
+              ("s", T.STRING, False), ("t", T.STRING, False)]
+    batches = [build_batch(n, schema, data, nulls, batch_id=0, encoders={"t": "uncompressed"})]
+    b = PlanBuilder()
+    c = [b.col(T.DECIMAL, 0, False, scale=2, precision=18), b.col(T.DECIMAL, 1, True, scale=3, precision=12), b.col(T.LONG, 2, False),
+         b.col(T.FLOAT, 3, False), b.col(T.BOOLEAN, 4, True), b.col(T.STRING, 5, False), b.col(T.STRING, 6, False)]
+    b.filter(c[2] >= b.lit(T.LONG))
+    b.project(*c)
+    pl = capi.Plan(_run.api, b.build()).set_literals([24])     # l >= 24  <=>  i >= 32
+    for x in batches:
+        pl.submit(x)
+    rows = pl.finish()
+    want = [[int(data["d"][x]), None if nulls["e"][x] else int(data["e"][x]), int(data["l"][x]), float(data["f"][x]),
+             None if nulls["b"][x] else bool(data["b"][x]), bytes(data["s"][x]), bytes(data["t"][x])] for x in range(32, n)]
+    key = lambda r: r[2]
+    assert sorted(rows, key=key) == sorted(want, key=key)
+
+
 CASES = [case_sha_one_nullable_string_key_closed_form, case_sha_two_nullable_string_keys_closed_form,
          case_delta_stats_point_filters_after_updates, case_basic_delete_and_update_counts,
          case_sha_sum_of_every_numeric_type_per_string_key, case_sha_decimal_sum_and_avg_per_string_key, case_casts_follow_spark,
-         case_sha_null_key_bit_masking_1_to_32_key_columns, case_min_max_of_strings]
+         case_sha_null_key_bit_masking_1_to_32_key_columns, case_min_max_of_strings, case_projection_returns_the_stored_values]

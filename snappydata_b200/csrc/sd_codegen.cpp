@@ -642,6 +642,7 @@ struct Gen {
     }
     if ((int)p.tables.size() > MAX_TABLES) return fail(SD_ERR_UNSUPPORTED, "more than 40 dictionary lookup tables in one plan");
     sig << ";mode=" << p.mode << ";tables=" << p.tables.size() << ";rpt=" << p.rpt << ";minctas=" << p.min_ctas << ";staged=" << (p.stages > 0 ? 1 : 0) << ";reggroups=" << p.reg_groups << ";litnull=" << p.lit_nullable << ";slow=" << p.slow_paths;
+    if (const char* e = getenv("SD_JIT_DEFINES")) sig << ";defines=" << e;   // experiment switches compile (and cache) as distinct kernels
     p.signature = sig.str();
     char hbuf[32];
     snprintf(hbuf, sizeof(hbuf), "%016llx", (unsigned long long)std::hash<std::string>()(p.signature));

@@ -124,9 +124,19 @@ int jit_compile(const PlanSpec& spec, int device, KernelEntry& out) {
   if (nr != NVRTC_SUCCESS) return set_error(SD_ERR_CUDA, "nvrtcCreateProgram: %s", d.GetErrorString(nr));
   d.AddNameExpression(prog, name_expr.c_str());
   // -lineinfo adds ~50 % to the compile: only when a profile of a JIT kernel is wanted (SD_JIT_LINEINFO=1)
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-default-device", "-lineinfo"};
+  std::vector<std::string> optv = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-default-device"};
   const char* li = getenv("SD_JIT_LINEINFO");
-  nr = d.CompileProgram(prog, (li && atoi(li) > 0) ? 5 : 4, opts);
+  if (li && atoi(li) > 0) optv.push_back("-lineinfo");
+  if (const char* defs = getenv("SD_JIT_DEFINES")) {   // space-separated -DNAME=VALUE switches (experiments; part of the plan signature)
+    std::string tok;
+    for (const char* q = defs;; q++) {
+      if (*q == ' ' || *q == 0) { if (!tok.empty()) optv.push_back(tok); tok.clear(); if (!*q) break; }
+      else tok.push_back(*q);
+    }
+  }
+  std::vector<const char*> opts;
+  for (const std::string& o : optv) opts.push_back(o.c_str());
+  nr = d.CompileProgram(prog, (int)opts.size(), opts.data());
   if (nr != NVRTC_SUCCESS) {
     size_t ls = 0;
     d.GetProgramLogSize(prog, &ls);

@@ -158,6 +158,14 @@ __device__ __forceinline__ uint64_t hash_mix64(uint64_t h, uint64_t v) {
 }
 // STRMASK bit k: key k is a STRING held by reference (kc[k] = device address of its [len][bytes] record, 0 when NULL):
 // hashed and compared by its bytes
+#ifndef SD_EXP_RING
+#define SD_EXP_RING 0
+#endif
+#ifndef SD_EXP_HASH
+#define SD_EXP_HASH 0
+#endif
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ int64_t ld_relaxed_s64(const int64_t* p) { int64_t v; asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 template <int NK, uint32_t STRMASK>
 __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const int64_t* kc, uint32_t knull) {
   uint64_t h = 0x2545f4914f6cdd1dull ^ knull;
@@ -182,11 +190,21 @@ __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const
       }
     }
     while (st == 1u) { __nanosleep(20); st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]); }   // writer in flight
+#if SD_EXP_HASH == 1
+    // the entry is published (state 2, written after the key with a fence in between).  Reader side without a fence: strong
+    // (L1-bypassing) loads whose ADDRESS depends on the state value just read, so they cannot be performed before it
+    const size_t dep = (size_t)(st - 2u);   // 0; unknown to the compiler
+    bool same = ld_relaxed_u32(&t.knull[pos + dep]) == knull;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const int64_t have = ld_relaxed_s64(&t.keys[(size_t)pos * NK + k + dep]);
+#else
     __threadfence();
     bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
 #pragma unroll
     for (int k = 0; k < NK; k++) {
       const int64_t have = *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]);
+#endif
       if ((STRMASK >> k) & 1u) same = same && (have == kc[k] || (have && kc[k] && str_eq_recs(reinterpret_cast<const uint8_t*>(have), reinterpret_cast<const uint8_t*>(kc[k]))));
       else same = same && have == kc[k];
     }
@@ -1019,7 +1037,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   const int nstages = args.nstages;
   if (PLAN::STAGES > 0) {
     if (tid == 0) {
-      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], THREADS / 32); }
+      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], SD_EXP_RING == 2 ? THREADS : THREADS / 32); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // all THREADS + 32 threads: the only CTA-wide barrier the producer warp joins
@@ -1128,8 +1146,15 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           mbar_wait(&full_bar[c_stage], c_phase);   // (the NULL-aware loads derive their word prefixes per warp: no barrier here)
           if (with_nulls) load_all_staged_nulls<PLAN>(b, c16, tile_start, sm, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           else load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
+#if SD_EXP_RING == 2
+          mbar_arrive(&empty_bar[c_stage]);                        // every thread releases for itself (barrier counts THREADS arrivals)
+#else
+#if SD_EXP_RING == 1
+          __threadfence_block();                                   // this lane's stage loads are performed ...
+#endif
           __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // this warp holds its rows in registers now
+          if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // ... this warp holds its rows in registers now
+#endif
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }
         } else {
           load_all_fast<PLAN>(b, tile_start, regs, ColSeq());

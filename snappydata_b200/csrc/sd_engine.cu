@@ -1135,6 +1135,12 @@ int finish_hash(sd_plan* p) {
   }
   SD_CUDA(cudaMemcpyAsync(counters, p->d_counters, 16, cudaMemcpyDeviceToHost, p->stream));
   SD_CUDA(cudaStreamSynchronize(p->stream));
+  if (getenv("SD_DEBUG_VERIFY")) {   // diagnostic builds (SD_JIT_DEFINES=-DSD_EXP_VERIFY=1): staged tile vs global memory
+    unsigned long long dbg[8] = {0};
+    SD_CUDA(cudaMemcpy(dbg, p->d_counters, 64, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[verify] mismatching values %llu; first: column %llu stage %llu row %llu staged %016llx true %016llx\n", dbg[4],
+            (dbg[5] >> 56) - (dbg[5] ? 1 : 0), (dbg[5] >> 48) & 0xff, dbg[5] & 0xffffffffffffull, dbg[6], dbg[7]);
+  }
   // STRING keys are held by reference (address of the [len][bytes] record in a resident buffer): fetch their bytes
   std::vector<std::vector<std::string>> key_strings((size_t)nk);
   for (int k = 0; k < nk && count; k++) {

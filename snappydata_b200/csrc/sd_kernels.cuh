@@ -714,6 +714,32 @@ __device__ __forceinline__ void load_all_fast(const DevBatch<PLAN::NC>& b, int64
   int dummy[] = {0, (load_col_fast<PLAN, Cs>(b.cols[Cs], tile_start, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
   (void)dummy;
 }
+#ifndef SD_EXP_VERIFY
+#define SD_EXP_VERIFY 0
+#endif
+// SD_EXP_VERIFY (diagnostic builds only): the staged copy of a tile against the same rows read straight from global memory
+template <class PLAN, int C>
+__device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColRegs<PLAN, C>& b, uint32_t live, int64_t tile_start, int stage,
+                                           unsigned long long* counters) {
+#pragma unroll
+  for (int r = 0; r < PLAN::RPT; r++) {
+    if (!((live >> r) & 1u)) continue;
+    unsigned long long x = 0, y = 0;
+    memcpy(&x, &a.v[r], sizeof(a.v[r]));
+    memcpy(&y, &b.v[r], sizeof(b.v[r]));
+    if (x != y) {
+      atomicAdd(&counters[4], 1ull);
+      const unsigned long long tag = ((unsigned long long)(C + 1) << 56) | ((unsigned long long)stage << 48) | ((unsigned long long)(tile_start + row_in_tile(r)) & 0xffffffffffffull);
+      if (atomicCAS(&counters[5], 0ull, tag) == 0ull) { counters[6] = x; counters[7] = y; }
+    }
+  }
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ void verify_all(const AllCols<PLAN, Seq<Cs...>>& a, const AllCols<PLAN, Seq<Cs...>>& b, uint32_t live, int64_t tile_start,
+                                           int stage, unsigned long long* counters, Seq<Cs...>) {
+  int dummy[] = {0, (verify_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a), static_cast<const ColRegs<PLAN, Cs>&>(b), live, tile_start, stage, counters), 0)...};
+  (void)dummy;
+}
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void clear_upd_bits(const DevBatch<PLAN::NC>& b, TileSmem<PLAN>& sm, Seq<Cs...>) {
   const int tid = threadIdx.x;
@@ -1154,6 +1180,13 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 #endif
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // ... this warp holds its rows in registers now
+#endif
+#if SD_EXP_VERIFY
+          if (!with_nulls) {
+            AllCols<PLAN, ColSeq> chk;
+            load_all_fast<PLAN>(b, tile_start, chk, ColSeq());
+            verify_all<PLAN>(regs, chk, live, tile_start, c_stage, args.counters, ColSeq());
+          }
 #endif
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }
         } else {

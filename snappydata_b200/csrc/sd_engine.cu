@@ -1138,6 +1138,7 @@ int finish_hash(sd_plan* p) {
   if (getenv("SD_DEBUG_VERIFY")) {   // diagnostic builds (SD_JIT_DEFINES=-DSD_EXP_VERIFY=1): staged tile vs global memory
     unsigned long long dbg[8] = {0};
     SD_CUDA(cudaMemcpy(dbg, p->d_counters, 64, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[verify] of the mismatches: %llu = the stage's PREVIOUS occupant (read before the copy landed), %llu = its NEXT occupant (overwritten before the read)\n", dbg[2], dbg[3]);
     fprintf(stderr, "[verify] mismatching values %llu; first: column %llu stage %llu row %llu staged %016llx true %016llx\n", dbg[4],
             (dbg[5] >> 56) - (dbg[5] ? 1 : 0), (dbg[5] >> 48) & 0xff, dbg[5] & 0xffffffffffffull, dbg[6], dbg[7]);
   }

@@ -720,7 +720,8 @@ __device__ __forceinline__ void load_all_fast(const DevBatch<PLAN::NC>& b, int64
 // SD_EXP_VERIFY (diagnostic builds only): the staged copy of a tile against the same rows read straight from global memory
 template <class PLAN, int C>
 __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColRegs<PLAN, C>& b, uint32_t live, int64_t tile_start, int stage,
-                                           unsigned long long* counters) {
+                                           unsigned long long* counters, const DevCol& col, int nstages, int num_rows) {
+  typedef typename KindT<PLAN::kind(C)>::T T;
 #pragma unroll
   for (int r = 0; r < PLAN::RPT; r++) {
     if (!((live >> r) & 1u)) continue;
@@ -728,6 +729,13 @@ __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColR
     memcpy(&x, &a.v[r], sizeof(a.v[r]));
     memcpy(&y, &b.v[r], sizeof(b.v[r]));
     if (x != y) {
+      // whose value is it?  the stage's previous / next occupant inside the same batch (k tiles back / ahead, k = nstages)
+      const int64_t row = tile_start + row_in_tile(r), span = (int64_t)nstages * THREADS * PLAN::RPT;
+      const T* base = reinterpret_cast<const T*>(col.data);
+      unsigned long long pv = ~0ull, nv = ~0ull;
+      if (row - span >= 0) { pv = 0; memcpy(&pv, &base[row - span], sizeof(T)); }
+      if (row + span < num_rows) { nv = 0; memcpy(&nv, &base[row + span], sizeof(T)); }
+      if (x == pv) atomicAdd(&counters[2], 1ull); else if (x == nv) atomicAdd(&counters[3], 1ull);
       atomicAdd(&counters[4], 1ull);
       const unsigned long long tag = ((unsigned long long)(C + 1) << 56) | ((unsigned long long)stage << 48) | ((unsigned long long)(tile_start + row_in_tile(r)) & 0xffffffffffffull);
       if (atomicCAS(&counters[5], 0ull, tag) == 0ull) { counters[6] = x; counters[7] = y; }
@@ -736,8 +744,9 @@ __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColR
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void verify_all(const AllCols<PLAN, Seq<Cs...>>& a, const AllCols<PLAN, Seq<Cs...>>& b, uint32_t live, int64_t tile_start,
-                                           int stage, unsigned long long* counters, Seq<Cs...>) {
-  int dummy[] = {0, (verify_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a), static_cast<const ColRegs<PLAN, Cs>&>(b), live, tile_start, stage, counters), 0)...};
+                                           int stage, unsigned long long* counters, const DevBatch<PLAN::NC>& bt, int nstages, Seq<Cs...>) {
+  int dummy[] = {0, (verify_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a), static_cast<const ColRegs<PLAN, Cs>&>(b), live, tile_start, stage, counters,
+                                          bt.cols[Cs], nstages, bt.num_rows), 0)...};
   (void)dummy;
 }
 template <class PLAN, int... Cs>
@@ -1185,7 +1194,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           if (!with_nulls) {
             AllCols<PLAN, ColSeq> chk;
             load_all_fast<PLAN>(b, tile_start, chk, ColSeq());
-            verify_all<PLAN>(regs, chk, live, tile_start, c_stage, args.counters, ColSeq());
+            verify_all<PLAN>(regs, chk, live, tile_start, c_stage, args.counters, b, nstages, ColSeq());
           }
 #endif
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }

@@ -633,7 +633,8 @@ int hash_ensure(sd_plan* p, uint32_t capacity) {
     SD_CUDA(cudaMalloc(&p->hash.keys, (size_t)capacity * nk * 8));
     SD_CUDA(cudaMalloc(&p->hash.knull, (size_t)capacity * 4));
     SD_CUDA(cudaMalloc(&p->hash.vals, (size_t)capacity * ns * 8));
-    SD_CUDA(cudaMalloc(&p->hash.overflow, 64));
+    SD_CUDA(cudaMalloc(&p->hash.overflow, 1024));   // [0] overflow flag, [8] key count; the rest: diagnostic histograms (SD_EXP_VERIFY builds)
+    SD_CUDA(cudaMemset(p->hash.overflow, 0, 1024));
     p->hash.count = p->hash.overflow + 8;
     p->hash.mask = capacity - 1;
     p->hash.max_probe = std::min<uint32_t>(capacity, 4096);
@@ -1138,6 +1139,16 @@ int finish_hash(sd_plan* p) {
   if (getenv("SD_DEBUG_VERIFY")) {   // diagnostic builds (SD_JIT_DEFINES=-DSD_EXP_VERIFY=1): staged tile vs global memory
     unsigned long long dbg[8] = {0};
     SD_CUDA(cudaMemcpy(dbg, p->d_counters, 64, cudaMemcpyDeviceToHost));
+    uint32_t hist[64] = {0};
+    SD_CUDA(cudaMemcpy(hist, p->hash.overflow, 256, cudaMemcpyDeviceToHost));
+    SD_CUDA(cudaMemset(p->hash.overflow + 16, 0, 192));
+    fprintf(stderr, "[verify] by consumer warp:");
+    for (int i = 0; i < 8; i++) fprintf(stderr, " %u", hist[16 + i]);
+    fprintf(stderr, "   by eighth of the tile (128 rows each):");
+    for (int i = 0; i < 8; i++) fprintf(stderr, " %u", hist[24 + i]);
+    fprintf(stderr, "   by column:");
+    for (int i = 0; i < 4; i++) fprintf(stderr, " %u", hist[32 + i]);
+    fprintf(stderr, "   tiles with any mismatch (warp-level): %u of %u warp-tiles\n", hist[40], hist[41]);
     fprintf(stderr, "[verify] of the mismatches: %llu = the stage's PREVIOUS occupant (read before the copy landed), %llu = its NEXT occupant (overwritten before the read)\n", dbg[2], dbg[3]);
     fprintf(stderr, "[verify] mismatching values %llu; first: column %llu stage %llu row %llu staged %016llx true %016llx\n", dbg[4],
             (dbg[5] >> 56) - (dbg[5] ? 1 : 0), (dbg[5] >> 48) & 0xff, dbg[5] & 0xffffffffffffull, dbg[6], dbg[7]);

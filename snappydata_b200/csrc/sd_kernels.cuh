@@ -720,7 +720,7 @@ __device__ __forceinline__ void load_all_fast(const DevBatch<PLAN::NC>& b, int64
 // SD_EXP_VERIFY (diagnostic builds only): the staged copy of a tile against the same rows read straight from global memory
 template <class PLAN, int C>
 __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColRegs<PLAN, C>& b, uint32_t live, int64_t tile_start, int stage,
-                                           unsigned long long* counters, const DevCol& col, int nstages, int num_rows) {
+                                           unsigned long long* counters, const DevCol& col, int nstages, int num_rows, uint32_t* hist, int* any) {
   typedef typename KindT<PLAN::kind(C)>::T T;
 #pragma unroll
   for (int r = 0; r < PLAN::RPT; r++) {
@@ -737,6 +737,7 @@ __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColR
       if (row + span < num_rows) { nv = 0; memcpy(&nv, &base[row + span], sizeof(T)); }
       if (x == pv) atomicAdd(&counters[2], 1ull); else if (x == nv) atomicAdd(&counters[3], 1ull);
       atomicAdd(&counters[4], 1ull);
+      if (hist) { atomicAdd(&hist[16 + (threadIdx.x >> 5)], 1u); atomicAdd(&hist[24 + ((row_in_tile(r) >> 7) & 7)], 1u); atomicAdd(&hist[32 + (C & 3)], 1u); *any = 1; }
       const unsigned long long tag = ((unsigned long long)(C + 1) << 56) | ((unsigned long long)stage << 48) | ((unsigned long long)(tile_start + row_in_tile(r)) & 0xffffffffffffull);
       if (atomicCAS(&counters[5], 0ull, tag) == 0ull) { counters[6] = x; counters[7] = y; }
     }
@@ -744,9 +745,14 @@ __device__ __forceinline__ void verify_col(const ColRegs<PLAN, C>& a, const ColR
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void verify_all(const AllCols<PLAN, Seq<Cs...>>& a, const AllCols<PLAN, Seq<Cs...>>& b, uint32_t live, int64_t tile_start,
-                                           int stage, unsigned long long* counters, const DevBatch<PLAN::NC>& bt, int nstages, Seq<Cs...>) {
+                                           int stage, unsigned long long* counters, const DevBatch<PLAN::NC>& bt, int nstages, uint32_t* hist, Seq<Cs...>) {
+  int any = 0;
   int dummy[] = {0, (verify_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a), static_cast<const ColRegs<PLAN, Cs>&>(b), live, tile_start, stage, counters,
-                                          bt.cols[Cs], nstages, bt.num_rows), 0)...};
+                                          bt.cols[Cs], nstages, bt.num_rows, hist, &any), 0)...};
+  if (hist) {
+    const unsigned m = __ballot_sync(0xffffffffu, any != 0);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&hist[41], 1u); if (m) atomicAdd(&hist[40], 1u); }
+  }
   (void)dummy;
 }
 template <class PLAN, int... Cs>
@@ -1194,7 +1200,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           if (!with_nulls) {
             AllCols<PLAN, ColSeq> chk;
             load_all_fast<PLAN>(b, tile_start, chk, ColSeq());
-            verify_all<PLAN>(regs, chk, live, tile_start, c_stage, args.counters, b, nstages, ColSeq());
+            verify_all<PLAN>(regs, chk, live, tile_start, c_stage, args.counters, b, nstages, PLAN::MODE == MODE_HASH ? args.hash.overflow : nullptr, ColSeq());
           }
 #endif
           if (++c_stage == nstages) { c_stage = 0; c_phase ^= 1u; }

@@ -755,6 +755,20 @@ __device__ __forceinline__ void verify_all(const AllCols<PLAN, Seq<Cs...>>& a, c
   }
   (void)dummy;
 }
+template <class PLAN, int C>
+__device__ __forceinline__ unsigned long long regs_xor_col(const ColRegs<PLAN, C>& a) {
+  unsigned long long x = 0;
+#pragma unroll
+  for (int r = 0; r < PLAN::RPT; r++) { unsigned long long y = 0; memcpy(&y, &a.v[r], sizeof(a.v[r])); x ^= y; }
+  return x;
+}
+template <class PLAN, int... Cs>
+__device__ __forceinline__ unsigned long long regs_xor(const AllCols<PLAN, Seq<Cs...>>& a, Seq<Cs...>) {
+  unsigned long long x = 0;
+  int dummy[] = {0, (x ^= regs_xor_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a)), 0)...};
+  (void)dummy;
+  return x;
+}
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void clear_upd_bits(const DevBatch<PLAN::NC>& b, TileSmem<PLAN>& sm, Seq<Cs...>) {
   const int tid = threadIdx.x;
@@ -1104,6 +1118,9 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
             const int64_t tile_start = (int64_t)tile * TILE_ROWS;
             const int rows = min(TILE_ROWS, num_rows - (int)tile_start);
             mbar_wait(&empty_bar[stage], phase ^ 1u);
+#if defined(SD_EXP_PROD) && SD_EXP_PROD == 1
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
             issue_tile_copies<PLAN>(pc, c16, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
@@ -1115,6 +1132,9 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   int c_stage = 0;
   uint32_t c_phase = 0;
   int c_hint = -1;
+#if SD_EXP_RING == 5
+  uint64_t* rel_bar = nullptr;
+#endif
 
   // ---- accumulator init -------------------------------------------------------------------------
   uint64_t acc[NSLOT > 0 ? NSLOT : 1];
@@ -1189,9 +1209,19 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           else load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
 #if SD_EXP_RING == 2
           mbar_arrive(&empty_bar[c_stage]);                        // every thread releases for itself (barrier counts THREADS arrivals)
+#elif SD_EXP_RING == 5
+          if (rel_bar) { __syncwarp(); if ((tid & 31) == 0) mbar_arrive(rel_bar); }   // the PREVIOUS tile's stage: released one tile late
+          rel_bar = &empty_bar[c_stage];
 #else
 #if SD_EXP_RING == 1
           __threadfence_block();                                   // this lane's stage loads are performed ...
+#elif SD_EXP_RING == 3
+          {   // an instruction that needs every loaded value executes before the release
+            const unsigned long long x = regs_xor<PLAN>(regs, ColSeq());
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u64 p, %0, 0x5bd1e9955bd1e995;\n\t@p nanosleep.u32 1;\n\t}" ::"l"(x) : "memory");
+          }
+#elif SD_EXP_RING == 4
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
 #endif
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // ... this warp holds its rows in registers now

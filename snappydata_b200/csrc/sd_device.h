@@ -172,8 +172,6 @@ struct ScanArgs {
   int64_t out_cap;                // MODE_PROJECT: capacity in records
   int32_t batch_base;             // MODE_PROJECT: ordinal of this launch's first batch within the execution
   int32_t chunk_rows;             // rows per work item (multiple of every tile size; default CHUNK_ROWS)
-  int32_t hash_smem_cap;          // MODE_HASH: entries of the per-CTA shared-memory front table (power of two; 0: none)
-  int32_t pad3_;
   const uint8_t* lit_pool;        // bytes of the STRING literals of this execution (literal slot k: lits.i[k] = offset << 32 | length)
   int32_t fresh;                  // 1: first launch of an execution -- the last CTA OVERWRITES `result` (no host-side
                                   // identity upload, one dependent operation less in front of the kernel)

@@ -821,18 +821,6 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
     else if (shared <= 64 * 1024 && tile_smem + shared + min_ring <= budget1) { table_mode = TABLE_SHARED_ATOMIC; table_bytes = shared; }
     else { table_mode = TABLE_GLOBAL_ATOMIC; table_bytes = 64; }
   }
-  int hash_smem_cap = 0;
-  if (sp.mode == MODE_HASH && !getenv("SD_TUNE_NO_FRONT_TABLE")) {
-    // per-CTA shared-memory front table (sd_kernels.cuh: FrontTable): the largest power of two that leaves the ring >= 3 stages,
-    // with one CTA per SM so that the table gets most of the SM's shared memory
-    target_ctas = 1;
-    const size_t entry = 8 + 8 * (size_t)std::max(nk, 1) + 8 * (size_t)std::max(ns, 1);
-    const size_t ring_need = k->staged ? ring_fixed + 3 * k->stage_bytes + 256 : 0;
-    const size_t room = (size_t)p->smem_optin > tile_smem + ring_need + 1024 ? (size_t)p->smem_optin - tile_smem - ring_need - 1024 : 0;
-    size_t cap = 8192;
-    while (cap >= 256 && cap * entry + 16 > std::min<size_t>(room, size_t(144) << 10)) cap >>= 1;
-    if (cap >= 256) { hash_smem_cap = (int)cap; table_bytes = cap * entry + 16; }
-  }
   const size_t budget = (size_t)p->smem_optin / target_ctas - (target_ctas > 1 ? 1024 : 0);
   size_t ring_off = (tile_smem + table_bytes + 127) & ~size_t(127);
   int nstages = 0;
@@ -905,7 +893,6 @@ int launch_scan(sd_plan* p, const void* d_batches, const int32_t* d_prefix, int 
   args.batch_base = batch_base;
   args.chunk_rows = p->chunk_rows;
   args.fresh = fresh;
-  args.hash_smem_cap = hash_smem_cap;
   memcpy(args.radix, radix, sizeof(radix));
   if (p->litpool_dirty) {   // STRING literal bytes -> device (once per set of literal values)
     std::vector<uint8_t> pool;

@@ -158,12 +158,6 @@ __device__ __forceinline__ uint64_t hash_mix64(uint64_t h, uint64_t v) {
 }
 // STRMASK bit k: key k is a STRING held by reference (kc[k] = device address of its [len][bytes] record, 0 when NULL):
 // hashed and compared by its bytes
-#ifndef SD_EXP_RING
-#define SD_EXP_RING 0
-#endif
-#ifndef SD_EXP_HASH
-#define SD_EXP_HASH 0
-#endif
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ int64_t ld_relaxed_s64(const int64_t* p) { int64_t v; asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 template <int NK, uint32_t STRMASK>
@@ -190,84 +184,20 @@ __device__ __forceinline__ int64_t hash_find_or_insert(const HashTable& t, const
       }
     }
     while (st == 1u) { __nanosleep(20); st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]); }   // writer in flight
-#if SD_EXP_HASH == 1
-    // the entry is published (state 2, written after the key with a fence in between).  Reader side without a fence: strong
-    // (L1-bypassing) loads whose ADDRESS depends on the state value just read, so they cannot be performed before it
-    const size_t dep = (size_t)(st - 2u);   // 0; unknown to the compiler
+    // The entry is published: state 2 was stored after the key, with a fence in between (writer side above).  Reader side without
+    // a fence (__threadfence() here was a MEMBAR.SC.GPU + an L1 invalidate PER ROW: the largest stall of the hash kernels):
+    // strong (L1-bypassing) loads whose ADDRESS depends on the state value just read, so they are issued after it returned.
+    const size_t dep = (size_t)(st - 2u);   // 0; not known to the compiler
     bool same = ld_relaxed_u32(&t.knull[pos + dep]) == knull;
 #pragma unroll
     for (int k = 0; k < NK; k++) {
       const int64_t have = ld_relaxed_s64(&t.keys[(size_t)pos * NK + k + dep]);
-#else
-    __threadfence();
-    bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
-#pragma unroll
-    for (int k = 0; k < NK; k++) {
-      const int64_t have = *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]);
-#endif
       if ((STRMASK >> k) & 1u) same = same && (have == kc[k] || (have && kc[k] && str_eq_recs(reinterpret_cast<const uint8_t*>(have), reinterpret_cast<const uint8_t*>(kc[k]))));
       else same = same && have == kc[k];
     }
     if (same) return pos;
   }
   atomicExch(t.overflow, 1u);
-  return -1;
-}
-
-// ---- MODE_HASH front table: a small open-addressing table per CTA in SHARED memory.  A group-by with few thousand groups
-// otherwise sends every row to the same few global-memory lines (probe + NSLOT atomics that bounce between SMs: 200 GB/s in
-// profiles/r02_modes_ncu.txt); here the rows of a CTA meet in its own shared memory and the CTA merges its table into the
-// global one once, at the end.  Layout: [state u32 x cap][knull u32 x cap][keys i64 x cap*NK][vals u64 x cap*NSLOT][count u32].
-// When the table is 3/4 full the CTA stops inserting into it (high-cardinality keys go straight to the global table).
-template <int NK, int NSLOT>
-struct FrontTable {
-  uint32_t* state; uint32_t* knull; int64_t* keys; uint64_t* vals; uint32_t* count; uint32_t cap;
-  __device__ __forceinline__ void bind(uint8_t* base, uint32_t c) {
-    cap = c;
-    state = reinterpret_cast<uint32_t*>(base);
-    knull = state + c;
-    keys = reinterpret_cast<int64_t*>(knull + c);
-    vals = reinterpret_cast<uint64_t*>(keys + (size_t)c * NK);
-    count = reinterpret_cast<uint32_t*>(vals + (size_t)c * NSLOT);
-  }
-  static __host__ __device__ constexpr size_t bytes(size_t c) { return c * (8 + 8 * (size_t)NK + 8 * (size_t)NSLOT) + 16; }
-};
-template <int NK, int NSLOT, uint32_t STRMASK>
-__device__ __forceinline__ int front_find_or_insert(const FrontTable<NK, NSLOT>& t, const int64_t* kc, uint32_t knull) {
-  uint64_t h = 0x2545f4914f6cdd1dull ^ knull;
-#pragma unroll
-  for (int k = 0; k < NK; k++) {
-    if ((STRMASK >> k) & 1u) h = hash_mix64(h, kc[k] ? str_hash_rec(reinterpret_cast<const uint8_t*>(kc[k])) : 0ull);
-    else h = hash_mix64(h, (uint64_t)kc[k]);
-  }
-  const uint32_t mask = t.cap - 1u;
-  uint32_t pos = (uint32_t)(h >> 20) & mask;   // (other bits than the global table's: no correlated clustering)
-  for (int probe = 0; probe < 16; probe++, pos = (pos + 1u) & mask) {
-    uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);
-    if (st == 0u) {
-      if (*reinterpret_cast<volatile uint32_t*>(t.count) >= t.cap - (t.cap >> 2)) return -1;   // 3/4 full: the caller goes global
-      st = atomicCAS(&t.state[pos], 0u, 1u);
-      if (st == 0u) {
-#pragma unroll
-        for (int k = 0; k < NK; k++) t.keys[(size_t)pos * NK + k] = kc[k];
-        t.knull[pos] = knull;
-        __threadfence_block();
-        *reinterpret_cast<volatile uint32_t*>(&t.state[pos]) = 2u;
-        atomicAdd(t.count, 1u);
-        return (int)pos;
-      }
-    }
-    while (st == 1u) st = *reinterpret_cast<volatile uint32_t*>(&t.state[pos]);   // writer (same CTA) in flight
-    __threadfence_block();
-    bool same = *reinterpret_cast<volatile uint32_t*>(&t.knull[pos]) == knull;
-#pragma unroll
-    for (int k = 0; k < NK; k++) {
-      const int64_t have = *reinterpret_cast<volatile int64_t*>(&t.keys[(size_t)pos * NK + k]);
-      if ((STRMASK >> k) & 1u) same = same && (have == kc[k] || (have && kc[k] && str_eq_recs(reinterpret_cast<const uint8_t*>(have), reinterpret_cast<const uint8_t*>(kc[k]))));
-      else same = same && have == kc[k];
-    }
-    if (same) return (int)pos;
-  }
   return -1;
 }
 
@@ -755,20 +685,6 @@ __device__ __forceinline__ void verify_all(const AllCols<PLAN, Seq<Cs...>>& a, c
   }
   (void)dummy;
 }
-template <class PLAN, int C>
-__device__ __forceinline__ unsigned long long regs_xor_col(const ColRegs<PLAN, C>& a) {
-  unsigned long long x = 0;
-#pragma unroll
-  for (int r = 0; r < PLAN::RPT; r++) { unsigned long long y = 0; memcpy(&y, &a.v[r], sizeof(a.v[r])); x ^= y; }
-  return x;
-}
-template <class PLAN, int... Cs>
-__device__ __forceinline__ unsigned long long regs_xor(const AllCols<PLAN, Seq<Cs...>>& a, Seq<Cs...>) {
-  unsigned long long x = 0;
-  int dummy[] = {0, (x ^= regs_xor_col<PLAN, Cs>(static_cast<const ColRegs<PLAN, Cs>&>(a)), 0)...};
-  (void)dummy;
-  return x;
-}
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void clear_upd_bits(const DevBatch<PLAN::NC>& b, TileSmem<PLAN>& sm, Seq<Cs...>) {
   const int tid = threadIdx.x;
@@ -1092,7 +1008,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   const int nstages = args.nstages;
   if (PLAN::STAGES > 0) {
     if (tid == 0) {
-      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], SD_EXP_RING == 2 ? THREADS : THREADS / 32); }
+      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], THREADS / 32); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // all THREADS + 32 threads: the only CTA-wide barrier the producer warp joins
@@ -1118,9 +1034,6 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
             const int64_t tile_start = (int64_t)tile * TILE_ROWS;
             const int rows = min(TILE_ROWS, num_rows - (int)tile_start);
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-#if defined(SD_EXP_PROD) && SD_EXP_PROD == 1
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
             issue_tile_copies<PLAN>(pc, c16, tile_start, rows, ring + (size_t)stage * StageInfo<PLAN>::BYTES, &full_bar[stage], ColSeq());
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
@@ -1132,9 +1045,6 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   int c_stage = 0;
   uint32_t c_phase = 0;
   int c_hint = -1;
-#if SD_EXP_RING == 5
-  uint64_t* rel_bar = nullptr;
-#endif
 
   // ---- accumulator init -------------------------------------------------------------------------
   uint64_t acc[NSLOT > 0 ? NSLOT : 1];
@@ -1148,16 +1058,6 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   } else if (PLAN::MODE == MODE_NOKEY) {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) acc[s] = slot_identity(PLAN::slot_op(s));
-  } else if (PLAN::MODE == MODE_HASH && args.hash_smem_cap > 0) {
-    FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
-    ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
-    for (uint32_t e = tid; e < ft.cap; e += THREADS) {
-      ft.state[e] = 0u;
-#pragma unroll
-      for (int s2 = 0; s2 < NSLOT; s2++) ft.vals[(size_t)e * NSLOT + s2] = slot_identity(PLAN::slot_op(s2));
-    }
-    if (tid == 0) *ft.count = 0u;
-    consumer_sync();
   } else if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
     // nothing per CTA: the table / output buffer is global
   } else if (args.table_mode == TABLE_PRIVATE) {
@@ -1207,25 +1107,16 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
           mbar_wait(&full_bar[c_stage], c_phase);   // (the NULL-aware loads derive their word prefixes per warp: no barrier here)
           if (with_nulls) load_all_staged_nulls<PLAN>(b, c16, tile_start, sm, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
           else load_all_staged<PLAN>(c16, ring + (size_t)c_stage * StageInfo<PLAN>::BYTES, regs, ColSeq());
-#if SD_EXP_RING == 2
-          mbar_arrive(&empty_bar[c_stage]);                        // every thread releases for itself (barrier counts THREADS arrivals)
-#elif SD_EXP_RING == 5
-          if (rel_bar) { __syncwarp(); if ((tid & 31) == 0) mbar_arrive(rel_bar); }   // the PREVIOUS tile's stage: released one tile late
-          rel_bar = &empty_bar[c_stage];
-#else
-#if SD_EXP_RING == 1
-          __threadfence_block();                                   // this lane's stage loads are performed ...
-#elif SD_EXP_RING == 3
-          {   // an instruction that needs every loaded value executes before the release
-            const unsigned long long x = regs_xor<PLAN>(regs, ColSeq());
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u64 p, %0, 0x5bd1e9955bd1e995;\n\t@p nanosleep.u32 1;\n\t}" ::"l"(x) : "memory");
-          }
-#elif SD_EXP_RING == 4
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
+          // The rows of this tile are in registers now: release the stage.  The stage was read through the GENERIC proxy (ld.shared)
+          // and will be refilled through the ASYNC proxy (cp.async.bulk): the mbarrier alone does not order the two (PTX ISA, "async
+          // proxy": accesses to the same location across proxies need a cross-proxy fence).  Without the fence a refill can land
+          // while loads issued before the release are still pending -- seen when the LSU is busy with a hash plan's global
+          // atomics: ~1 % of the staged values then belong to the stage's NEXT tile (profiles/r02_ring_proxy_fence.txt).
+#ifndef SD_EXP_NO_PROXY_FENCE   // (diagnostic builds reproduce the failure with -DSD_EXP_NO_PROXY_FENCE)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
           __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);   // ... this warp holds its rows in registers now
-#endif
+          if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);
 #if SD_EXP_VERIFY
           if (!with_nulls) {
             AllCols<PLAN, ColSeq> chk;
@@ -1320,17 +1211,6 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
             int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
             uint32_t knull = 0;
             PLAN::keys(row, ctx, kc, knull);
-            if (args.hash_smem_cap > 0) {   // the CTA's own shared-memory table first
-              FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
-              ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
-              const int fe = front_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1), PLAN::STRKEYMASK>(ft, kc, knull);
-              if (fe >= 0) {
-                uint64_t* t = ft.vals + (size_t)fe * NSLOT;
-#pragma unroll
-                for (int s = 0; s < NSLOT; s++) slot_atomic(PLAN::slot_op(s), t + s, sv[s]);
-                continue;
-              }
-            }
             const int64_t e = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), PLAN::STRKEYMASK>(args.hash, kc, knull);
             if (e >= 0) {
               uint64_t* t = args.hash.vals + (size_t)e * NSLOT;
@@ -1368,26 +1248,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   consumer_sync();
   uint64_t* my_partials = args.partials + (size_t)blockIdx.x * NE;
   const int lane = tid & 31, warp = tid >> 5;
-  if (PLAN::MODE == MODE_HASH && args.hash_smem_cap > 0) {
-    // the CTA's front table -> the global table (one find-or-insert + NSLOT atomics per group this CTA has seen)
-    FrontTable<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), (NSLOT > 0 ? NSLOT : 1)> ft;
-    ft.bind(reinterpret_cast<uint8_t*>(table), (uint32_t)args.hash_smem_cap);
-    for (uint32_t e = tid; e < ft.cap; e += THREADS) {
-      if (ft.state[e] != 2u) continue;
-      int64_t kc[PLAN::NKEYS > 0 ? PLAN::NKEYS : 1];
-#pragma unroll
-      for (int k = 0; k < (PLAN::NKEYS > 0 ? PLAN::NKEYS : 1); k++) kc[k] = ft.keys[(size_t)e * (PLAN::NKEYS > 0 ? PLAN::NKEYS : 1) + k];
-      const int64_t g = hash_find_or_insert<(PLAN::NKEYS > 0 ? PLAN::NKEYS : 1), PLAN::STRKEYMASK>(args.hash, kc, ft.knull[e]);
-      if (g >= 0) {
-        uint64_t* t = args.hash.vals + (size_t)g * NSLOT;
-#pragma unroll
-        for (int s = 0; s < NSLOT; s++) {
-          const uint64_t v = ft.vals[(size_t)e * NSLOT + s];
-          if (v != slot_identity(PLAN::slot_op(s))) slot_atomic(PLAN::slot_op(s), t + s, v);
-        }
-      }
-    }
-  } else if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
+  if (PLAN::MODE == MODE_HASH || PLAN::MODE == MODE_PROJECT) {
     // results live in the global hash table / the output record buffer
   } else if (PLAN::MODE == MODE_NOKEY) {
     uint64_t* scratch = table;   // [NSLOT][THREADS/32]

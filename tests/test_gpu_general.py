@@ -460,34 +460,6 @@ def test_high_cardinality_group_by_grows_the_hash_table(gpu_api):
     assert_rowsets_match(gp.finish(), got, 1)
 
 
-@pytest.mark.parametrize("front", [True, False])
-@pytest.mark.parametrize("ngroups", [300, 7000])
-def test_hash_group_by_front_table_on_and_off(gpu_api, ngroups, front, monkeypatch):
-    """MODE_HASH with the per-CTA shared-memory front table (sd_kernels.cuh FrontTable) and without it: fewer groups than the
-    front table holds (every row meets in shared memory) and more (the table fills, later keys go to the global table and the
-    same key can live in both until the end-of-kernel merge).  Nullable key, every kind of slot."""
-    if front:
-        monkeypatch.delenv("SD_TUNE_NO_FRONT_TABLE", raising=False)
-    else:
-        monkeypatch.setenv("SD_TUNE_NO_FRONT_TABLE", "1")
-    r = np.random.default_rng(ngroups)
-    n = 150_000
-    schema = [("k", T.INT, True), ("k2", T.LONG, False), ("v", T.DOUBLE, True), ("w", T.INT, False)]
-    bs = []
-    for i in range(2):
-        kk = r.integers(0, ngroups, n).astype(np.int32)
-        v = r.normal(0, 5, n)
-        v[r.integers(0, n, 5)] = np.nan
-        data = {"k": kk, "k2": (kk % 3).astype(np.int64) - 1, "v": v, "w": r.integers(-50, 50, n).astype(np.int32)}
-        bs.append(build_batch(n, schema, data, {"k": r.random(n) < 0.02, "v": r.random(n) < 0.1}, batch_id=i))
-    b = PlanBuilder()
-    k, k2, v, w = b.col(T.INT, 0, True), b.col(T.LONG, 1, False), b.col(T.DOUBLE, 2, True), b.col(T.INT, 3, False)
-    b.group_by(k, k2)
-    b.count().sum(v).avg(w).min(v).max(v).min(w).max(w).count(v)
-    gp, _, got = both(gpu_api, b.build(), [], bs, 2)
-    assert len(got) >= ngroups
-
-
 # ---- MODE_PROJECT: filter + project, no aggregate (BASELINE.json configs[3], SURVEY.md 8d C4) -----------
 def _rowkey(r):
     return tuple((0, 0) if v is None else (1, v) if isinstance(v, bytes) else (2, float(v)) for v in r)

@@ -1,5 +1,6 @@
 """Diagnostic (round 2): MODE_HASH group-by l_shipdate over generated lineitem, EVERY group compared with numpy.
-usage: python tools/hash_diag.py <nbatches> <repeats>      env: SD_TUNE_NO_FRONT_TABLE, SD_TUNE_NSTAGES ..."""
+usage: python tools/hash_diag.py <nbatches> <repeats>      env: SD_TUNE_NSTAGES, SD_JIT_DEFINES (-DSD_EXP_VERIFY=1 with SD_DEBUG_VERIFY=1:
+staged tiles against global memory; -DSD_EXP_NO_PROXY_FENCE: the release without the generic->async proxy fence) ..."""
 import os
 import sys
 
@@ -30,7 +31,7 @@ b = PlanBuilder()
 ship, qty, price = b.col(T.DATE, P.L_SHIPDATE), b.col(T.DOUBLE, P.L_QUANTITY), b.col(T.DOUBLE, P.L_EXTENDEDPRICE)
 b.group_by(ship); b.count().sum(qty).sum(price)
 gp = capi.Plan(api, b.build())
-tag = "front=%s nstages=%s NB=%d" % ("off" if os.environ.get("SD_TUNE_NO_FRONT_TABLE") else "on", os.environ.get("SD_TUNE_NSTAGES", "-"), NB)
+tag = "defines=[%s] nstages=%s NB=%d" % (os.environ.get("SD_JIT_DEFINES", ""), os.environ.get("SD_TUNE_NSTAGES", "-"), NB)
 for it in range(REP):
     gp.reset().set_literals([])
     gp.scan_store(store)

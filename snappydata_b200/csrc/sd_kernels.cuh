@@ -1008,7 +1008,13 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   const int nstages = args.nstages;
   if (PLAN::STAGES > 0) {
     if (tid == 0) {
-      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], THREADS / 32); }
+      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); 
+#ifdef SD_EXP_ARRIVE_ALL
+        mbar_init(&empty_bar[i], THREADS); }
+#else
+        mbar_init(&empty_bar[i], THREADS / 32); }
+#endif
+
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // all THREADS + 32 threads: the only CTA-wide barrier the producer warp joins
@@ -1115,8 +1121,12 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 #ifndef SD_EXP_NO_PROXY_FENCE   // (diagnostic builds reproduce the failure with -DSD_EXP_NO_PROXY_FENCE)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
+#ifdef SD_EXP_ARRIVE_ALL   // every thread releases for itself (the empty barrier then counts THREADS arrivals)
+          mbar_arrive(&empty_bar[c_stage]);
+#else
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);
+#endif
 #if SD_EXP_VERIFY
           if (!with_nulls) {
             AllCols<PLAN, ColSeq> chk;

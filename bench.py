@@ -785,7 +785,7 @@ def main():
             out["also_c5"] = workloads.run_c5(api, torch, local_rank, args.steps, args.warmup, peak)
             parity_failed = parity_failed or not out["also_c5"]["parity_check"]["ok"]
     if comm is not None:
-        out["exchange"] = dict(comm.info(), kind="sd_plan_exchange: ncclAllGather of partial rows by value inside libsnappygpu.so + merge on every rank")
+        out["exchange"] = dict(comm.info(), kind="sd_plan_exchange inside libsnappygpu.so: one ncclAllGather per query of every rank's key dictionaries + raw device state (dense plans; partial rows otherwise), merged on every rank")
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

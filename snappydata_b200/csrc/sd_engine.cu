@@ -2196,6 +2196,25 @@ int sd_comm_info(sd_comm* c, int64_t out[4]) {
 // The sender queues header H2D + a device-to-device copy of the state + the all-gather behind its scan kernel and meets the
 // result with ONE synchronisation: no read-back of its own state, no row building, no second upload before the collective
 // (the by-value form below needs all three).  Receivers turn each rank's state into partial rows with that rank's dictionaries.
+// averaged host-side laps of the per-query path (SD_DEBUG_TIMING=1; printed every 64 calls)
+struct LapStats {
+  static constexpr int N = 8;
+  double sum[N] = {0}; int64_t calls = 0; const char* names[N] = {nullptr};
+  std::chrono::steady_clock::time_point t0;
+  bool on = getenv("SD_DEBUG_TIMING") != nullptr;
+  void begin() { if (on) t0 = std::chrono::steady_clock::now(); }
+  void lap(int i, const char* name) {
+    if (!on) return;
+    const auto t = std::chrono::steady_clock::now();
+    sum[i] += std::chrono::duration<double, std::micro>(t - t0).count(); names[i] = name; t0 = t;
+  }
+  void end(const char* what, int rank) {
+    if (!on || (++calls % 64) != 0) return;
+    fprintf(stderr, "[%s rank %d] avg us over %lld calls:", what, rank, (long long)calls);
+    for (int i = 0; i < N; i++) if (names[i]) fprintf(stderr, "  %s %.1f", names[i], sum[i] / (double)calls);
+    fprintf(stderr, "\n");
+  }
+};
 static bool dense_exchange_eligible(const sd_plan* p) {
   if (getenv("SD_TUNE_EXCHANGE_ROWS")) return false;
   const PlanSpec& sp = p->spec;
@@ -2208,6 +2227,8 @@ static bool dense_exchange_eligible(const sd_plan* p) {
 int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   if (!p || !c) return set_error(SD_ERR_INVALID, "sd_plan_exchange: null argument");
   if (c->device != p->device) return set_error(SD_ERR_INVALID, "communicator lives on device %d, plan on %d", c->device, p->device);
+  static thread_local LapStats laps;
+  laps.begin();
   int rc = launch_what_is_pending(p);
   if (rc) return rc;
   const PlanSpec& sp = p->spec;
@@ -2259,10 +2280,13 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
       if (sent) memcpy(c->h_send + 16, mine.data(), sent);
       SD_CUDA(cudaMemcpyAsync(c->d_send, c->h_send, 16 + sent, cudaMemcpyHostToDevice, p->stream));
     }
+    laps.lap(0, "prepare+copies");
     rc = comm_all_gather_bytes(c->nccl, c->d_send, c->d_recv, c->cap, p->stream);
     if (rc) return rc;
     SD_CUDA(cudaMemcpyAsync(c->h_recv, c->d_recv, c->cap * (size_t)c->world, cudaMemcpyDeviceToHost, p->stream));
+    laps.lap(1, "enqueue-allgather");
     SD_CUDA(cudaStreamSynchronize(p->stream));
+    laps.lap(2, "wait(kernel+allgather+d2h)");
     c->exchanges++;
     size_t maxlen = 0;
     for (int r = 0; r < c->world; r++) {
@@ -2320,6 +2344,7 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
       p->metrics[0] = nr;
     }
   }
+  laps.lap(3, "decode-blobs");
   std::vector<uint8_t> merged;
   int64_t nrows = 0;
   rc = merge_rows_impl(p->spec, all.data(), (int64_t)all.size(), false, merged, &nrows);
@@ -2327,6 +2352,8 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
   p->finished_rows.swap(merged);
   p->finished_nrows = nrows;
   p->dev_rows_len = -1;
+  laps.lap(4, "merge");
+  laps.end("sd_plan_exchange", c->rank);
   return 0;
 }
 
@@ -2335,13 +2362,21 @@ int sd_plan_exchange(sd_plan* p, sd_comm* c) {
 // reference (SnappySession plan cache: new literal values, same generated code).
 int sd_plan_execute_store(sd_plan* p, sd_store* s, const int32_t* bucket_ids, int32_t nbuckets, const sd_literal* lits, int32_t nlits,
                           sd_comm* comm, void* out_rows, int64_t cap, int64_t* out_len, int64_t* out_nrows) {
+  static thread_local LapStats laps;
+  laps.begin();
   int rc = sd_plan_reset(p);
   if (rc) return rc;
+  laps.lap(0, "reset");
   if (lits || nlits) { rc = sd_plan_set_literals(p, lits, nlits); if (rc) return rc; }
   rc = sd_plan_scan_store(p, s, bucket_ids, nbuckets);
   if (rc) return rc;
+  laps.lap(1, "literals+scan-enqueue");
   if (comm) { rc = sd_plan_exchange(p, comm); if (rc) return rc; }
-  return sd_plan_finish(p, out_rows, cap, out_len, out_nrows);
+  laps.lap(2, "exchange");
+  rc = sd_plan_finish(p, out_rows, cap, out_len, out_nrows);
+  laps.lap(3, "finish");
+  laps.end("sd_plan_execute_store", comm ? comm->rank : 0);
+  return rc;
 }
 
 }  // extern "C"

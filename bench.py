@@ -76,7 +76,7 @@ def parse_args():
 def ncu_traffic_per_row(q1):
     """DRAM bytes per row of the scan kernel from the committed `ncu --set full` capture (profiles/)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["q1" if q1 else "q6"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["q1" if q1 else "q6"]
         return (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["rows"]
     except Exception:
         return None
@@ -670,7 +670,7 @@ def main():
     tpr = ncu_traffic_per_row(q1)
     out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                        "traffic": (tpr * main_run.local_rows) if tpr else None,
-                       "traffic_source": "profiles/r01_traffic.json (ncu --set full, 200M-row launch) scaled by rows", "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
+                       "traffic_source": "profiles/r02_traffic.json (ncu --set full, 200M-row launch) scaled by rows", "peak_source": peak_src, "kernel": "sd::scan_aggregate_kernel<" + main_run.plan.kernel_name() + ">",
                        "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": algo_per_launch,
                        "frac_of_nominal_7700": achieved / 7700.0,
                        "note": "per rank (rank 0); one launch scans the rank's whole shard; `peak` is a measured COPY bandwidth "

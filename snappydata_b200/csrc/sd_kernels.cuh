@@ -434,65 +434,57 @@ __device__ __noinline__ typename KindT<KIND>::T delta_value_at(const DevDelta* d
   return KIND == K_CODE ? (T)null_code : (T)0;
 }
 
-// Overlay lists (delete positions, update-delta positions) are ascending; a warp visits its 64-row segments in ascending
-// order inside a chunk, so it walks every list once, with a cursor of its own (no shared state, no CTA barrier).  The warp
-// keeps a WINDOW of a list in registers: lane i holds entry base + i (INT_MAX beyond the end).  One coalesced load per list
-// per tile -- all lists' loads are issued before any is used, so their latencies overlap -- serves both segments of the
-// tile; a window is reloaded only when a segment runs off its end (32 entries ~ 4 tiles of a typical delta).  (Before:
-// two DEPENDENT loads per list per segment, list after list: long-scoreboard was the overlay kernel's top stall.)
-struct ListWin { int32_t p; int base; };
-__device__ __forceinline__ void win_load(const int32_t* pos, int n, int base, int lane, ListWin& w) {
-  w.base = base;
-  w.p = (pos != nullptr && base + lane < n) ? __ldg(pos + base + lane) : 0x7fffffff;
-}
-// entries in [a, a + 64) -> bit mask (bit = position - a); *first = list index of the lowest one
-__device__ __forceinline__ uint64_t win_segment_mask(const int32_t* pos, int n, int32_t a, ListWin& w, int lane, int* first) {
-  while (__all_sync(0xffffffffu, w.p < a)) win_load(pos, n, w.base + 32, lane, w);   // (the sentinel ends it)
-  *first = w.base + __popc(__ballot_sync(0xffffffffu, w.p < a));
+// The entries of the ascending list `pos` that fall into the 64-row segment [a, a + 64), found by one warp on its own:
+// -> bit mask (bit = position - a) and, in *first, the list index of the lowest one; *cur is the warp's cursor into the
+// list (everything below it lies before this warp's previous segments) and is advanced past the segment.  One or two
+// coalesced 32-entry loads, ballots and warp OR-reductions; no shared memory, no barrier.
+__device__ __forceinline__ uint64_t warp_segment_mask(const int32_t* pos, int n, int32_t a, int& cur, int lane, int* first) {
+  for (;;) {   // skip what belongs to other warps' segments
+    const int idx = cur + lane;
+    const int32_t p = idx < n ? __ldg(pos + idx) : 0x7fffffff;
+    const int c = __popc(__ballot_sync(0xffffffffu, p < a));
+    cur += c;
+    if (c < 32) break;
+  }
+  *first = cur;
   uint64_t mask = 0;
   for (;;) {
-    const bool in = w.p >= a && w.p < a + 64;
-    const int bit = in ? (int)(w.p - a) : 0;
+    const int idx = cur + lane;
+    const int32_t p = idx < n ? __ldg(pos + idx) : 0x7fffffff;
+    const bool in = p < a + 64;
+    const int bit = in ? (int)(p - a) : 0;
     const unsigned lo = __reduce_or_sync(0xffffffffu, (in && bit < 32) ? (1u << bit) : 0u);
     const unsigned hi = __reduce_or_sync(0xffffffffu, (in && bit >= 32) ? (1u << (bit - 32)) : 0u);
     mask |= (uint64_t)lo | ((uint64_t)hi << 32);
-    if (__shfl_sync(0xffffffffu, w.p, 31) >= a + 64) break;   // the window reaches past the segment (or the list has ended)
-    win_load(pos, n, w.base + 32, lane, w);
+    const int c = __popc(__ballot_sync(0xffffffffu, in));
+    cur += c;
+    if (c < 32) break;
   }
   return mask;
 }
 __device__ __noinline__ int warp_cursor_init(const int32_t* pos, int n, int32_t a) { return lower_bound_i32(pos, 0, n, a); }
 
-// phase A, per column: this warp's windows of the depth-0 / depth-1 delta positions
-template <class PLAN, int C>
-__device__ __forceinline__ void overlay_windows(const DevCol& col, int64_t tile_start, bool first_tile, const TileSmem<PLAN>& sm, ListWin (&w)[2]) {
-  const DevDelta *d0 = col.delta0, *d1 = col.delta1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t a0 = (int32_t)tile_start + warp * 64;
-  int b0 = 0, b1 = 0;
-  if (first_tile) {
-    if (d0) b0 = warp_cursor_init(d0->positions, d0->n, a0);
-    if (d1) b1 = warp_cursor_init(d1->positions, d1->n, a0);
-  } else { b0 = sm.wcur[C][warp][0]; b1 = sm.wcur[C][warp][1]; }
-  win_load(d0 ? d0->positions : nullptr, d0 ? d0->n : 0, b0, lane, w[0]);
-  win_load(d1 ? d1->positions : nullptr, d1 ? d1->n : 0, b1, lane, w[1]);
-}
-// phase B, per column: rows whose position is in the depth-0 delta take that value, else the depth-1 delta's
+// overlay of one column, per warp: rows whose position is in the depth-0 delta take that value, else the depth-1 delta's
 // (enc/UpdatedColumnDecoder.scala:95-104)
 template <class PLAN, int C>
-__device__ __forceinline__ void warp_overlay_col(const DevCol& col, int64_t tile_start, TileSmem<PLAN>& sm, ColRegs<PLAN, C>& regs, ListWin (&w)[2]) {
+__device__ __forceinline__ void warp_overlay_col(const DevCol& col, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm, ColRegs<PLAN, C>& regs) {
   typedef typename KindT<PLAN::kind(C)>::T T;
   constexpr int K = PLAN::kind(C);
   const DevDelta *d0 = col.delta0, *d1 = col.delta1;
   if (!(d0 || d1)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t a0 = (int32_t)tile_start + warp * 64;
+  int cur0 = 0, cur1 = 0;
+  if (first_tile) {
+    if (d0) cur0 = warp_cursor_init(d0->positions, d0->n, a0);
+    if (d1) cur1 = warp_cursor_init(d1->positions, d1->n, a0);
+  } else { cur0 = sm.wcur[C][warp][0]; cur1 = sm.wcur[C][warp][1]; }
 #pragma unroll
   for (int u = 0; u < PLAN::RPT / 2; u++) {
     const int32_t a = a0 + u * 2 * THREADS;
     int f0 = 0, f1 = 0;
-    const uint64_t m0 = d0 ? win_segment_mask(d0->positions, d0->n, a, w[0], lane, &f0) : 0ull;
-    const uint64_t m1 = d1 ? win_segment_mask(d1->positions, d1->n, a, w[1], lane, &f1) : 0ull;
+    const uint64_t m0 = d0 ? warp_segment_mask(d0->positions, d0->n, a, cur0, lane, &f0) : 0ull;
+    const uint64_t m1 = d1 ? warp_segment_mask(d1->positions, d1->n, a, cur1, lane, &f1) : 0ull;
     if ((m0 | m1) == 0ull) continue;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -509,34 +501,28 @@ __device__ __forceinline__ void warp_overlay_col(const DevCol& col, int64_t tile
     }
   }
   __syncwarp();
-  if (lane == 0) { sm.wcur[C][warp][0] = w[0].base; sm.wcur[C][warp][1] = w[1].base; }   // (entries below the next segment are skipped by the ballot)
+  if (lane == 0) { sm.wcur[C][warp][0] = cur0; sm.wcur[C][warp][1] = cur1; }
   __syncwarp();
 }
 template <class PLAN, int... Cs>
 __device__ __forceinline__ void warp_overlay_all(const DevBatch<PLAN::NC>& b, int64_t tile_start, bool first_tile, TileSmem<PLAN>& sm,
                                                  AllCols<PLAN, Seq<Cs...>>& regs, uint32_t& live, Seq<Cs...>) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t a0 = (int32_t)tile_start + warp * 64;
-  // phase A: every list's window (independent loads, in flight together)
-  ListWin wd;
-  win_load(b.deletes, b.deletes ? b.num_deletes : 0, b.deletes ? (first_tile ? warp_cursor_init(b.deletes, b.num_deletes, a0) : sm.wdel[warp]) : 0, lane, wd);
-  ListWin wc[PLAN::NC > 0 ? PLAN::NC : 1][2];
-  int dummy0[] = {0, (overlay_windows<PLAN, Cs>(b.cols[Cs], tile_start, first_tile, sm, wc[Cs]), 0)...};
-  (void)dummy0;
-  // phase B
   if (b.deletes) {   // delete mask (enc/ColumnDeleteDecoder.scala:49-55)
+    const int32_t a0 = (int32_t)tile_start + warp * 64;
+    int cur = first_tile ? warp_cursor_init(b.deletes, b.num_deletes, a0) : sm.wdel[warp];
 #pragma unroll
     for (int u = 0; u < PLAN::RPT / 2; u++) {
       int f;
-      const uint64_t m = win_segment_mask(b.deletes, b.num_deletes, a0 + u * 2 * THREADS, wd, lane, &f);
+      const uint64_t m = warp_segment_mask(b.deletes, b.num_deletes, a0 + u * 2 * THREADS, cur, lane, &f);
       if ((m >> (2 * lane)) & 1ull) live &= ~(1u << (2 * u));
       if ((m >> (2 * lane + 1)) & 1ull) live &= ~(1u << (2 * u + 1));
     }
     __syncwarp();
-    if (lane == 0) sm.wdel[warp] = wd.base;
+    if (lane == 0) sm.wdel[warp] = cur;
     __syncwarp();
   }
-  int dummy[] = {0, (warp_overlay_col<PLAN, Cs>(b.cols[Cs], tile_start, sm, static_cast<ColRegs<PLAN, Cs>&>(regs), wc[Cs]), 0)...};
+  int dummy[] = {0, (warp_overlay_col<PLAN, Cs>(b.cols[Cs], tile_start, first_tile, sm, static_cast<ColRegs<PLAN, Cs>&>(regs)), 0)...};
   (void)dummy;
 }
 
@@ -1022,12 +1008,7 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
   const int nstages = args.nstages;
   if (PLAN::STAGES > 0) {
     if (tid == 0) {
-      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); 
-#ifdef SD_EXP_ARRIVE_ALL
-        mbar_init(&empty_bar[i], THREADS); }
-#else
-        mbar_init(&empty_bar[i], THREADS / 32); }
-#endif
+      for (int i = 0; i < nstages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], THREADS / 32); }
 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1135,12 +1116,8 @@ __global__ void __launch_bounds__(THREADS + (PLAN::STAGES > 0 ? 32 : 0), PLAN::M
 #ifndef SD_EXP_NO_PROXY_FENCE   // (diagnostic builds reproduce the failure with -DSD_EXP_NO_PROXY_FENCE)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
-#ifdef SD_EXP_ARRIVE_ALL   // every thread releases for itself (the empty barrier then counts THREADS arrivals)
-          mbar_arrive(&empty_bar[c_stage]);
-#else
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[c_stage]);
-#endif
 #if SD_EXP_VERIFY
           if (!with_nulls) {
             AllCols<PLAN, ColSeq> chk;

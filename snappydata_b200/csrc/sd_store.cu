@@ -527,6 +527,10 @@ int store_flush_lz4(sd_store* s) {
   if (const char* e = getenv("SD_TUNE_LZ4_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= sd_store::LZ4_STREAMS) nstreams = v; }
   const int k = s->lz4_next++ % nstreams;
   SD_CUDA(cudaStreamWaitEvent(s->lz4_streams[k], s->lz4_copied, 0));
+  for (int q = 0; q + 1 < s->num_copy_streams; q++) {   // ... and over the extra copy queues
+    SD_CUDA(cudaEventRecord(s->extra_done[q], s->extra_streams[q]));
+    SD_CUDA(cudaStreamWaitEvent(s->lz4_streams[k], s->extra_done[q], 0));
+  }
   int rc = lz4_launch(s->lz4_streams[k], reinterpret_cast<const Lz4Job*>(d_jobs), (int)s->pending_lz4.size(), s->d_lz4_error);
   if (rc) return rc;
   SD_CUDA(cudaEventRecord(s->lz4_done[k], s->lz4_streams[k]));
@@ -583,7 +587,12 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
       const size_t span = (size_t)(hi - lo);
       uint8_t* d0 = s->lz4_stage.alloc(span + 64, 16, (16 - (reinterpret_cast<uintptr_t>(lo) & 15)) & 15);   // same residue mod 16 as the host span
       if (!d0) return SD_ERR_CUDA;
-      SD_CUDA(cudaMemcpyAsync(d0, lo, span, cudaMemcpyHostToDevice, s->copy_stream));
+      cudaStream_t st = s->copy_stream;
+      if (s->num_copy_streams > 1) {   // SD_TUNE_COPY_STREAMS: span copies rotate over several H2D queues (a copy's setup hides under its neighbour)
+        const int k = s->next_stream++ % s->num_copy_streams;
+        if (k > 0) st = s->extra_streams[k - 1];
+      }
+      SD_CUDA(cudaMemcpyAsync(d0, lo, span, cudaMemcpyHostToDevice, st));
       s->h2d_bytes += (int64_t)span;
       s->span_h0 = lo; s->span_d0 = d0; s->span_len = span;
     }

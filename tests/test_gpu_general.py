@@ -394,8 +394,15 @@ def _rowkey2(r):
                  else (3, struct.pack("<q", int(v))) for v in r)
 
 
-def test_lz4_lineitem_q1_q6(gpu_api):
+@pytest.mark.parametrize("copy_streams", [1, 3])
+def test_lz4_lineitem_q1_q6(gpu_api, copy_streams, monkeypatch):
+    """(copy_streams > 1: SD_TUNE_COPY_STREAMS -- the batches' compressed spans rotate over several H2D queues and the expansion
+    waits for all of them)"""
     from snappydata_b200 import lineitem, plan as P
+    if copy_streams > 1:
+        monkeypatch.setenv("SD_TUNE_COPY_STREAMS", str(copy_streams))
+    else:
+        monkeypatch.delenv("SD_TUNE_COPY_STREAMS", raising=False)
     plain = lineitem.gen_table(260_001, 65_000, seed=21)
     for desc, lits, nk in ((P.q6_plan(), P.Q6_LITERALS, 0), (P.q1_plan(), P.Q1_LITERALS, 2)):
         op = oracle.plan(desc).set_literals(lits)

@@ -1814,8 +1814,6 @@ int sd_plan_reset(sd_plan* p) {
     for (int k = 0; k + 1 < p->priv->num_copy_streams; k++) cudaStreamSynchronize(p->priv->extra_streams[k]);
     p->priv->batches.clear(); p->priv->arena.reset(); p->priv->version++; p->priv->h2d_bytes = 0;
     p->priv->pending_lz4.clear();
-    p->priv->win_h0 = nullptr; p->priv->win_d0 = nullptr; p->priv->win_cap = p->priv->win_len = 0;   // an un-issued copy window dies with the execution
-    p->priv->last_span_end = nullptr;
     store_lz4_check(p->priv);   // waits for queued expansions (their result is being discarded) and releases the staging
     p->priv->lz4_stage.reset();
   }

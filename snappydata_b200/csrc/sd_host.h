@@ -198,12 +198,6 @@ struct sd_store {
   int lz4_next = 0;
   // compressed payloads of one batch that lie (almost) back to back in host memory travel as ONE copy
   const uint8_t* span_h0 = nullptr; uint8_t* span_d0 = nullptr; size_t span_len = 0;
-  // RETAINED buffers only: consecutive batches whose compressed spans are contiguous in host memory (arena-allocated region
-  // memory) share ONE host->device copy -- the window [win_h0, win_h0 + win_len) is copied to win_d0 when it closes (a span
-  // that does not continue it, the window's capacity, or the next LZ4 flush).  ~3.7 MB copies reach ~46 GB/s on this link,
-  // 15 MB ones ~52 (profiles/r02_lz4.txt)
-  const uint8_t* win_h0 = nullptr; uint8_t* win_d0 = nullptr; size_t win_cap = 0, win_len = 0;
-  const uint8_t* last_span_end = nullptr; bool adjacent_spans = false;
   sd::PinnedArena lz4_jobs_host;
   sd::PinnedArena enc_host;        // sd_encode.cu: prefixes / descriptors on their way to the device
   std::mutex enc_mu;               // one encoder at a time per store; `mu` is taken only to lay the buffers out and to publish

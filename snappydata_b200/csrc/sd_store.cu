@@ -503,18 +503,9 @@ int store_register_encoded(sd_store* s, const uint8_t* prefix, int64_t prefix_le
   return upload_column(s, prefix, prefix_len, type, nullable, num_rows, c, total_len);
 }
 
-// issue the copy of the open coalescing window (sd_host.h: win_*), if any
-static int store_flush_window(sd_store* s) {
-  if (!s->win_h0) return 0;
-  SD_CUDA(cudaMemcpyAsync(s->win_d0, s->win_h0, s->win_len, cudaMemcpyHostToDevice, s->copy_stream));
-  s->h2d_bytes += (int64_t)s->win_len;
-  s->win_h0 = nullptr; s->win_d0 = nullptr; s->win_cap = s->win_len = 0;
-  return 0;
-}
 int store_flush_lz4(sd_store* s) {
   if (s->pending_lz4.empty()) return 0;
   SD_CUDA(cudaSetDevice(s->device));
-  { int rcw = store_flush_window(s); if (rcw) return rcw; }   // the payloads of the queued jobs must be on their way first
   if (!s->d_lz4_error) {
     SD_CUDA(cudaMalloc(&s->d_lz4_error, 64));
     SD_CUDA(cudaMemset(s->d_lz4_error, 0, 64));
@@ -563,10 +554,7 @@ int store_lz4_check(sd_store* s) {
     if (s->lz4_used[k]) { SD_CUDA(cudaStreamSynchronize(s->lz4_streams[k])); s->lz4_used[k] = false; }
   unsigned int err = 0;
   SD_CUDA(cudaMemcpy(&err, s->d_lz4_error, 4, cudaMemcpyDeviceToHost));
-  if (s->pending_lz4.empty()) {   // nothing refers to the staged payloads any more (an open copy window without jobs has no reader either)
-    s->win_h0 = nullptr; s->win_d0 = nullptr; s->win_cap = s->win_len = 0;
-    s->lz4_stage.reset(); s->lz4_jobs_host.reset();
-  }
+  if (s->pending_lz4.empty()) { s->lz4_stage.reset(); s->lz4_jobs_host.reset(); }   // nothing refers to the staged payloads any more
   if (err) {
     SD_CUDA(cudaMemset(s->d_lz4_error, 0, 4));
     return set_error(SD_ERR_INVALID, "corrupt LZ4 payload in a column buffer (device decode failed)");
@@ -597,23 +585,6 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
     }
     if (cnt >= 2 && (size_t)(hi - lo) <= sum + sum / 8 + 4096) {
       const size_t span = (size_t)(hi - lo);
-      if (s->retain_buffers && s->num_copy_streams == 1 && !getenv("SD_TUNE_NO_COPY_WINDOW")) {
-        uint8_t* d0;
-        if (s->win_h0 && lo >= s->win_h0 + s->win_len && (size_t)(lo - (s->win_h0 + s->win_len)) < 64 && (size_t)(hi - s->win_h0) <= s->win_cap) {
-          d0 = s->win_d0 + (lo - s->win_h0);             // continues the open window: same host -> device offset
-          s->win_len = (size_t)(hi - s->win_h0);
-        } else {
-          int rcw = store_flush_window(s);
-          if (rcw) return rcw;
-          if (s->last_span_end && lo >= s->last_span_end && (size_t)(lo - s->last_span_end) < 64) s->adjacent_spans = true;   // the caller's buffers ARE laid out back to back
-          const size_t cap = s->adjacent_spans ? std::max<size_t>(span, size_t(16) << 20) : span;
-          d0 = s->lz4_stage.alloc(cap + 64, 16, (16 - (reinterpret_cast<uintptr_t>(lo) & 15)) & 15);   // same residue mod 16 as the host span
-          if (!d0) return SD_ERR_CUDA;
-          s->win_h0 = lo; s->win_d0 = d0; s->win_cap = cap; s->win_len = span;
-        }
-        s->last_span_end = hi;
-        s->span_h0 = lo; s->span_d0 = d0; s->span_len = span;
-      } else {
       uint8_t* d0 = s->lz4_stage.alloc(span + 64, 16, (16 - (reinterpret_cast<uintptr_t>(lo) & 15)) & 15);   // same residue mod 16 as the host span
       if (!d0) return SD_ERR_CUDA;
       cudaStream_t st = s->copy_stream;
@@ -624,7 +595,6 @@ int store_put(sd_store* s, const sd_batch* b, const int32_t* table_ordinals) {
       SD_CUDA(cudaMemcpyAsync(d0, lo, span, cudaMemcpyHostToDevice, st));
       s->h2d_bytes += (int64_t)span;
       s->span_h0 = lo; s->span_d0 = d0; s->span_len = span;
-      }
     }
   }
   for (int i = 0; i < b->ncols; i++) {

@@ -37,6 +37,7 @@ struct JNINativeInterface_ {
   jint* (*GetIntArrayElements)(JNIEnv*, jintArray, jboolean*);
   void (*ReleaseIntArrayElements)(JNIEnv*, jintArray, jint*, jint);
   void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
+  void (*SetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, const jbyte*);
   void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jsize, jsize, const jlong*);
 };
 #endif

@@ -117,14 +117,15 @@ static int family_resolve(JNIEnv* env, const col_family* f, int n, const void** 
   return 0;
 }
 
-JNIEXPORT void JNICALL JFN(batchSubmit)(JNIEnv* env, jobject self, jlong plan, jint numRows, jint nCols,
+/* One ColumnBatch from the JVM -> sd_batch -> sd_batch_submit (to_store == 0: `handle` is an sd_plan) or sd_store_put_batch
+ * (to_store != 0: `handle` is an sd_store; the batch becomes resident). */
+static void do_batch(JNIEnv* env, int to_store, jlong handle, jint numRows, jint nCols,
     jlongArray colAddrs, jlongArray colLens, jobjectArray heapCols, jintArray heapOffsets,
     jlongArray delta0Addrs, jlongArray delta0Lens, jobjectArray delta0Heap, jintArray delta0Offsets,
     jlongArray delta1Addrs, jlongArray delta1Lens, jobjectArray delta1Heap, jintArray delta1Offsets,
     jlong deleteAddr, jlong deleteLen, jbyteArray deleteHeap, jint deleteOffset,
     jlong statsAddr, jlong statsLen, jbyteArray statsHeap, jint statsOffset, jint statsNCols,
     jint bucketId, jlong batchId) {
-  (void)self;
   const void* cols[MAXC]; const void* d0[MAXC]; const void* d1[MAXC];
   int64_t lens[MAXC], d0l[MAXC], d1l[MAXC];
   if (nCols < 0 || nCols > MAXC) { throw_msg(env, "java/lang/IllegalArgumentException", "batchSubmit: 0 <= nCols <= 256"); return; }
@@ -169,7 +170,7 @@ JNIEXPORT void JNICALL JFN(batchSubmit)(JNIEnv* env, jobject self, jlong plan, j
     b.stats_len = b.stats_row ? statsLen : 0;
     b.stats_ncols = statsNCols; b.bucket_id = bucketId; b.batch_id = batchId;
     /* every Java array has been copied or is a direct buffer retained by the iterator: nothing is pinned from here on */
-    rc = sd_batch_submit((sd_plan*)(intptr_t)plan, &b);
+    rc = to_store ? sd_store_put_batch((sd_store*)(intptr_t)handle, &b) : sd_batch_submit((sd_plan*)(intptr_t)handle, &b);
     ok = 1;
   }
 done:
@@ -183,6 +184,94 @@ done:
   if (f1.len) (*env)->ReleaseLongArrayElements(env, delta1Lens, f1.len, JNI_ABORT);
   if (f1.off) (*env)->ReleaseIntArrayElements(env, delta1Offsets, f1.off, JNI_ABORT);
   if (ok && rc) throw_last(env);
+}
+
+#define BATCH_PARAMS jint numRows, jint nCols, \
+    jlongArray colAddrs, jlongArray colLens, jobjectArray heapCols, jintArray heapOffsets, \
+    jlongArray delta0Addrs, jlongArray delta0Lens, jobjectArray delta0Heap, jintArray delta0Offsets, \
+    jlongArray delta1Addrs, jlongArray delta1Lens, jobjectArray delta1Heap, jintArray delta1Offsets, \
+    jlong deleteAddr, jlong deleteLen, jbyteArray deleteHeap, jint deleteOffset, \
+    jlong statsAddr, jlong statsLen, jbyteArray statsHeap, jint statsOffset, jint statsNCols, jint bucketId, jlong batchId
+#define BATCH_ARGS numRows, nCols, colAddrs, colLens, heapCols, heapOffsets, delta0Addrs, delta0Lens, delta0Heap, delta0Offsets, \
+    delta1Addrs, delta1Lens, delta1Heap, delta1Offsets, deleteAddr, deleteLen, deleteHeap, deleteOffset, \
+    statsAddr, statsLen, statsHeap, statsOffset, statsNCols, bucketId, batchId
+
+JNIEXPORT void JNICALL JFN(batchSubmit)(JNIEnv* env, jobject self, jlong plan, BATCH_PARAMS) {
+  (void)self;
+  do_batch(env, 0, plan, BATCH_ARGS);
+}
+
+/* ---- residency: batches kept in HBM across queries ------------------------------------- */
+/* schemaAddr: nCols x sd_column (type, nullable, table_ordinal, scale, precision: jvm/abi_offsets.txt) */
+JNIEXPORT jlong JNICALL JFN(storeCreate)(JNIEnv* env, jobject self, jint device, jint nCols, jlong schemaAddr) {
+  (void)self;
+  sd_store* s = NULL;
+  if (sd_store_create(device, nCols, (const sd_column*)(intptr_t)schemaAddr, &s)) { throw_last(env); return 0; }
+  return (jlong)(intptr_t)s;
+}
+JNIEXPORT void JNICALL JFN(storePutBatch)(JNIEnv* env, jobject self, jlong store, BATCH_PARAMS) {
+  (void)self;
+  do_batch(env, 1, store, BATCH_ARGS);
+}
+JNIEXPORT void JNICALL JFN(storeDestroy)(JNIEnv* env, jobject self, jlong store) {
+  (void)env; (void)self;
+  sd_store_destroy((sd_store*)(intptr_t)store);
+}
+/* scan the resident batches of `bucketIds` (all buckets when null) with the plan's current literals */
+JNIEXPORT void JNICALL JFN(planScanStore)(JNIEnv* env, jobject self, jlong plan, jlong store, jintArray bucketIds) {
+  (void)self;
+  jint* ids = NULL;
+  jsize n = 0;
+  if (bucketIds != NULL) {
+    n = (*env)->GetArrayLength(env, bucketIds);
+    ids = (*env)->GetIntArrayElements(env, bucketIds, NULL);
+    if (ids == NULL) return;                                 /* OutOfMemoryError is pending */
+  }
+  int rc = sd_plan_scan_store((sd_plan*)(intptr_t)plan, (sd_store*)(intptr_t)store, (const int32_t*)ids, (int32_t)n);
+  if (ids) (*env)->ReleaseIntArrayElements(env, bucketIds, ids, JNI_ABORT);
+  if (rc) throw_last(env);
+}
+
+/* ---- the cross-partition exchange ------------------------------------------------------ */
+/* rank 0 fills a 128-byte id; the caller broadcasts it (a Spark broadcast variable) */
+JNIEXPORT void JNICALL JFN(commUniqueId)(JNIEnv* env, jobject self, jbyteArray out128) {
+  (void)self;
+  uint8_t id[128];
+  if (out128 == NULL || (*env)->GetArrayLength(env, out128) < 128) { throw_msg(env, "java/lang/IllegalArgumentException", "commUniqueId: byte[128]"); return; }
+  if (sd_comm_unique_id(id)) { throw_last(env); return; }
+  (*env)->SetByteArrayRegion(env, out128, 0, 128, (const jbyte*)id);
+}
+JNIEXPORT jlong JNICALL JFN(commCreate)(JNIEnv* env, jobject self, jbyteArray id128, jint rank, jint world, jint device) {
+  (void)self;
+  uint8_t id[128];
+  sd_comm* c = NULL;
+  if (id128 == NULL || (*env)->GetArrayLength(env, id128) < 128) { throw_msg(env, "java/lang/IllegalArgumentException", "commCreate: byte[128]"); return 0; }
+  (*env)->GetByteArrayRegion(env, id128, 0, 128, (jbyte*)id);
+  if ((*env)->ExceptionCheck(env)) return 0;
+  if (sd_comm_create(id, rank, world, device, &c)) { throw_last(env); return 0; }   /* blocks until every rank has joined: no JNI state is held */
+  return (jlong)(intptr_t)c;
+}
+JNIEXPORT void JNICALL JFN(commDestroy)(JNIEnv* env, jobject self, jlong comm) {
+  (void)env; (void)self;
+  sd_comm_destroy((sd_comm*)(intptr_t)comm);
+}
+/* all-gather + merge of this partition's partial result with the other ranks'; planFinish then returns the merged partial rows */
+JNIEXPORT void JNICALL JFN(planExchange)(JNIEnv* env, jobject self, jlong plan, jlong comm) {
+  (void)self;
+  if (sd_plan_exchange((sd_plan*)(intptr_t)plan, (sd_comm*)(intptr_t)comm)) throw_last(env);
+}
+
+/* ---- page-locked host memory: result buffers of planFinish (projected rows arrive by ONE device->host copy at link speed) and
+ *      long-lived staging.  The address is wrapped on the Scala side with Platform / a direct ByteBuffer view. ---------------- */
+JNIEXPORT jlong JNICALL JFN(hostAlloc)(JNIEnv* env, jobject self, jlong bytes) {
+  (void)self;
+  void* p = NULL;
+  if (sd_host_alloc(bytes, &p)) { throw_last(env); return 0; }
+  return (jlong)(intptr_t)p;
+}
+JNIEXPORT void JNICALL JFN(hostFree)(JNIEnv* env, jobject self, jlong addr) {
+  (void)env; (void)self;
+  sd_host_free((void*)(intptr_t)addr);
 }
 
 JNIEXPORT void JNICALL JFN(rowsSubmit)(JNIEnv* env, jobject self, jlong plan, jlong rowsAddr, jlong len, jint nrows) {

@@ -33,4 +33,35 @@ object SnappyGpuNative {
   @native def planMetrics(plan: Long, out: Array[Long]): Unit
   @native def planDestroy(plan: Long): Unit
   @native def finalMerge(planDescAddr: Long, rowsAddr: Long, len: Long, outAddr: Long, cap: Long): Long
+
+  // ---- residency (INTEGRATION.md 4): a server keeps the ColumnBatches of its buckets in HBM across queries --------------
+  /** schemaAddr: nCols x sd_column (layout pinned in jvm/abi_offsets.txt), written by GpuPlanSerializer */
+  @native def storeCreate(device: Int, nCols: Int, schemaAddr: Long): Long
+  /** same buffer conventions as batchSubmit; the batch is resident when the call returns */
+  @native def storePutBatch(store: Long, numRows: Int, nCols: Int,
+      colAddrs: Array[Long], colLens: Array[Long], heapCols: Array[Array[Byte]], heapOffsets: Array[Int],
+      delta0Addrs: Array[Long], delta0Lens: Array[Long], delta0Heap: Array[Array[Byte]], delta0Offsets: Array[Int],
+      delta1Addrs: Array[Long], delta1Lens: Array[Long], delta1Heap: Array[Array[Byte]], delta1Offsets: Array[Int],
+      deleteAddr: Long, deleteLen: Long, deleteHeap: Array[Byte], deleteOffset: Int,
+      statsAddr: Long, statsLen: Long, statsHeap: Array[Byte], statsOffset: Int, statsNCols: Int,
+      bucketId: Int, batchId: Long): Unit
+  @native def storeDestroy(store: Long): Unit
+  /** scan the resident batches of these buckets (null: all) with the literals set by planSetLiterals; a store that has
+    * grown since the plan's last scan is re-scanned incrementally (only the new batches get descriptors) */
+  @native def planScanStore(plan: Long, store: Long, bucketIds: Array[Int]): Unit
+
+  // ---- the exchange between co-located GPU partitions (INTEGRATION.md 4b) ------------------------------------------------
+  /** rank 0 calls this and broadcasts the 128 bytes; every rank passes them to commCreate */
+  @native def commUniqueId(out128: Array[Byte]): Unit
+  /** blocks until all `world` ranks have joined */
+  @native def commCreate(id128: Array[Byte], rank: Int, world: Int, device: Int): Long
+  @native def commDestroy(comm: Long): Unit
+  /** after this partition's scans: all-gather + merge; planFinish then returns the merged partial rows on every rank */
+  @native def planExchange(plan: Long, comm: Long): Unit
+
+  // ---- page-locked host memory --------------------------------------------------------------------------------------------
+  /** for planFinish's output (the projected rows of a scan without aggregate arrive in ONE device->host copy at link speed
+    * when the buffer is page-locked) and for long-lived staging; wrap with Platform.* / UnsafeRow.pointTo(null, addr, size) */
+  @native def hostAlloc(bytes: Long): Long
+  @native def hostFree(addr: Long): Unit
 }

@@ -51,3 +51,17 @@ def test_struct_layout_constants_of_the_scala_serializer():
         assert d[field] == off
     lit = want["sd_literal"][1]
     assert (lit["is_null"], lit["i"], lit["d"], lit["s"], lit["slen"]) == (4, 8, 16, 24, 32)
+
+
+def test_every_scala_native_has_a_jni_function_and_vice_versa():
+    """SnappyGpuNative.scala's @native declarations and snappy_gpu_jni.c's JFN(...) entry points name the same set (a missing
+    one is an UnsatisfiedLinkError at the first call on a box that does have a JVM)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scala = open(os.path.join(root, "jvm/src/main/scala/io/snappydata/gpu/SnappyGpuNative.scala")).read()
+    c = open(os.path.join(root, "jvm/native/snappy_gpu_jni.c")).read()
+    declared = set(re.findall(r"@native\s+def\s+(\w+)", scala))
+    defined = set(re.findall(r"JNICALL\s+JFN\((\w+)\)", c))
+    assert declared == defined, (sorted(declared - defined), sorted(defined - declared))
+    assert {"storeCreate", "storePutBatch", "planScanStore", "commCreate", "planExchange", "hostAlloc"} <= declared

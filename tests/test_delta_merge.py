@@ -88,3 +88,54 @@ def test_errors():
     good = encode_delta(10, np.array([1, 2], dtype=np.int32), np.array([5, 6]), T.INT, np.array([True, False]))
     with pytest.raises(capi.SdError):   # NULL entry for a NOT NULL column
         _merge(T.INT, False, good, encode_delta(10, np.array([3], dtype=np.int32), np.array([1]), T.INT), True, 10)
+
+
+def test_fuzzed_delta_buffers_never_overrun_or_crash():
+    """Corrupted inputs (bit flips, truncation, overwritten header words, spliced-in noise) to sd_delta_merge end in an error or in
+    an output inside the caller's capacity; positions / counts / lengths read from the buffers are validated before use."""
+    from snappydata_b200.column_format import encode_column
+    api = capi.product_api()
+    f = api.lib.sd_delta_merge
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(capi.sd_column), C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    r = np.random.default_rng(9)
+    n_ok = n_err = 0
+    for t in (T.INT, T.DOUBLE, T.STRING, T.BOOLEAN):
+        for nullable in (False, True):
+            n = 2000
+            p_new = np.sort(r.choice(n, 60, replace=False)).astype(np.int32)
+            p_old = np.sort(r.choice(n, 300, replace=False)).astype(np.int32)
+            v_new, v_old = _values(t, r, len(p_new)), _values(t, r, len(p_old))
+            n_new = (r.random(len(p_new)) < 0.2) if nullable else None
+            n_old = (r.random(len(p_old)) < 0.2) if nullable else None
+            new, old = encode_delta(n, p_new, v_new, t, n_new), encode_delta(n, p_old, v_old, t, n_old)
+            full = encode_column(_values(t, r, n), t, (r.random(n) < 0.1) if nullable else None)
+            col = capi.sd_column(int(t), int(nullable), 0, 0, 0)
+            for trial in range(60):
+                a, b, is_delta = bytearray(new), bytearray(old if trial % 3 else full), int(trial % 3 != 0)
+                tgt = a if trial % 2 else b
+                kind = trial % 5
+                if kind == 0:
+                    for _ in range(1 + trial % 4):
+                        i = int(r.integers(0, len(tgt)))
+                        tgt[i] ^= 1 << int(r.integers(0, 8))
+                elif kind == 1:
+                    del tgt[int(r.integers(0, len(tgt))):]
+                elif kind == 2:
+                    i = int(r.integers(0, max(1, len(tgt) - 4)))
+                    tgt[i:i + 4] = int(r.integers(-2**31, 2**31)).to_bytes(4, "little", signed=True)
+                elif kind == 3:
+                    i = int(r.integers(0, len(tgt)))
+                    k = min(len(tgt) - i, int(r.integers(1, 32)))
+                    tgt[i:i + k] = bytes(r.integers(0, 256, k, dtype=np.uint8))
+                cap = len(a) + len(b) + 4096
+                out = C.create_string_buffer(cap + 64)
+                m = C.c_int64()
+                rc = f(C.byref(col), bytes(a), len(a), bytes(b), len(b), is_delta, n, out, cap, C.byref(m))
+                assert out.raw[cap:] == bytes(64)
+                if rc == 0:
+                    assert 0 <= m.value <= cap
+                    n_ok += 1
+                else:
+                    n_err += 1
+    assert n_ok > 50 and n_err > 50

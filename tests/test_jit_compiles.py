@@ -48,6 +48,18 @@ def _plans():
     b.group_by(s2, v)
     b.min(s1).max(s1).count()
     out["strings"] = b.build()
+    b = PlanBuilder()   # 32 grouping keys of mixed types (one NULL bit each), hash table; the plan halves its tile or drops the ring
+    ks = [b.col((T.INT, T.LONG, T.DATE, T.STRING)[i % 4], i, i % 3 == 0) for i in range(32)]
+    v = b.col(T.DOUBLE, 32, True)
+    b.group_by(*ks)
+    b.count().sum(v).max(ks[1])
+    out["keys32"] = b.build()
+    b = PlanBuilder()   # projection of every field width (device row writer's kinds), nullable columns, raw + dictionary strings
+    ts = [T.BOOLEAN, T.BYTE, T.SHORT, T.INT, T.DATE, T.FLOAT, T.DOUBLE, T.LONG, T.TIMESTAMP, T.STRING, T.DECIMAL]
+    cs = [b.col(t, i, i % 2 == 0, scale=2 if t == T.DECIMAL else 0, precision=12 if t == T.DECIMAL else 0) for i, t in enumerate(ts)]
+    b.filter(cs[3].is_null() | (cs[3] > b.lit(T.INT)) & cs[9].startswith(b.lit(T.STRING)))
+    b.project(*cs, cs[3] + cs[2].cast(T.INT), cs[6] * cs[6])
+    out["project_all"] = b.build()
     return out
 
 
@@ -84,7 +96,7 @@ def _compile(source, name):
     return dt
 
 
-@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable", "decimal", "strings"])
+@pytest.mark.parametrize("label", ["c1", "q6", "q1", "hash", "project", "groups_nullable", "decimal", "strings", "keys32", "project_all"])
 def test_every_kernel_variant_compiles_for_sm_100a(label):
     desc = _plans()[label]
     seen = set()
